@@ -1,0 +1,162 @@
+/*
+ * ytb200.h -- C ABI of libytb200.so, the B200 (sm_100a) ray caster that replaces
+ * yt's Cython ImageSampler path.  Plain pointers and sizes only; no torch, no
+ * Python, no C++ types.  Every entry point returns 0 on success and a negative
+ * code on failure; ytb200_last_error() then holds a human-readable message
+ * (thread-local).  There is NO CPU fallback: every call needs a CUDA device.
+ *
+ * Each entry point names the reference interface (paths relative to the yt
+ * checkout) it stands in for.  INTEGRATION.md shows the ctypes binding a yt
+ * maintainer would add in yt/visualization/volume_rendering/utils.py.
+ */
+#ifndef YTB200_H
+#define YTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YTB200_ABI_VERSION 1
+#define YTB200_MAX_FIELDS 6   /* dvs[6]: yt/utilities/lib/image_samplers.pyx:384,474 */
+#define YTB200_MAX_TABLES 6   /* fits[6]: yt/utilities/lib/image_samplers.pyx:425-430 */
+
+/* sampler kinds == the three ImageSampler subclasses named by the north star */
+enum {
+    YTB200_PROJECTION = 0,              /* ProjectionSampler             image_samplers.pyx:327-343 */
+    YTB200_INTERPOLATED_PROJECTION = 1, /* InterpolatedProjectionSampler image_samplers.pyx:346-402 */
+    YTB200_VOLUME_RENDER = 2            /* VolumeRenderSampler           image_samplers.pyx:405-494 */
+};
+
+/* lens modes == the (extent_function, vector_function) pairs of image_samplers.pyx:85-103 */
+enum {
+    YTB200_LENS_PLANE_PARALLEL = 0, /* lenses.pyx:22-55 + 179-192 */
+    YTB200_LENS_PERSPECTIVE = 1,    /* lenses.pyx:60-161 + 196-207 (needs camera_data) */
+    YTB200_LENS_GENERIC = 2         /* lenses.pyx:169-175 + 196-207 (per-pixel rays, full image) */
+};
+
+/* data centring of a brick set */
+enum { YTB200_CELL_CENTRED = 0, YTB200_VERTEX_CENTRED = 1 };
+/* device storage of brick data */
+enum { YTB200_STORE_F32 = 0, YTB200_STORE_F64 = 1 };
+/* arithmetic mode: FAST = fp64 traversal + fp32 sampling/compositing (the product path);
+ * EXACT = everything fp64 in the reference's evaluation order (needs STORE_F64). */
+enum { YTB200_PREC_FAST = 0, YTB200_PREC_EXACT = 1 };
+
+typedef struct ytb200_ctx ytb200_ctx;           /* one device + one stream */
+typedef struct ytb200_brickset ytb200_brickset; /* device-resident PartitionedGrid list */
+typedef struct ytb200_tf ytb200_tf;             /* device-resident FieldInterpolationTables */
+typedef struct ytb200_frame ytb200_frame;       /* device image + z-buffer + rays of one sampler */
+
+/* ImageSampler.__init__ arguments (image_samplers.pyx:59-130), flattened. */
+typedef struct ytb200_camera {
+    int32_t lens;            /* YTB200_LENS_* */
+    int32_t nx, ny;          /* image.shape[0], image.shape[1] */
+    double vp_pos[12];       /* plane-parallel: lens.py:89-94 packing (inv_mat.ravel("F"), back_center) */
+    double vp_dir[3];        /* plane-parallel: box_vectors[2] */
+    const double *vp_pos_px; /* other lenses: HOST pointer, C-order (nx, ny, 3) */
+    const double *vp_dir_px; /* other lenses: HOST pointer, C-order (nx, ny, 3) */
+    double center[3];
+    double bounds[4];
+    double x_vec[3], y_vec[3];
+    double width[3];
+    int32_t has_camera_data; /* kwargs["camera_data"] given (camera.py:278-280) */
+    double camera_data[15];  /* rows: position, width, east, north, normal */
+} ytb200_camera;
+
+/* Per-cast statistics, all measured on the device. */
+typedef struct ytb200_stats {
+    double kernel_ms;    /* CUDA-event time of the cast kernels on the context stream (0 if not timed) */
+    int64_t n_launches;  /* kernels launched by the call */
+    int64_t n_cells;     /* cells handed to sample() (only filled by ytb200_frame_count) */
+    int64_t n_samples;   /* n_cells * n_samples for the sampling kinds, n_cells for PROJECTION */
+} ytb200_stats;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int ytb200_abi_version(void);
+const char *ytb200_last_error(void);
+int ytb200_device_count(int *count);
+
+/* ---- context: device + stream.  `stream` is a cudaStream_t (or NULL to create one). --------
+ * Replaces the OpenMP parallel region / num_threads of cast_through_kdtree (image_samplers.pyx:172). */
+int ytb200_ctx_create(int device, void *stream, ytb200_ctx **out);
+int ytb200_ctx_destroy(ytb200_ctx *ctx);
+int ytb200_ctx_synchronize(ytb200_ctx *ctx);
+void *ytb200_ctx_stream(ytb200_ctx *ctx);
+int ytb200_ctx_sm_count(ytb200_ctx *ctx);
+
+/* ---- bricks: PartitionedGrid.__cinit__ (partitioned_grid.pyx:28-63) ------------------------ */
+int ytb200_bricks_create(ytb200_ctx *ctx, int64_t n_bricks, int n_fields, int centring, int storage,
+                         ytb200_brickset **out);
+/* data[f] are HOST fp64 C-contiguous arrays of shape dims (+1 per axis when vertex-centred);
+ * mask is a HOST u8 array of shape dims or NULL for "all ones". Converts to `storage` and uploads. */
+int ytb200_brick_upload(ytb200_brickset *set, int64_t index, const int64_t dims[3], const double left_edge[3],
+                        const double right_edge[3], const double *const *data, const uint8_t *mask);
+/* Same, but data[f] / mask are DEVICE pointers already in the set's storage type; not copied, not owned. */
+int ytb200_brick_attach(ytb200_brickset *set, int64_t index, const int64_t dims[3], const double left_edge[3],
+                        const double right_edge[3], const void *const *dev_data, const uint8_t *dev_mask);
+/* Must be called after the last upload/attach and before the first cast (uploads the brick table). */
+int ytb200_bricks_commit(ytb200_brickset *set);
+int ytb200_bricks_destroy(ytb200_brickset *set);
+/* Device pointers of brick `index` (data_out[n_fields], *mask_out may be NULL = all ones), so that a
+ * brick uploaded once can be attached to other sets without a copy (bricks are cached across frames
+ * like node.data in amr_kdtree.py:326-327). */
+int ytb200_brick_device_ptrs(const ytb200_brickset *set, int64_t index, void **data_out, void **mask_out);
+int64_t ytb200_bricks_device_bytes(const ytb200_brickset *set);
+
+/* ---- transfer function: VolumeRenderSampler.__cinit__ + FIT_initialize_table
+ * (image_samplers.pyx:405-447, field_interpolation_tables.pxd:44-61) ------------------------- */
+int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nbins, const double *const *y,
+                     const double *bounds /* n_tables x 2 */, const int32_t field_ids[6],
+                     const int32_t weight_field_ids[6], const int32_t weight_table_ids[6],
+                     const int32_t field_table_ids[6], int grey_opacity, ytb200_tf **out);
+int ytb200_tf_destroy(ytb200_tf *tf);
+
+/* ---- frame: the image / z-buffer / ray set one ImageSampler instance owns ------------------- */
+int ytb200_frame_create(ytb200_ctx *ctx, const ytb200_camera *cam, ytb200_frame **out);
+int ytb200_frame_destroy(ytb200_frame *f);
+/* H2D of the caller's (nx,ny,4) fp64 image (initial colours, image_samplers.pyx:183-184) and (nx,ny)
+ * fp64 z-buffer (NULL = ones, image_samplers.pyx:78-80).  Asynchronous on the context stream. */
+int ytb200_frame_upload(ytb200_frame *f, const double *image_host, const double *zbuffer_host);
+/* Zero the device image and set the z-buffer to ones without touching the host. */
+int ytb200_frame_clear(ytb200_frame *f);
+/* Cast `n_order` bricks of `set`, in the given order (the order AMRKDTree.traverse yields them,
+ * render_source.py:594-597), into the frame's device image.  Asynchronous.
+ * == for b in order: sampler(brick_b)  (image_samplers.pyx:132-197, grid_traversal.pyx:26-140). */
+int ytb200_frame_cast(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
+                      int64_t n_order, const ytb200_tf *tf, int n_samples, int precision, ytb200_stats *stats);
+/* Same traversal, but only counts cells/samples (exact denominator of the Gsamples/s metric). */
+int ytb200_frame_count(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
+                       int64_t n_order, int n_samples, ytb200_stats *stats);
+/* D2H of the image into the caller's fp64 (nx,ny,4) array (sampler.aimage); synchronises. */
+int ytb200_frame_download(ytb200_frame *f, double *image_host);
+/* Device pointer of the fp64 (nx,ny,4) image, for zero-copy consumers (torch, NCCL). */
+void *ytb200_frame_device_image(ytb200_frame *f);
+
+/* ---- partial images for object-space multi-GPU rendering (replaces reduce_tree_images,
+ * amr_kdtree.py:297-323 / amr_kdtools.py:6-50).  A partial is the per-channel affine map
+ * C -> A + B*C of all samples a rank owns, stored as fp64 (nx,ny,8): A[4],B[4]. -- */
+int ytb200_frame_cast_partial(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
+                              int64_t n_order, const ytb200_tf *tf, int n_samples, int precision,
+                              double *partial_dev /* device (nx,ny,8) */, ytb200_stats *stats);
+/* out = later o earlier on n_pixels pixels: A = A2 + B2*A1, B = B2*B1.  `out` may alias either input. */
+int ytb200_partial_compose(ytb200_ctx *ctx, const double *earlier_dev, const double *later_dev,
+                           double *out_dev, int64_t n_pixels);
+/* image = A + B * image on n_pixels pixels (applies the composed map to the initial colours). */
+int ytb200_partial_apply(ytb200_ctx *ctx, const double *partial_dev, double *image_dev, int64_t n_pixels);
+
+/* ---- one-shot convenience: everything above for host buffers --------------------------------
+ * upload image+zbuffer -> cast -> download.  This is the call the e2e benchmark times. */
+int ytb200_render(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order, int64_t n_order,
+                  const ytb200_tf *tf, int n_samples, int precision, const double *zbuffer_host,
+                  double *image_host_inout, ytb200_stats *stats);
+
+/* Pinned host memory for the image / z-buffer (cudaHostAlloc). */
+int ytb200_host_alloc(int64_t bytes, void **out);
+int ytb200_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YTB200_H */

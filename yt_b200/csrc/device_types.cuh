@@ -1,0 +1,75 @@
+// Device-side data layout shared by the kernels and the C ABI (libytb200.so).
+//
+// Naming follows the reference's domain: a *brick* is one PartitionedGrid /
+// VolumeContainer (yt/utilities/lib/volume_container.pxd:13-33), a *frame* is the
+// image + z-buffer + ray set of one ImageSampler (image_samplers.pyx:59-130), a
+// *table* is one FieldInterpolationTable (field_interpolation_tables.pxd:27-39).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define YTB_MAX_FIELDS 6
+#define YTB_MAX_TABLES 6
+
+namespace ytb {
+
+// One brick as the kernels see it.  Geometry stays fp64 (the DDA is fp64); `data`
+// points at fp32 or fp64 arrays depending on the owning set's storage.
+struct DevBrick {
+    double le[3], re[3], dds[3], idds[3];
+    int dims[3];
+    int n_fields;
+    const void *data[YTB_MAX_FIELDS];
+    const unsigned char *mask;  // nullptr == all ones
+};
+
+// Ray description.  Plane-parallel rays are generated in the kernel from vp_pos/vp_dir
+// exactly as lenses.pyx:179-192 does; every other lens reads per-pixel fp64 arrays.
+struct DevCamera {
+    int lens, nx, ny;
+    double vp_pos[12];
+    double vp_dir[3];
+    double width[3];
+    const double *pos_px;  // device (nx,ny,3) or nullptr
+    const double *dir_px;  // device (nx,ny,3) or nullptr
+    // conservative pixel-footprint helpers (ours, not the reference's bbox: SURVEY.md H5/H6/H12)
+    double ext_rows[6];    // plane-parallel: rows of inv([east north dir]) giving (px,py) of a point
+    double ext_origin[3];  // plane-parallel: back_center; perspective: camera position
+    double persp[15];      // perspective: camera_data rows (position,width,east,north,normal)
+    int ext_mode;          // 0 full image, 1 plane-parallel projection, 2 pinhole projection
+};
+
+// Transfer-function description.  Table payloads live in global memory and are staged
+// into shared memory by each CTA.
+struct DevTF {
+    int n_fits, grey, colour_fast;  // colour_fast: ColorTransferFunction layout (see tf_create)
+    int nbins[YTB_MAX_TABLES];
+    int offset[YTB_MAX_TABLES];     // element offset of table i inside the payload arrays
+    int field_id[YTB_MAX_TABLES], weight_field_id[YTB_MAX_TABLES], weight_table_id[YTB_MAX_TABLES];
+    int field_table_id[6];
+    int total_bins;
+    // fp64 (EXACT): values / d0 / dy exactly as FIT_initialize_table builds them
+    double b0[YTB_MAX_TABLES], b1[YTB_MAX_TABLES], idbin[YTB_MAX_TABLES];
+    const double *values, *d0, *dy;
+    // fp32 (FAST): (value, next-value - value) pairs; bounds split hi/lo so x-b0 keeps fp64-ish accuracy
+    float b0_hi[YTB_MAX_TABLES], b0_lo[YTB_MAX_TABLES], b1_f[YTB_MAX_TABLES], idbin_f[YTB_MAX_TABLES];
+    const float2 *pairs;
+    // colour_fast payload: per bin (r,g,b,a) values and (dr,dg,db,da) increments
+    const float4 *colour;  // 2*nbins float4: [2*bin] = values, [2*bin+1] = increments
+};
+
+struct CastParams {
+    DevCamera cam;
+    const DevBrick *bricks;
+    const int *order;       // brick indices in the reference's traversal order
+    const int4 *extent;     // per order entry: [i0,i1) x [j0,j1) pixel footprint
+    int n_order;
+    int n_samples;
+    double *image;          // (nx,ny,4) fp64, in/out
+    const double *zbuffer;  // (nx,ny) fp64 or nullptr (== ones)
+    double *partial;        // (nx,ny,8) fp64 affine map output, or nullptr
+    DevTF tf;
+    unsigned long long *counters;  // [0] cells handed to sample()
+};
+
+}  // namespace ytb

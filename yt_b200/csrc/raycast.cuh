@@ -1,0 +1,333 @@
+// Ray/brick traversal and the three cell samplers, as device functions.
+//
+// What is reproduced (bit-for-bit in the fp64 parts) and where it comes from:
+//   * ray/box entry, start cell, Amanatides-Woo stepping, tie rule, max_t clamp
+//       -- walk_volume, yt/utilities/lib/grid_traversal.pyx:26-140
+//   * ProjectionSampler / InterpolatedProjectionSampler / VolumeRenderSampler cell bodies
+//       -- yt/utilities/lib/image_samplers.pyx:327-343, 372-402, 453-487
+//   * trilinear vertex interpolation -- fixed_interpolator.cpp:34-52
+//   * transfer-function lookup + compositing -- field_interpolation_tables.pxd:66-110
+//
+// How it is done here is ours: one thread per ray, fp64 DDA written with explicit
+// round-to-nearest intrinsics (so nvcc never contracts a*b+c into an FMA and every
+// discrete decision -- entry face, start cell, tie -- matches the reference on the same
+// inputs), the 8 cell corners cached in registers for the n_samples samples of a cell,
+// fp32 sampling/compositing in FAST mode, tables in shared memory.
+#pragma once
+#include "device_types.cuh"
+
+namespace ytb {
+
+// ---- non-contracting fp64 helpers ----------------------------------------------------------
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+struct BrickGeom {
+    double le[3], re[3], dds[3], idds[3];
+    int dims[3];
+};
+
+__device__ __forceinline__ void load_geom(BrickGeom &g, const DevBrick *b)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        g.le[i] = b->le[i]; g.re[i] = b->re[i]; g.dds[i] = b->dds[i]; g.idds[i] = b->idds[i];
+        g.dims[i] = b->dims[i];
+    }
+}
+
+// Snap a face coordinate onto the brick edge when within 1e-10 of a cell (grid_traversal.pyx:67-74).
+__device__ __forceinline__ double snap_edge(double v, double le, double re, double tol)
+{
+    if (fabs(dsub(v, le)) < tol) return le;
+    if (fabs(dsub(v, re)) < tol) return re;
+    return v;
+}
+
+// walk_volume.  `S::cell(enter_t, exit_t, ix, iy, iz)` is the sampler_function.
+// Returns the number of cells visited ("hit").
+template <class S>
+__device__ __forceinline__ int walk_brick(const BrickGeom &g, const double (&vp)[3], const double (&vd)[3],
+                                          double max_t, S &smp)
+{
+    if (max_t > 1.0) max_t = 1.0;
+    double intersect_t = 1.1;
+    int direction = -1;
+    if (g.le[0] <= vp[0] && vp[0] < g.re[0] && g.le[1] <= vp[1] && vp[1] < g.re[1] &&
+        g.le[2] <= vp[2] && vp[2] < g.re[2]) {
+        intersect_t = 0.0;
+        direction = 3;
+    }
+    int step[3];
+    double iv[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        iv[i] = 0.0;
+        if (vd[i] < 0.0) step[i] = -1;
+        else if (vd[i] == 0.0) { step[i] = 0; continue; }
+        else step[i] = 1;
+        iv[i] = ddiv(1.0, vd[i]);
+        if (direction == 3) continue;
+        const int x = (i + 1) % 3, y = (i + 2) % 3;
+        const double face = step[i] > 0 ? g.le[i] : g.re[i];
+        const double tl = dmul(dsub(face, vp[i]), iv[i]);
+        double tx = dadd(vp[x], dmul(tl, vd[x]));
+        double ty = dadd(vp[y], dmul(tl, vd[y]));
+        tx = snap_edge(tx, g.le[x], g.re[x], dmul(1e-10, g.dds[x]));
+        ty = snap_edge(ty, g.le[y], g.re[y], dmul(1e-10, g.dds[y]));
+        if (g.le[x] <= tx && tx <= g.re[x] && g.le[y] <= ty && ty <= g.re[y] && 0.0 <= tl && tl < intersect_t) {
+            direction = i;
+            intersect_t = tl;
+        }
+    }
+    if (!((0.0 <= intersect_t) && (intersect_t < max_t))) return 0;
+    int cur[3];
+    double tmax[3], tdelta[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        tdelta[i] = dmul(dmul((double)step[i], iv[i]), g.dds[i]);
+        if (i == direction && step[i] > 0) cur[i] = 0;
+        else if (i == direction && step[i] < 0) cur[i] = g.dims[i] - 1;
+        else {
+            const double pos = dadd(dmul(intersect_t, vd[i]), vp[i]);
+            double c = dmul(dsub(pos, g.le[i]), g.idds[i]);
+            if (-1.0 < c && c < 0.0 && step[i] > 0) c = 0.0;
+            else if ((double)(g.dims[i] - 1) < c && c < (double)g.dims[i] && step[i] < 0) c = (double)(g.dims[i] - 1);
+            cur[i] = (int)floor(c);
+        }
+        double edge = 0.0;
+        if (step[i] > 0) edge = dadd(dmul((double)(cur[i] + 1), g.dds[i]), g.le[i]);
+        else if (step[i] < 0) edge = dadd(dmul((double)cur[i], g.dds[i]), g.le[i]);
+        tmax[i] = dmul(dsub(edge, vp[i]), iv[i]);
+        if (step[i] == 0) tmax[i] = 1e60;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if (cur[i] == g.dims[i] && step[i] >= 0) return 0;
+        if (cur[i] == -1 && step[i] <= -1) return 0;
+    }
+    double enter_t = intersect_t;
+    int hit = 0;
+    while (true) {
+        hit++;
+        int i;
+        if (tmax[0] < tmax[1]) i = (tmax[0] < tmax[2]) ? 0 : 2;
+        else                   i = (tmax[1] < tmax[2]) ? 1 : 2;
+        const double tm = (i == 0) ? tmax[0] : ((i == 1) ? tmax[1] : tmax[2]);
+        const double exit_t = tm < max_t ? tm : max_t;
+        smp.cell(enter_t, exit_t, cur[0], cur[1], cur[2]);
+        enter_t = tm;
+        bool out;
+        if (i == 0)      { cur[0] += step[0]; tmax[0] = dadd(tmax[0], tdelta[0]); out = cur[0] < 0 || cur[0] >= g.dims[0]; }
+        else if (i == 1) { cur[1] += step[1]; tmax[1] = dadd(tmax[1], tdelta[1]); out = cur[1] < 0 || cur[1] >= g.dims[1]; }
+        else             { cur[2] += step[2]; tmax[2] = dadd(tmax[2], tdelta[2]); out = cur[2] < 0 || cur[2] >= g.dims[2]; }
+        if (out || enter_t >= max_t) break;
+    }
+    return hit;
+}
+
+// ---- small helpers ----------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ R pick6(const R (&a)[6], int idx)
+{
+    R r = a[0];
+    if (idx == 1) r = a[1];
+    if (idx == 2) r = a[2];
+    if (idx == 3) r = a[3];
+    if (idx == 4) r = a[4];
+    if (idx == 5) r = a[5];
+    return r;
+}
+
+// std::isnormal for fp64 (field_interpolation_tables.pxd:71).
+__device__ __forceinline__ bool is_normal64(double x)
+{
+    const double a = fabs(x);
+    return a >= 2.2250738585072014e-308 && a <= 1.7976931348623157e308;  // false for NaN/0/subnormal/inf
+}
+
+// ---- EXACT (fp64) pieces: reference evaluation order, no contraction -----------------------------
+__device__ __forceinline__ double offset_interpolate64(const double *d, int sx, int sy, const double (&dp)[3])
+{
+    double dv = dsub(1.0, dp[2]);
+    double v0 = dadd(dmul(dv, d[0]),       dmul(dp[2], d[1]));
+    double v1 = dadd(dmul(dv, d[sy]),      dmul(dp[2], d[sy + 1]));
+    double v2 = dadd(dmul(dv, d[sx]),      dmul(dp[2], d[sx + 1]));
+    double v3 = dadd(dmul(dv, d[sx + sy]), dmul(dp[2], d[sx + sy + 1]));
+    dv = dsub(1.0, dp[1]);
+    v0 = dadd(dmul(dv, v0), dmul(dp[1], v1));
+    v1 = dadd(dmul(dv, v2), dmul(dp[1], v3));
+    dv = dsub(1.0, dp[0]);
+    return dadd(dmul(dv, v0), dmul(dp[0], v1));
+}
+
+struct TFShared64 {  // shared-memory views of the fp64 tables
+    const double *values, *d0, *dy;
+};
+
+__device__ __forceinline__ double fit_get_value64(const DevTF &tf, const TFShared64 &t, int i, const double (&dvs)[6])
+{
+    const double x = pick6(dvs, tf.field_id[i]);
+    if (x >= tf.b1[i] || x <= tf.b0[i]) return 0.0;
+    if (!is_normal64(x)) return 0.0;
+    int bin = (int)dmul(dsub(x, tf.b0[i]), tf.idbin[i]);
+    bin = max(0, min(bin, tf.nbins[i] - 2));
+    const int o = tf.offset[i] + bin;
+    const double dd = dsub(x, t.d0[o]);
+    double out = dadd(t.values[o], dmul(dd, t.dy[o]));
+    const int wfi = tf.weight_field_id[i];
+    if (wfi != -1) out = dmul(out, pick6(dvs, wfi));
+    return out;
+}
+
+// FIT_eval_transfer (field_interpolation_tables.pxd:85-110).  B[] (transmittance) is only
+// maintained when PARTIAL (multi-GPU affine partials).
+template <bool PARTIAL>
+__device__ __forceinline__ void eval_transfer64(const DevTF &tf, const TFShared64 &t, double dt,
+                                                const double (&dvs)[6], double (&rgba)[4], double (&B)[4])
+{
+    double ist[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) ist[i] = (i < tf.n_fits) ? fit_get_value64(tf, t, i, dvs) : 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        if (i < tf.n_fits) {
+            const int fid = tf.weight_table_id[i];
+            if (fid != -1) ist[i] = dmul(ist[i], pick6(ist, fid));
+        }
+    }
+    if (tf.grey) {
+        const double ta = fmax(dsub(1.0, dmul(dt, pick6(ist, tf.field_table_id[3]))), 0.0);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const double tc = pick6(ist, tf.field_table_id[c]);
+            rgba[c] = dadd(dmul(dt, tc), dmul(ta, rgba[c]));
+            if (PARTIAL) B[c] = dmul(B[c], ta);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double tc = pick6(ist, tf.field_table_id[c]);
+            const double ta = fmax(dsub(1.0, dmul(dt, tc)), 0.0);
+            rgba[c] = dadd(dmul(dt, tc), dmul(ta, rgba[c]));
+            if (PARTIAL) B[c] = dmul(B[c], ta);
+        }
+    }
+}
+
+// ---- FAST (fp32) pieces ---------------------------------------------------------------------------
+struct Corners {
+    float c000, dz00, c010, dz01, c100, dz10, c110, dz11;  // low-z value and z-increment of the 4 z-edges
+};
+
+template <typename T>
+__device__ __forceinline__ void load_corners(Corners &c, const T *d, int sx, int sy)
+{
+    const float a0 = (float)__ldg(d), a1 = (float)__ldg(d + 1);
+    const float b0 = (float)__ldg(d + sy), b1 = (float)__ldg(d + sy + 1);
+    const float e0 = (float)__ldg(d + sx), e1 = (float)__ldg(d + sx + 1);
+    const float f0 = (float)__ldg(d + sx + sy), f1 = (float)__ldg(d + sx + sy + 1);
+    c.c000 = a0; c.dz00 = a1 - a0;
+    c.c010 = b0; c.dz01 = b1 - b0;
+    c.c100 = e0; c.dz10 = e1 - e0;
+    c.c110 = f0; c.dz11 = f1 - f0;
+}
+
+__device__ __forceinline__ float trilinear(const Corners &c, float x, float y, float z)
+{
+    const float v00 = fmaf(z, c.dz00, c.c000);
+    const float v01 = fmaf(z, c.dz01, c.c010);
+    const float v10 = fmaf(z, c.dz10, c.c100);
+    const float v11 = fmaf(z, c.dz11, c.c110);
+    const float v0 = fmaf(y, v01 - v00, v00);
+    const float v1 = fmaf(y, v11 - v10, v10);
+    return fmaf(x, v1 - v0, v0);
+}
+
+// One table lookup in fp32.  (x - b0) is formed with b0 split hi/lo so the bin coordinate keeps
+// ~1e-7 relative accuracy even when |b0| >> (b1 - b0) (log fields).  Zero, NaN, inf and
+// out-of-bounds values give 0 like FIT_get_value (field_interpolation_tables.pxd:70-71).
+__device__ __forceinline__ float fit_get_value32(const DevTF &tf, const float2 *pairs, int i, const float (&dvs)[6])
+{
+    const float x = pick6(dvs, tf.field_id[i]);
+    const float u = (x - tf.b0_hi[i]) - tf.b0_lo[i];
+    if (!(u > 0.f) || !(x < tf.b1_f[i]) || x == 0.f) return 0.f;
+    const float fb = u * tf.idbin_f[i];
+    int bin = (int)fb;
+    bin = max(0, min(bin, tf.nbins[i] - 2));
+    const float2 p = pairs[tf.offset[i] + bin];
+    float out = fmaf(fb - (float)bin, p.y, p.x);
+    const int wfi = tf.weight_field_id[i];
+    if (wfi != -1) out *= pick6(dvs, wfi);
+    return out;
+}
+
+template <bool PARTIAL>
+__device__ __forceinline__ void eval_transfer32(const DevTF &tf, const float2 *pairs, float dt,
+                                                const float (&dvs)[6], float (&rgba)[4], float (&B)[4])
+{
+    float ist[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) ist[i] = (i < tf.n_fits) ? fit_get_value32(tf, pairs, i, dvs) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        if (i < tf.n_fits) {
+            const int fid = tf.weight_table_id[i];
+            if (fid != -1) ist[i] *= pick6(ist, fid);
+        }
+    }
+    if (tf.grey) {
+        const float ta = fmaxf(1.f - dt * pick6(ist, tf.field_table_id[3]), 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            rgba[c] = fmaf(ta, rgba[c], dt * pick6(ist, tf.field_table_id[c]));
+            if (PARTIAL) B[c] *= ta;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float t = dt * pick6(ist, tf.field_table_id[c]);
+            const float ta = fmaxf(1.f - t, 0.f);
+            rgba[c] = fmaf(ta, rgba[c], t);
+            if (PARTIAL) B[c] *= ta;
+        }
+    }
+}
+
+// ColorTransferFunction fast path: 4 tables on field 0 with common bounds/nbins, RGB weighted by
+// the alpha table (transfer_functions.py:385-406).  One bin computation, two 16-byte table reads.
+template <bool PARTIAL, bool GREY>
+__device__ __forceinline__ void eval_colour32(const float4 *tab, float b0_hi, float b0_lo, float b1, float idbin,
+                                              int nbins_m2, float dt, float x, float (&rgba)[4], float (&B)[4])
+{
+    const float u = (x - b0_hi) - b0_lo;
+    if (!(u > 0.f) || !(x < b1) || x == 0.f) return;  // all tables 0 -> identity map
+    const float fb = u * idbin;
+    int bin = (int)fb;
+    bin = max(0, min(bin, nbins_m2));
+    const float fr = fb - (float)bin;
+    const float4 v = tab[2 * bin], d = tab[2 * bin + 1];
+    const float ta_ = fmaf(fr, d.w, v.w);
+    const float tr = fmaf(fr, d.x, v.x) * ta_;
+    const float tg = fmaf(fr, d.y, v.y) * ta_;
+    const float tb = fmaf(fr, d.z, v.z) * ta_;
+    if (GREY) {
+        const float ta = fmaxf(1.f - dt * ta_, 0.f);
+        rgba[0] = fmaf(ta, rgba[0], dt * tr);
+        rgba[1] = fmaf(ta, rgba[1], dt * tg);
+        rgba[2] = fmaf(ta, rgba[2], dt * tb);
+        rgba[3] = fmaf(ta, rgba[3], dt * ta_);
+        if (PARTIAL) { B[0] *= ta; B[1] *= ta; B[2] *= ta; B[3] *= ta; }
+    } else {
+        const float t0 = dt * tr, t1 = dt * tg, t2 = dt * tb;
+        const float a0 = fmaxf(1.f - t0, 0.f), a1 = fmaxf(1.f - t1, 0.f), a2 = fmaxf(1.f - t2, 0.f);
+        rgba[0] = fmaf(a0, rgba[0], t0);
+        rgba[1] = fmaf(a1, rgba[1], t1);
+        rgba[2] = fmaf(a2, rgba[2], t2);
+        if (PARTIAL) { B[0] *= a0; B[1] *= a1; B[2] *= a2; }
+    }
+}
+
+}  // namespace ytb

@@ -1,0 +1,744 @@
+// libytb200.so -- C ABI (include/ytb200.h) over the cast kernels.  Host side only does what
+// the reference's Cython glue does: argument marshalling, table initialisation, launches.
+// No CPU compute path exists: every call needs a CUDA device and fails loudly otherwise.
+#include "../../include/ytb200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cast_kernels.cuh"
+
+using namespace ytb;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(-100 - (int)e_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+enum { E_ARG = -1, E_STATE = -2, E_UNSUPPORTED = -3 };
+
+// ------------------------------------------------------------------------------------------------
+// objects
+// ------------------------------------------------------------------------------------------------
+struct ytb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    unsigned long long *counters = nullptr;  // device
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct ytb200_brickset {
+    ytb200_ctx *ctx = nullptr;
+    int64_t n = 0;
+    int n_fields = 0, centring = 0, storage = 0;
+    std::vector<DevBrick> host;
+    std::vector<void *> owned;
+    DevBrick *dev = nullptr;
+    bool committed = false;
+    bool any_mask = false;
+    int64_t bytes = 0;
+};
+
+struct ytb200_tf {
+    ytb200_ctx *ctx = nullptr;
+    DevTF d{};
+    std::vector<void *> owned;
+};
+
+struct ytb200_frame {
+    ytb200_ctx *ctx = nullptr;
+    DevCamera cam{};
+    double *image = nullptr, *zbuffer = nullptr;
+    double *pos_px = nullptr, *dir_px = nullptr;
+    int *order_dev = nullptr;
+    int4 *extent_dev = nullptr;
+    int64_t order_cap = 0;
+    std::vector<int> order_host;
+    const ytb200_brickset *order_set = nullptr;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// library / context
+// ------------------------------------------------------------------------------------------------
+extern "C" int ytb200_abi_version(void) { return YTB200_ABI_VERSION; }
+extern "C" const char *ytb200_last_error(void) { return g_err.c_str(); }
+
+extern "C" int ytb200_device_count(int *count)
+{
+    if (!count) return fail(E_ARG, "count is NULL");
+    CK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+extern "C" int ytb200_ctx_create(int device, void *stream, ytb200_ctx **out)
+{
+    if (!out) return fail(E_ARG, "out is NULL");
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (n == 0) return fail(E_STATE, "no CUDA device: libytb200 has no CPU fallback");
+    if (device < 0 || device >= n) return fail(E_ARG, "device %d out of range (0..%d)", device, n - 1);
+    DeviceGuard g(device);
+    auto *c = new ytb200_ctx;
+    c->device = device;
+    if (stream) c->stream = (cudaStream_t)stream;
+    else { CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaMalloc(&c->counters, 8 * sizeof(unsigned long long)));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    *out = c;
+    return 0;
+}
+
+extern "C" int ytb200_ctx_destroy(ytb200_ctx *c)
+{
+    if (!c) return 0;
+    DeviceGuard g(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->counters);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int ytb200_ctx_synchronize(ytb200_ctx *c)
+{
+    if (!c) return fail(E_ARG, "ctx is NULL");
+    DeviceGuard g(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" void *ytb200_ctx_stream(ytb200_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int ytb200_ctx_sm_count(ytb200_ctx *c) { return c ? c->sm_count : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// bricks
+// ------------------------------------------------------------------------------------------------
+extern "C" int ytb200_bricks_create(ytb200_ctx *ctx, int64_t n_bricks, int n_fields, int centring, int storage,
+                                    ytb200_brickset **out)
+{
+    if (!ctx || !out) return fail(E_ARG, "NULL argument");
+    if (n_bricks < 0 || n_bricks > 0x7fffffff) return fail(E_ARG, "bad brick count %lld", (long long)n_bricks);
+    if (n_fields < 1 || n_fields > YTB200_MAX_FIELDS) return fail(E_ARG, "n_fields must be 1..6, got %d", n_fields);
+    if (centring != YTB200_CELL_CENTRED && centring != YTB200_VERTEX_CENTRED) return fail(E_ARG, "bad centring");
+    if (storage != YTB200_STORE_F32 && storage != YTB200_STORE_F64) return fail(E_ARG, "bad storage");
+    auto *s = new ytb200_brickset;
+    s->ctx = ctx; s->n = n_bricks; s->n_fields = n_fields; s->centring = centring; s->storage = storage;
+    s->host.resize((size_t)n_bricks);
+    memset(s->host.data(), 0, sizeof(DevBrick) * (size_t)n_bricks);
+    *out = s;
+    return 0;
+}
+
+static int fill_geometry(ytb200_brickset *s, int64_t index, const int64_t dims[3], const double le[3], const double re[3])
+{
+    if (!s) return fail(E_ARG, "set is NULL");
+    if (index < 0 || index >= s->n) return fail(E_ARG, "brick index %lld out of range", (long long)index);
+    DevBrick &b = s->host[(size_t)index];
+    for (int i = 0; i < 3; i++) {
+        if (dims[i] < 1 || dims[i] > 0x7ffffff0) return fail(E_ARG, "bad dims[%d]=%lld", i, (long long)dims[i]);
+        b.le[i] = le[i]; b.re[i] = re[i]; b.dims[i] = (int)dims[i];
+        b.dds[i] = (b.re[i] - b.le[i]) / (double)dims[i];  // partitioned_grid.pyx:51-52
+        b.idds[i] = 1.0 / b.dds[i];
+    }
+    b.n_fields = s->n_fields;
+    s->committed = false;
+    return 0;
+}
+
+extern "C" int ytb200_brick_upload(ytb200_brickset *s, int64_t index, const int64_t dims[3], const double le[3],
+                                   const double re[3], const double *const *data, const uint8_t *mask)
+{
+    if (!s || !dims || !le || !re || !data) return fail(E_ARG, "NULL argument");
+    int rc = fill_geometry(s, index, dims, le, re);
+    if (rc) return rc;
+    DeviceGuard g(s->ctx->device);
+    cudaStream_t st = s->ctx->stream;
+    const int c = s->centring == YTB200_VERTEX_CENTRED ? 1 : 0;
+    const size_t nelem = (size_t)(dims[0] + c) * (size_t)(dims[1] + c) * (size_t)(dims[2] + c);
+    const size_t ncell = (size_t)dims[0] * (size_t)dims[1] * (size_t)dims[2];
+    DevBrick &b = s->host[(size_t)index];
+    const size_t chunk = (size_t)1 << 24;  // 16 Mi elements = 128 MiB fp64 staging
+    double *stage = nullptr;
+    if (s->storage == YTB200_STORE_F32) CK(cudaMalloc(&stage, sizeof(double) * (nelem < chunk ? nelem : chunk)));
+    for (int f = 0; f < s->n_fields; f++) {
+        if (!data[f]) { cudaFree(stage); return fail(E_ARG, "data[%d] is NULL", f); }
+        void *dst = nullptr;
+        if (s->storage == YTB200_STORE_F64) {
+            CK(cudaMalloc(&dst, nelem * sizeof(double)));
+            CK(cudaMemcpyAsync(dst, data[f], nelem * sizeof(double), cudaMemcpyHostToDevice, st));
+            s->bytes += (int64_t)(nelem * sizeof(double));
+        } else {
+            CK(cudaMalloc(&dst, nelem * sizeof(float)));
+            for (size_t o = 0; o < nelem; o += chunk) {
+                const size_t m = nelem - o < chunk ? nelem - o : chunk;
+                CK(cudaMemcpyAsync(stage, data[f] + o, m * sizeof(double), cudaMemcpyHostToDevice, st));
+                f64_to_f32_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(stage, (float *)dst + o, (long long)m);
+                CK(cudaGetLastError());
+            }
+            s->bytes += (int64_t)(nelem * sizeof(float));
+        }
+        s->owned.push_back(dst);
+        b.data[f] = dst;
+    }
+    b.mask = nullptr;
+    if (mask) {
+        bool all_one = true;
+        for (size_t i = 0; i < ncell; i++) if (mask[i] != 1) { all_one = false; break; }
+        if (!all_one) {
+            void *dm = nullptr;
+            CK(cudaMalloc(&dm, ncell));
+            CK(cudaMemcpyAsync(dm, mask, ncell, cudaMemcpyHostToDevice, st));
+            s->owned.push_back(dm);
+            b.mask = (const unsigned char *)dm;
+            s->any_mask = true;
+            s->bytes += (int64_t)ncell;
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    if (stage) CK(cudaFree(stage));
+    return 0;
+}
+
+extern "C" int ytb200_brick_attach(ytb200_brickset *s, int64_t index, const int64_t dims[3], const double le[3],
+                                   const double re[3], const void *const *dev_data, const uint8_t *dev_mask)
+{
+    if (!s || !dims || !le || !re || !dev_data) return fail(E_ARG, "NULL argument");
+    int rc = fill_geometry(s, index, dims, le, re);
+    if (rc) return rc;
+    DevBrick &b = s->host[(size_t)index];
+    const int c = s->centring == YTB200_VERTEX_CENTRED ? 1 : 0;
+    const size_t nelem = (size_t)(dims[0] + c) * (size_t)(dims[1] + c) * (size_t)(dims[2] + c);
+    for (int f = 0; f < s->n_fields; f++) {
+        if (!dev_data[f]) return fail(E_ARG, "dev_data[%d] is NULL", f);
+        b.data[f] = dev_data[f];
+        s->bytes += (int64_t)(nelem * (s->storage == YTB200_STORE_F64 ? 8 : 4));
+    }
+    b.mask = dev_mask;
+    if (dev_mask) s->any_mask = true;
+    return 0;
+}
+
+extern "C" int ytb200_bricks_commit(ytb200_brickset *s)
+{
+    if (!s) return fail(E_ARG, "set is NULL");
+    DeviceGuard g(s->ctx->device);
+    for (int64_t i = 0; i < s->n; i++)
+        if (!s->host[(size_t)i].data[0]) return fail(E_STATE, "brick %lld has no data", (long long)i);
+    if (!s->dev && s->n) CK(cudaMalloc(&s->dev, sizeof(DevBrick) * (size_t)s->n));
+    if (s->n) {
+        CK(cudaMemcpyAsync(s->dev, s->host.data(), sizeof(DevBrick) * (size_t)s->n, cudaMemcpyHostToDevice, s->ctx->stream));
+        CK(cudaStreamSynchronize(s->ctx->stream));
+    }
+    s->committed = true;
+    return 0;
+}
+
+extern "C" int ytb200_bricks_destroy(ytb200_brickset *s)
+{
+    if (!s) return 0;
+    DeviceGuard g(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (void *p : s->owned) cudaFree(p);
+    cudaFree(s->dev);
+    delete s;
+    return 0;
+}
+
+extern "C" int ytb200_brick_device_ptrs(const ytb200_brickset *s, int64_t index, void **data_out, void **mask_out)
+{
+    if (!s || !data_out || !mask_out) return fail(E_ARG, "NULL argument");
+    if (index < 0 || index >= s->n) return fail(E_ARG, "brick index %lld out of range", (long long)index);
+    const DevBrick &b = s->host[(size_t)index];
+    for (int f = 0; f < s->n_fields; f++) data_out[f] = const_cast<void *>(b.data[f]);
+    *mask_out = const_cast<unsigned char *>(b.mask);
+    return 0;
+}
+
+extern "C" int64_t ytb200_bricks_device_bytes(const ytb200_brickset *s) { return s ? s->bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// transfer function
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int to_device(ytb200_tf *t, const std::vector<T> &h, const T **out)
+{
+    void *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(T) * (h.size() ? h.size() : 1)));
+    CK(cudaMemcpyAsync(d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, t->ctx->stream));
+    t->owned.push_back(d);
+    *out = (const T *)d;
+    return 0;
+}
+
+extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nbins, const double *const *y,
+                                const double *bounds, const int32_t field_ids[6], const int32_t weight_field_ids[6],
+                                const int32_t weight_table_ids[6], const int32_t field_table_ids[6], int grey_opacity,
+                                ytb200_tf **out)
+{
+    if (!ctx || !out || !nbins || !y || !bounds || !field_ids || !weight_field_ids || !weight_table_ids || !field_table_ids)
+        return fail(E_ARG, "NULL argument");
+    if (n_tables < 1 || n_tables > YTB200_MAX_TABLES) return fail(E_ARG, "n_tables must be 1..6, got %d", n_tables);
+    DeviceGuard g(ctx->device);
+    auto *t = new ytb200_tf;
+    t->ctx = ctx;
+    DevTF &d = t->d;
+    d.n_fits = n_tables;
+    d.grey = grey_opacity ? 1 : 0;
+    int total = 0;
+    for (int i = 0; i < n_tables; i++) {
+        if (nbins[i] < 2) { delete t; return fail(E_ARG, "table %d needs >= 2 bins", i); }
+        if (field_ids[i] < 0 || field_ids[i] >= 6 || weight_field_ids[i] < -1 || weight_field_ids[i] >= 6 ||
+            weight_table_ids[i] < -1 || weight_table_ids[i] >= n_tables) {
+            delete t;
+            return fail(E_ARG, "table %d: field/weight ids out of range", i);
+        }
+        d.nbins[i] = nbins[i]; d.offset[i] = total; total += nbins[i];
+        d.field_id[i] = field_ids[i]; d.weight_field_id[i] = weight_field_ids[i]; d.weight_table_id[i] = weight_table_ids[i];
+    }
+    for (int i = 0; i < 6; i++) {
+        if (field_table_ids[i] < 0 || field_table_ids[i] >= 6) { delete t; return fail(E_ARG, "field_table_ids[%d] out of range", i); }
+        d.field_table_id[i] = field_table_ids[i];
+    }
+    d.total_bins = total;
+    std::vector<double> values(total), d0(total, 0.0), dy(total, 0.0);
+    std::vector<float2> pairs(total);
+    for (int i = 0; i < n_tables; i++) {
+        // FIT_initialize_table, field_interpolation_tables.pxd:44-61
+        const double b0 = bounds[2 * i], b1 = bounds[2 * i + 1];
+        const double dbin = (b1 - b0) / (nbins[i] - 1), idbin = 1.0 / dbin;
+        d.b0[i] = b0; d.b1[i] = b1; d.idbin[i] = idbin;
+        d.b0_hi[i] = (float)b0; d.b0_lo[i] = (float)(b0 - (double)d.b0_hi[i]);
+        d.b1_f[i] = (float)b1; d.idbin_f[i] = (float)idbin;
+        for (int j = 0; j < nbins[i]; j++) {
+            const int o = d.offset[i] + j;
+            values[o] = y[i][j];
+            if (j < nbins[i] - 1) {
+                d0[o] = b0 + j * dbin;
+                dy[o] = (y[i][j + 1] - y[i][j]) * idbin;
+                pairs[o] = make_float2((float)y[i][j], (float)(y[i][j + 1] - y[i][j]));
+            } else {
+                pairs[o] = make_float2((float)y[i][j], 0.f);
+            }
+        }
+    }
+    // ColorTransferFunction layout (transfer_functions.py:385-406)
+    bool colour = n_tables == 4;
+    for (int i = 0; colour && i < 4; i++) {
+        colour = nbins[i] == nbins[0] && bounds[2 * i] == bounds[0] && bounds[2 * i + 1] == bounds[1] &&
+                 field_ids[i] == 0 && weight_field_ids[i] == -1 && weight_table_ids[i] == (i < 3 ? 3 : -1) &&
+                 field_table_ids[i] == i;
+    }
+    d.colour_fast = colour ? 1 : 0;
+    int rc = 0;
+    rc |= to_device(t, values, &d.values);
+    rc |= to_device(t, d0, &d.d0);
+    rc |= to_device(t, dy, &d.dy);
+    rc |= to_device(t, pairs, &d.pairs);
+    if (colour) {
+        std::vector<float4> col(2 * (size_t)nbins[0]);
+        for (int j = 0; j < nbins[0]; j++) {
+            float v[4], dv[4];
+            for (int c = 0; c < 4; c++) {
+                v[c] = (float)y[c][j];
+                dv[c] = j < nbins[0] - 1 ? (float)(y[c][j + 1] - y[c][j]) : 0.f;
+            }
+            col[2 * j] = make_float4(v[0], v[1], v[2], v[3]);
+            col[2 * j + 1] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+        }
+        rc |= to_device(t, col, &d.colour);
+    }
+    if (rc) { ytb200_tf_destroy(t); return rc; }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ytb200_tf_destroy(t); return fail(-100 - (int)e, "tf upload: %s", cudaGetErrorString(e)); }
+    *out = t;
+    return 0;
+}
+
+extern "C" int ytb200_tf_destroy(ytb200_tf *t)
+{
+    if (!t) return 0;
+    DeviceGuard g(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    for (void *p : t->owned) cudaFree(p);
+    delete t;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame
+// ------------------------------------------------------------------------------------------------
+static bool invert3(const double m[9], double inv[9])
+{
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    const double scale = fabs(a * e * i) + fabs(b * f * g) + fabs(c * d * h) + fabs(c * e * g) + fabs(b * d * i) + fabs(a * f * h);
+    if (!(fabs(det) > 1e-12 * scale) || !std::isfinite(det)) return false;
+    const double id = 1.0 / det;
+    inv[0] = (e * i - f * h) * id; inv[1] = (c * h - b * i) * id; inv[2] = (b * f - c * e) * id;
+    inv[3] = (f * g - d * i) * id; inv[4] = (a * i - c * g) * id; inv[5] = (c * d - a * f) * id;
+    inv[6] = (d * h - e * g) * id; inv[7] = (b * g - a * h) * id; inv[8] = (a * e - b * d) * id;
+    return true;
+}
+
+extern "C" int ytb200_frame_create(ytb200_ctx *ctx, const ytb200_camera *cam, ytb200_frame **out)
+{
+    if (!ctx || !cam || !out) return fail(E_ARG, "NULL argument");
+    if (cam->nx < 1 || cam->ny < 1) return fail(E_ARG, "bad image shape %d x %d", cam->nx, cam->ny);
+    if (cam->lens < 0 || cam->lens > 2) return fail(E_ARG, "bad lens %d", cam->lens);
+    if (cam->lens != YTB200_LENS_PLANE_PARALLEL && (!cam->vp_pos_px || !cam->vp_dir_px))
+        return fail(E_ARG, "Bad lens shape / direction: per-pixel vp_pos/vp_dir required for this lens");
+    DeviceGuard g(ctx->device);
+    auto *f = new ytb200_frame;
+    f->ctx = ctx;
+    DevCamera &c = f->cam;
+    c.lens = cam->lens; c.nx = cam->nx; c.ny = cam->ny;
+    memcpy(c.vp_pos, cam->vp_pos, sizeof c.vp_pos);
+    memcpy(c.vp_dir, cam->vp_dir, sizeof c.vp_dir);
+    memcpy(c.width, cam->width, sizeof c.width);
+    c.ext_mode = 0;
+    const size_t npx = (size_t)cam->nx * cam->ny;
+    if (cam->lens == YTB200_LENS_PLANE_PARALLEL) {
+        // a point X maps to image-plane coordinates by solving X - back_center = e*px + n*py + d*t
+        const double m[9] = {c.vp_pos[0], c.vp_pos[3], c.vp_dir[0], c.vp_pos[1], c.vp_pos[4], c.vp_dir[1],
+                             c.vp_pos[2], c.vp_pos[5], c.vp_dir[2]};
+        double inv[9];
+        if (invert3(m, inv) && cam->nx > 1 && cam->ny > 1 && cam->width[0] != 0.0 && cam->width[1] != 0.0) {
+            memcpy(c.ext_rows, inv, sizeof(double) * 6);
+            for (int i = 0; i < 3; i++) c.ext_origin[i] = c.vp_pos[9 + i];
+            c.ext_mode = 1;
+        }
+    } else {
+        cudaError_t e;
+        if ((e = cudaMalloc(&f->pos_px, npx * 3 * sizeof(double))) != cudaSuccess ||
+            (e = cudaMalloc(&f->dir_px, npx * 3 * sizeof(double))) != cudaSuccess) {
+            ytb200_frame_destroy(f);
+            return fail(-100 - (int)e, "ray buffers: %s", cudaGetErrorString(e));
+        }
+        cudaMemcpyAsync(f->pos_px, cam->vp_pos_px, npx * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(f->dir_px, cam->vp_dir_px, npx * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+        c.pos_px = f->pos_px; c.dir_px = f->dir_px;
+        if (cam->lens == YTB200_LENS_PERSPECTIVE && cam->has_camera_data && cam->nx > 1 && cam->ny > 1) {
+            memcpy(c.persp, cam->camera_data, sizeof c.persp);
+            for (int i = 0; i < 3; i++) c.ext_origin[i] = cam->camera_data[i];
+            if (cam->camera_data[3] != 0.0 && cam->camera_data[5] != 0.0) c.ext_mode = 2;
+        }
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc(&f->image, npx * 4 * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc(&f->zbuffer, npx * sizeof(double))) != cudaSuccess) {
+        ytb200_frame_destroy(f);
+        return fail(-100 - (int)e, "frame buffers: %s", cudaGetErrorString(e));
+    }
+    *out = f;
+    int rc = ytb200_frame_clear(f);
+    if (rc) { ytb200_frame_destroy(f); *out = nullptr; return rc; }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int ytb200_frame_destroy(ytb200_frame *f)
+{
+    if (!f) return 0;
+    DeviceGuard g(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaFree(f->image); cudaFree(f->zbuffer); cudaFree(f->pos_px); cudaFree(f->dir_px);
+    cudaFree(f->order_dev); cudaFree(f->extent_dev);
+    delete f;
+    return 0;
+}
+
+extern "C" int ytb200_frame_upload(ytb200_frame *f, const double *image_host, const double *zbuffer_host)
+{
+    if (!f || !image_host) return fail(E_ARG, "NULL argument");
+    DeviceGuard g(f->ctx->device);
+    const size_t npx = (size_t)f->cam.nx * f->cam.ny;
+    CK(cudaMemcpyAsync(f->image, image_host, npx * 4 * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
+    if (zbuffer_host) {
+        CK(cudaMemcpyAsync(f->zbuffer, zbuffer_host, npx * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
+    } else {
+        fill_f64_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, f->ctx->stream>>>(f->zbuffer, 1.0, (long long)npx);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int ytb200_frame_clear(ytb200_frame *f)
+{
+    if (!f) return fail(E_ARG, "frame is NULL");
+    DeviceGuard g(f->ctx->device);
+    const size_t npx = (size_t)f->cam.nx * f->cam.ny;
+    CK(cudaMemsetAsync(f->image, 0, npx * 4 * sizeof(double), f->ctx->stream));
+    fill_f64_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, f->ctx->stream>>>(f->zbuffer, 1.0, (long long)npx);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ytb200_frame_download(ytb200_frame *f, double *image_host)
+{
+    if (!f || !image_host) return fail(E_ARG, "NULL argument");
+    DeviceGuard g(f->ctx->device);
+    const size_t npx = (size_t)f->cam.nx * f->cam.ny;
+    CK(cudaMemcpyAsync(image_host, f->image, npx * 4 * sizeof(double), cudaMemcpyDeviceToHost, f->ctx->stream));
+    CK(cudaStreamSynchronize(f->ctx->stream));
+    return 0;
+}
+
+extern "C" void *ytb200_frame_device_image(ytb200_frame *f) { return f ? (void *)f->image : nullptr; }
+
+// Upload the order list and compute per-brick pixel footprints (cached while unchanged).
+static int prepare_order(ytb200_frame *f, const ytb200_brickset *set, const int64_t *order, int64_t n_order, int *launches)
+{
+    if (!set->committed) return fail(E_STATE, "brick set not committed (call ytb200_bricks_commit)");
+    if (set->ctx->device != f->ctx->device) return fail(E_ARG, "brick set and frame live on different devices");
+    if (n_order < 0 || n_order > set->n * 64 + 1024) return fail(E_ARG, "bad n_order %lld", (long long)n_order);
+    bool same = f->order_set == set && (int64_t)f->order_host.size() == n_order;
+    if (same)
+        for (int64_t i = 0; i < n_order; i++)
+            if (f->order_host[(size_t)i] != (int)order[i]) { same = false; break; }
+    if (same) return 0;
+    f->order_host.resize((size_t)n_order);
+    for (int64_t i = 0; i < n_order; i++) {
+        if (order[i] < 0 || order[i] >= set->n) return fail(E_ARG, "order[%lld]=%lld out of range", (long long)i, (long long)order[i]);
+        f->order_host[(size_t)i] = (int)order[i];
+    }
+    f->order_set = nullptr;
+    if (n_order > f->order_cap) {
+        CK(cudaStreamSynchronize(f->ctx->stream));
+        cudaFree(f->order_dev); cudaFree(f->extent_dev);
+        f->order_dev = nullptr; f->extent_dev = nullptr;
+        CK(cudaMalloc(&f->order_dev, sizeof(int) * (size_t)n_order));
+        CK(cudaMalloc(&f->extent_dev, sizeof(int4) * (size_t)n_order));
+        f->order_cap = n_order;
+    }
+    if (n_order) {
+        CK(cudaMemcpyAsync(f->order_dev, f->order_host.data(), sizeof(int) * (size_t)n_order, cudaMemcpyHostToDevice, f->ctx->stream));
+        extent_kernel<<<(unsigned)((n_order + 127) / 128), 128, 0, f->ctx->stream>>>(f->cam, set->dev, f->order_dev, (int)n_order, f->extent_dev);
+        CK(cudaGetLastError());
+        if (launches) (*launches)++;
+    }
+    f->order_set = set;
+    return 0;
+}
+
+template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T>
+static cudaError_t launch_one(const CastParams &p, unsigned grid, size_t smem, cudaStream_t st)
+{
+    auto k = cast_kernel<KIND, EXACT, TFM, PARTIAL, NF1, T>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<grid, CTA_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int KIND, int TFM, bool PARTIAL, bool NF1>
+static cudaError_t launch_prec(const CastParams &p, unsigned grid, size_t smem, cudaStream_t st, bool exact, bool f64)
+{
+    if (exact) return launch_one<KIND, true, (KIND == KIND_VR ? TFM_GENERAL : TFM_NONE), PARTIAL, NF1, double>(p, grid, smem, st);
+    if (f64) return launch_one<KIND, false, TFM, PARTIAL, NF1, double>(p, grid, smem, st);
+    return launch_one<KIND, false, TFM, PARTIAL, NF1, float>(p, grid, smem, st);
+}
+
+template <int KIND, int TFM>
+static cudaError_t launch_kind(const CastParams &p, unsigned grid, size_t smem, cudaStream_t st, bool exact, bool f64,
+                               bool partial, bool nf1)
+{
+    if (partial) {
+        if (nf1) return launch_prec<KIND, TFM, true, true>(p, grid, smem, st, exact, f64);
+        return launch_prec<KIND, (TFM == TFM_COLOUR ? TFM_GENERAL : TFM), true, false>(p, grid, smem, st, exact, f64);
+    }
+    if (nf1) return launch_prec<KIND, TFM, false, true>(p, grid, smem, st, exact, f64);
+    return launch_prec<KIND, (TFM == TFM_COLOUR ? TFM_GENERAL : TFM), false, false>(p, grid, smem, st, exact, f64);
+}
+
+static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order, int64_t n_order,
+                       const ytb200_tf *tf, int n_samples, int precision, double *partial, ytb200_stats *stats)
+{
+    if (!f || !set || (!order && n_order > 0)) return fail(E_ARG, "NULL argument");
+    if (kind < 0 || kind > 2) return fail(E_ARG, "bad sampler kind %d", kind);
+    if (precision != YTB200_PREC_FAST && precision != YTB200_PREC_EXACT) return fail(E_ARG, "bad precision %d", precision);
+    if (kind == YTB200_VOLUME_RENDER && !tf) return fail(E_ARG, "VolumeRenderSampler needs a transfer function");
+    if (kind != YTB200_PROJECTION && n_samples < 1) return fail(E_ARG, "n_samples must be >= 1");
+    if (kind == YTB200_PROJECTION && set->centring != YTB200_CELL_CENTRED)
+        return fail(E_ARG, "ProjectionSampler needs cell-centred bricks");
+    if (kind != YTB200_PROJECTION && set->centring != YTB200_VERTEX_CENTRED)
+        return fail(E_ARG, "interpolating samplers need vertex-centred bricks");
+    const bool exact = precision == YTB200_PREC_EXACT;
+    if (exact && set->storage != YTB200_STORE_F64) return fail(E_ARG, "EXACT precision needs fp64 brick storage");
+    if (kind == YTB200_VOLUME_RENDER) {
+        for (int i = 0; i < tf->d.n_fits; i++)
+            if (tf->d.field_id[i] >= set->n_fields || tf->d.weight_field_id[i] >= set->n_fields)
+                return fail(E_ARG, "transfer function table %d refers to field beyond n_fields=%d", i, set->n_fields);
+    }
+    DeviceGuard g(f->ctx->device);
+    cudaStream_t st = f->ctx->stream;
+    int launches = 0;
+    if (stats) CK(cudaEventRecord(f->ctx->ev0, st));
+    int rc = prepare_order(f, set, order, n_order, &launches);
+    if (rc) return rc;
+    if (n_order > 0 || partial) {
+        CastParams p{};
+        p.cam = f->cam;
+        p.bricks = set->dev; p.order = f->order_dev; p.extent = f->extent_dev; p.n_order = (int)n_order;
+        p.n_samples = n_samples < 1 ? 1 : n_samples;
+        p.image = f->image; p.zbuffer = f->zbuffer; p.partial = partial;
+        if (tf) p.tf = tf->d;
+        p.counters = f->ctx->counters;
+        const unsigned grid = (unsigned)(((f->cam.nx + TILE_I - 1) / TILE_I) * ((f->cam.ny + TILE_J - 1) / TILE_J));
+        const bool nf1 = set->n_fields == 1;
+        const bool f64 = set->storage == YTB200_STORE_F64;
+        size_t smem = 0;
+        cudaError_t e;
+        if (kind == YTB200_VOLUME_RENDER) {
+            const bool colour = !exact && nf1 && tf->d.colour_fast;
+            if (exact) smem = (size_t)tf->d.total_bins * 3 * sizeof(double);
+            else if (colour) smem = (size_t)tf->d.nbins[0] * 2 * sizeof(float4);
+            else smem = (size_t)tf->d.total_bins * sizeof(float2);
+            if (smem > 200 * 1024) return fail(E_UNSUPPORTED, "transfer function tables (%zu B) exceed shared memory", smem);
+            if (colour) e = launch_kind<KIND_VR, TFM_COLOUR>(p, grid, smem, st, exact, f64, partial != nullptr, nf1);
+            else e = launch_kind<KIND_VR, TFM_GENERAL>(p, grid, smem, st, exact, f64, partial != nullptr, nf1);
+        } else if (kind == YTB200_INTERPOLATED_PROJECTION) {
+            e = launch_kind<KIND_IPROJ, TFM_NONE>(p, grid, 0, st, exact, f64, partial != nullptr, nf1);
+        } else {
+            e = launch_kind<KIND_PROJ, TFM_NONE>(p, grid, 0, st, exact, f64, partial != nullptr, false);
+        }
+        if (e != cudaSuccess) return fail(-100 - (int)e, "cast launch: %s", cudaGetErrorString(e));
+        launches++;
+    }
+    if (stats) {
+        CK(cudaEventRecord(f->ctx->ev1, st));
+        CK(cudaEventSynchronize(f->ctx->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, f->ctx->ev0, f->ctx->ev1));
+        stats->kernel_ms = ms;
+        stats->n_launches = launches;
+        stats->n_cells = 0;
+        stats->n_samples = 0;
+    }
+    return 0;
+}
+
+extern "C" int ytb200_frame_cast(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
+                                 int64_t n_order, const ytb200_tf *tf, int n_samples, int precision, ytb200_stats *stats)
+{
+    return cast_common(f, kind, set, order, n_order, tf, n_samples, precision, nullptr, stats);
+}
+
+extern "C" int ytb200_frame_cast_partial(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
+                                         int64_t n_order, const ytb200_tf *tf, int n_samples, int precision,
+                                         double *partial_dev, ytb200_stats *stats)
+{
+    if (!partial_dev) return fail(E_ARG, "partial_dev is NULL");
+    return cast_common(f, kind, set, order, n_order, tf, n_samples, precision, partial_dev, stats);
+}
+
+extern "C" int ytb200_frame_count(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
+                                  int64_t n_order, int n_samples, ytb200_stats *stats)
+{
+    if (!f || !set || !stats || (!order && n_order > 0)) return fail(E_ARG, "NULL argument");
+    if (kind < 0 || kind > 2) return fail(E_ARG, "bad sampler kind %d", kind);
+    DeviceGuard g(f->ctx->device);
+    cudaStream_t st = f->ctx->stream;
+    int launches = 0;
+    int rc = prepare_order(f, set, order, n_order, &launches);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(f->ctx->counters, 0, 8 * sizeof(unsigned long long), st));
+    CastParams p{};
+    p.cam = f->cam;
+    p.bricks = set->dev; p.order = f->order_dev; p.extent = f->extent_dev; p.n_order = (int)n_order;
+    p.zbuffer = f->zbuffer; p.counters = f->ctx->counters;
+    const unsigned grid = (unsigned)(((f->cam.nx + TILE_I - 1) / TILE_I) * ((f->cam.ny + TILE_J - 1) / TILE_J));
+    CK(cudaEventRecord(f->ctx->ev0, st));
+    count_kernel<<<grid, CTA_THREADS, 0, st>>>(p, kind);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(f->ctx->ev1, st));
+    unsigned long long n = 0;
+    CK(cudaMemcpyAsync(&n, f->ctx->counters, sizeof n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, f->ctx->ev0, f->ctx->ev1));
+    stats->kernel_ms = ms;
+    stats->n_launches = launches + 1;
+    stats->n_cells = (int64_t)n;
+    stats->n_samples = (int64_t)n * (kind == YTB200_PROJECTION ? 1 : (n_samples < 1 ? 1 : n_samples));
+    return 0;
+}
+
+extern "C" int ytb200_partial_compose(ytb200_ctx *ctx, const double *earlier, const double *later, double *out, int64_t n)
+{
+    if (!ctx || !earlier || !later || !out || n < 0) return fail(E_ARG, "bad argument");
+    if (n == 0) return 0;
+    DeviceGuard g(ctx->device);
+    compose_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const double4 *)earlier, (const double4 *)later, (double4 *)out, (long long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ytb200_partial_apply(ytb200_ctx *ctx, const double *partial, double *image, int64_t n)
+{
+    if (!ctx || !partial || !image || n < 0) return fail(E_ARG, "bad argument");
+    if (n == 0) return 0;
+    DeviceGuard g(ctx->device);
+    apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const double4 *)partial, (double4 *)image, (long long)n);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ytb200_render(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order, int64_t n_order,
+                             const ytb200_tf *tf, int n_samples, int precision, const double *zbuffer_host,
+                             double *image_host_inout, ytb200_stats *stats)
+{
+    int rc = ytb200_frame_upload(f, image_host_inout, zbuffer_host);
+    if (rc) return rc;
+    rc = ytb200_frame_cast(f, kind, set, order, n_order, tf, n_samples, precision, stats);
+    if (rc) return rc;
+    return ytb200_frame_download(f, image_host_inout);
+}
+
+extern "C" int ytb200_host_alloc(int64_t bytes, void **out)
+{
+    if (!out || bytes <= 0) return fail(E_ARG, "bad argument");
+    CK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return 0;
+}
+
+extern "C" int ytb200_host_free(void *p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return 0;
+}

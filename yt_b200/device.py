@@ -1,0 +1,228 @@
+"""Thin Python handles over the C-ABI objects of libytb200 (ctx, brick set, tables, frame).
+
+Nothing here computes: these classes marshal numpy arrays into the plain-pointer calls of
+``include/ytb200.h`` and own the opaque handles (every create has a destroy).
+"""
+import ctypes as C
+import os
+import weakref
+
+import numpy as np
+
+from . import _lib as L
+
+_contexts = {}
+
+
+class Context:
+    """One device + one stream (``ytb200_ctx``)."""
+
+    def __init__(self, device=0, stream=None):
+        lib = L.load()
+        h = C.c_void_p()
+        L.check(lib.ytb200_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+        self._fin = weakref.finalize(self, lib.ytb200_ctx_destroy, h)
+
+    def synchronize(self):
+        L.check(L.load().ytb200_ctx_synchronize(self.handle))
+
+    @property
+    def stream(self):
+        return L.load().ytb200_ctx_stream(self.handle)
+
+    @property
+    def sm_count(self):
+        return L.load().ytb200_ctx_sm_count(self.handle)
+
+
+def default_device():
+    """Device index for this process: ``YTB200_DEVICE`` or ``LOCAL_RANK`` (torchrun) or 0."""
+    for k in ("YTB200_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(k, "") != "":
+            return int(os.environ[k])
+    return 0
+
+
+def get_context(device=None):
+    """Process-wide default context per device (created on first use)."""
+    if device is None:
+        device = default_device()
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(L.dp)
+
+
+class BrickSet:
+    """Device-resident list of bricks (``ytb200_brickset``)."""
+
+    def __init__(self, ctx, n_bricks, n_fields, centring, storage=L.STORE_F32):
+        lib = L.load()
+        h = C.c_void_p()
+        L.check(lib.ytb200_bricks_create(ctx.handle, int(n_bricks), int(n_fields), int(centring), int(storage), C.byref(h)))
+        self.handle, self.ctx = h, ctx
+        self.n, self.n_fields, self.centring, self.storage = int(n_bricks), int(n_fields), int(centring), int(storage)
+        self._keep = []      # objects whose device memory we borrow (attach)
+        self._fin = weakref.finalize(self, lib.ytb200_bricks_destroy, h)
+
+    def upload(self, index, data, mask, left_edge, right_edge, dims):
+        """Host fp64 arrays -> device (converted to the set's storage type)."""
+        dims = np.ascontiguousarray(dims, dtype=np.int64)
+        c = 1 if self.centring == L.VERTEX_CENTRED else 0
+        shape = tuple(int(d) + c for d in dims)
+        arrs = []
+        for f in range(self.n_fields):
+            a = _f64(data[f])
+            if a.shape != shape:
+                raise ValueError(f"field {f} has shape {a.shape}, expected {shape}")
+            arrs.append(a)
+        ptrs = (L.dp * self.n_fields)(*[_dptr(a) for a in arrs])
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            if m.shape != tuple(int(d) for d in dims):
+                raise ValueError(f"mask has shape {m.shape}, expected {tuple(int(d) for d in dims)}")
+        le, re = _f64(left_edge), _f64(right_edge)
+        L.check(L.load().ytb200_brick_upload(
+            self.handle, int(index), dims.ctypes.data_as(L.i64p), _dptr(le), _dptr(re), ptrs,
+            m.ctypes.data_as(L.u8p) if m is not None else None))
+
+    def attach(self, index, dev_ptrs, dev_mask, left_edge, right_edge, dims, keep=None):
+        """Borrow device arrays (already in this set's storage type); `keep` is kept alive."""
+        dims = np.ascontiguousarray(dims, dtype=np.int64)
+        ptrs = (C.c_void_p * self.n_fields)(*[C.c_void_p(int(p)) for p in dev_ptrs])
+        le, re = _f64(left_edge), _f64(right_edge)
+        L.check(L.load().ytb200_brick_attach(
+            self.handle, int(index), dims.ctypes.data_as(L.i64p), _dptr(le), _dptr(re), ptrs,
+            C.c_void_p(int(dev_mask)) if dev_mask else None))
+        if keep is not None:
+            self._keep.append(keep)
+
+    def commit(self):
+        L.check(L.load().ytb200_bricks_commit(self.handle))
+        return self
+
+    def device_ptrs(self, index):
+        data = (C.c_void_p * self.n_fields)()
+        mask = C.c_void_p()
+        L.check(L.load().ytb200_brick_device_ptrs(self.handle, int(index), data, C.byref(mask)))
+        return [int(p or 0) for p in data], int(mask.value or 0)
+
+    @property
+    def device_bytes(self):
+        return L.load().ytb200_bricks_device_bytes(self.handle)
+
+
+class TransferTables:
+    """Device-resident FieldInterpolationTables built from a transfer-function object with the
+    reference's duck type (image_samplers.pyx:429-446): ``n_field_tables``, ``tables[i].y``,
+    ``tables[i].x_bounds``, ``field_ids``, ``weight_field_ids``, ``weight_table_ids``,
+    ``field_table_ids``, ``grey_opacity``."""
+
+    def __init__(self, ctx, tf_obj):
+        lib = L.load()
+        n = int(tf_obj.n_field_tables)
+        assert n <= 6
+        ys = [_f64(tf_obj.tables[i].y) for i in range(n)]
+        nbins = np.array([y.shape[0] for y in ys], dtype=np.int32)
+        bounds = np.array([[float(tf_obj.tables[i].x_bounds[0]), float(tf_obj.tables[i].x_bounds[1])]
+                           for i in range(n)], dtype=np.float64)
+        yp = (L.dp * n)(*[_dptr(y) for y in ys])
+
+        def i32(v):
+            return np.array([int(x) for x in list(v)[:6]], dtype=np.int32)
+        fid, wfid, wtid, ftid = i32(tf_obj.field_ids), i32(tf_obj.weight_field_ids), i32(tf_obj.weight_table_ids), i32(tf_obj.field_table_ids)
+        h = C.c_void_p()
+        L.check(lib.ytb200_tf_create(
+            ctx.handle, n, nbins.ctypes.data_as(L.i32p), yp, _dptr(bounds), fid.ctypes.data_as(L.i32p),
+            wfid.ctypes.data_as(L.i32p), wtid.ctypes.data_as(L.i32p), ftid.ctypes.data_as(L.i32p),
+            int(bool(getattr(tf_obj, "grey_opacity", 0))), C.byref(h)))
+        self.handle, self.ctx = h, ctx
+        self.grey_opacity = bool(getattr(tf_obj, "grey_opacity", 0))
+        self._fin = weakref.finalize(self, lib.ytb200_tf_destroy, h)
+
+
+class Frame:
+    """Device image + z-buffer + ray set of one sampler (``ytb200_frame``)."""
+
+    def __init__(self, ctx, cam_struct, keep=()):
+        lib = L.load()
+        h = C.c_void_p()
+        L.check(lib.ytb200_frame_create(ctx.handle, C.byref(cam_struct), C.byref(h)))
+        self.handle, self.ctx = h, ctx
+        self.nx, self.ny = cam_struct.nx, cam_struct.ny
+        self._keep = keep
+        self._fin = weakref.finalize(self, lib.ytb200_frame_destroy, h)
+
+    def upload(self, image, zbuffer=None):
+        assert image.dtype == np.float64 and image.flags.c_contiguous
+        L.check(L.load().ytb200_frame_upload(
+            self.handle, image.ctypes.data, zbuffer.ctypes.data if zbuffer is not None else None))
+
+    def clear(self):
+        L.check(L.load().ytb200_frame_clear(self.handle))
+
+    def _order(self, order):
+        o = np.ascontiguousarray(order, dtype=np.int64)
+        return o, o.ctypes.data_as(L.i64p), int(o.shape[0])
+
+    def cast(self, kind, bricks, order, tf=None, n_samples=10, precision=L.PREC_FAST, timed=False):
+        o, op, n = self._order(order)
+        st = L.Stats() if timed else None
+        L.check(L.load().ytb200_frame_cast(
+            self.handle, int(kind), bricks.handle, op, n, tf.handle if tf is not None else None,
+            int(n_samples), int(precision), C.byref(st) if timed else None))
+        return st
+
+    def cast_partial(self, kind, bricks, order, partial_ptr, tf=None, n_samples=10, precision=L.PREC_FAST, timed=False):
+        o, op, n = self._order(order)
+        st = L.Stats() if timed else None
+        L.check(L.load().ytb200_frame_cast_partial(
+            self.handle, int(kind), bricks.handle, op, n, tf.handle if tf is not None else None,
+            int(n_samples), int(precision), C.c_void_p(int(partial_ptr)), C.byref(st) if timed else None))
+        return st
+
+    def count(self, kind, bricks, order, n_samples=10):
+        o, op, n = self._order(order)
+        st = L.Stats()
+        L.check(L.load().ytb200_frame_count(self.handle, int(kind), bricks.handle, op, n, int(n_samples), C.byref(st)))
+        return st
+
+    def download(self, image):
+        assert image.dtype == np.float64 and image.flags.c_contiguous
+        L.check(L.load().ytb200_frame_download(self.handle, image.ctypes.data))
+        return image
+
+    def render(self, kind, bricks, order, image, zbuffer=None, tf=None, n_samples=10, precision=L.PREC_FAST):
+        """upload -> cast -> download through the single C call the e2e benchmark times."""
+        o, op, n = self._order(order)
+        L.check(L.load().ytb200_render(
+            self.handle, int(kind), bricks.handle, op, n, tf.handle if tf is not None else None, int(n_samples),
+            int(precision), zbuffer.ctypes.data if zbuffer is not None else None, image.ctypes.data, None))
+        return image
+
+    @property
+    def device_image(self):
+        return L.load().ytb200_frame_device_image(self.handle)
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array over cudaHostAlloc'd memory (freed when the array's base is collected)."""
+    lib = L.load()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = C.c_void_p()
+    L.check(lib.ytb200_host_alloc(max(n, 1), C.byref(p)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.ytb200_host_free, C.c_void_p(p.value))
+    return arr
