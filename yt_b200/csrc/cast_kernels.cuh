@@ -130,12 +130,21 @@ struct CellSampler {
             Corners c;
             load_corners(c, (const T *)br->data[0] + offset, sx, sy);
             if (KIND == KIND_IPROJ) {
-                float sum = 0.f;
+                // the projection family carries the 1e-6 bar: sample in fp64 (contraction allowed)
+                const T *d = (const T *)br->data[0] + offset;
+                const double a0 = (double)__ldg(d), a1 = (double)__ldg(d + 1), b0 = (double)__ldg(d + sy), b1 = (double)__ldg(d + sy + 1);
+                const double e0 = (double)__ldg(d + sx), e1 = (double)__ldg(d + sx + 1), f0 = (double)__ldg(d + sx + sy), f1 = (double)__ldg(d + sx + sy + 1);
+                double xd = fma(tmid, dc[0], o[0]) - (double)ix, yd = fma(tmid, dc[1], o[1]) - (double)iy, zd = fma(tmid, dc[2], o[2]) - (double)iz;
+                const double sxd = dc[0] * dt64, syd = dc[1] * dt64, szd = dc[2] * dt64;
+                double sum = 0.0;
                 for (int s = 0; s < n_samples; s++) {
-                    sum += trilinear(c, x, y, z);
-                    x += sxs; y += sys; z += szs;
+                    const double v00 = fma(zd, a1 - a0, a0), v01 = fma(zd, b1 - b0, b0);
+                    const double v10 = fma(zd, e1 - e0, e0), v11 = fma(zd, f1 - f0, f0);
+                    const double v0 = fma(yd, v01 - v00, v00), v1 = fma(yd, v11 - v10, v10);
+                    sum += fma(xd, v1 - v0, v0);
+                    xd += sxd; yd += syd; zd += szd;
                 }
-                acc[0] = fma((double)sum, dt64, acc[0]);
+                acc[0] = fma(sum, dt64, acc[0]);
             } else {
                 if (TFM == TFM_COLOUR) {
                     const float b0h = tf->b0_hi[0], b0l = tf->b0_lo[0], b1 = tf->b1_f[0], idb = tf->idbin_f[0];
@@ -162,30 +171,44 @@ struct CellSampler {
             }
         } else {
             // any number of fields: corners re-read (L1) per sample; general but not the tuned path
-            float sum[3] = {0.f, 0.f, 0.f};
-            for (int s = 0; s < n_samples; s++) {
-                float dvs[6];
-#pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    dvs[j] = 0.f;
-                    if (j < n_fields) {
-                        Corners c;
-                        load_corners(c, (const T *)br->data[j] + offset, sx, sy);
-                        dvs[j] = trilinear(c, x, y, z);
-                    }
-                }
-                if (KIND == KIND_IPROJ) {
-                    sum[0] += dvs[0]; sum[1] += dvs[1]; sum[2] += dvs[2];
-                } else {
-                    eval_transfer32<PARTIAL>(*tf, pairs, dt, dvs, rgba, B);
-                }
-                x += sxs; y += sys; z += szs;
-            }
             if (KIND == KIND_IPROJ) {
+                double xd = fma(tmid, dc[0], o[0]) - (double)ix, yd = fma(tmid, dc[1], o[1]) - (double)iy, zd = fma(tmid, dc[2], o[2]) - (double)iz;
+                const double sxd = dc[0] * dt64, syd = dc[1] * dt64, szd = dc[2] * dt64;
                 const int nf = n_fields < 3 ? n_fields : 3;
+                double sum[3] = {0.0, 0.0, 0.0};
+                for (int s = 0; s < n_samples; s++) {
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        if (j < nf) {
+                            const T *d = (const T *)br->data[j] + offset;
+                            const double a0 = (double)__ldg(d), a1 = (double)__ldg(d + 1), b0 = (double)__ldg(d + sy), b1 = (double)__ldg(d + sy + 1);
+                            const double e0 = (double)__ldg(d + sx), e1 = (double)__ldg(d + sx + 1), f0 = (double)__ldg(d + sx + sy), f1 = (double)__ldg(d + sx + sy + 1);
+                            const double v00 = fma(zd, a1 - a0, a0), v01 = fma(zd, b1 - b0, b0);
+                            const double v10 = fma(zd, e1 - e0, e0), v11 = fma(zd, f1 - f0, f0);
+                            const double v0 = fma(yd, v01 - v00, v00), v1 = fma(yd, v11 - v10, v10);
+                            sum[j] += fma(xd, v1 - v0, v0);
+                        }
+                    }
+                    xd += sxd; yd += syd; zd += szd;
+                }
 #pragma unroll
                 for (int j = 0; j < 3; j++)
-                    if (j < nf) acc[j] = fma((double)sum[j], dt64, acc[j]);
+                    if (j < nf) acc[j] = fma(sum[j], dt64, acc[j]);
+            } else {
+                for (int s = 0; s < n_samples; s++) {
+                    float dvs[6];
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        dvs[j] = 0.f;
+                        if (j < n_fields) {
+                            Corners c;
+                            load_corners(c, (const T *)br->data[j] + offset, sx, sy);
+                            dvs[j] = trilinear(c, x, y, z);
+                        }
+                    }
+                    eval_transfer32<PARTIAL>(*tf, pairs, dt, dvs, rgba, B);
+                    x += sxs; y += sys; z += szs;
+                }
             }
         }
     }
