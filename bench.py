@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- the north-star frame: 1024^3 uniform-grid VolumeSource rendered at 2048^2.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one frame: cast every ray of the image through the whole volume (VolumeRenderSampler,
+n_samples=10, ColorTransferFunction) -- the reference's `for brick in traverse(): sampler(brick)`.
+
+  value     Gsamples/s with bricks, tables and the (zeroed) image already in HBM; timed with CUDA
+            events on the launching stream, max over ranks.
+  e2e       the same frame through the C-ABI call ytb200_render with HOST (pinned) image and z-buffer:
+            H2D + cast + D2H inside the timed region.  Bricks stay device-resident across frames, as
+            the reference keeps PartitionedGrids cached on the kd-tree nodes (amr_kdtree.py:326-327).
+  roofline  algorithmic HBM bytes of the cast kernel / its measured duration vs the measured copy
+            bandwidth (MEASURED_PEAKS.json).  The volume-render kernel is issue-bound, not HBM-bound
+            (SURVEY.md 8d): `issue` carries the instruction-issue view next to it.
+  cpu_baseline / --impl reference
+            the reference's own Cython samplers (compiled unmodified into oracle/_ref) on the box's
+            host cores, on a bounded sample (256^3 brick @ 512^2, same view / tables / n_samples).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (cells per side, image side, sampler kind)
+    "northstar_vr_1024c_2048px": (1024, 2048, "vr"),
+    "cfg2_vr_512c_1024px": (512, 1024, "vr"),
+    "cfg3_proj_1024c_2048px": (1024, 2048, "proj"),
+    "tiny_vr_64c_256px": (64, 256, "vr"),
+}
+N_SAMPLES = 10
+SEED = 0
+
+
+def bench_tf():
+    from yt_b200.volume_rendering.transfer_functions import ColorTransferFunction
+    tf = ColorTransferFunction((0.0, 1.0), 256)
+    cols = [(0.9, 0.2, 0.1), (0.2, 0.8, 0.2), (0.1, 0.3, 0.9), (0.9, 0.9, 0.3)]
+    for k, c in enumerate(cols):
+        tf.add_gaussian(0.35 + 0.1 * k, 0.02 ** 2, list(c) + [10.0 ** (k - 1)])
+    return tf
+
+
+def bench_camera(res):
+    """Default camera of yt.create_scene on a unit-cube dataset (camera.py:127-137): corner view."""
+    from tests.common import make_camera
+    return make_camera("plane-parallel", resolution=(res, res))
+
+
+def sampler_call_args(cam, image, zbuffer):
+    from tests.common import sampler_args
+    args, kwargs = sampler_args(cam, zbuffer=zbuffer, image=image)
+    kwargs.pop("camera_data")
+    return args, kwargs
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        busy = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def kd_slab(n, rank, world):
+    """Cell range of rank `rank`'s convex sub-volume: kd split of the single grid at depth log2(world),
+    always halving the longest remaining axis on a cell boundary."""
+    lo, hi = [0, 0, 0], [n, n, n]
+    path = []
+    size, r = world, rank
+    while size > 1:
+        ext = [hi[a] - lo[a] for a in range(3)]
+        ax = int(np.argmax(ext))
+        mid = lo[ax] + ext[ax] // 2
+        half = size // 2
+        upper = r >= half
+        path.append((ax, mid, upper))
+        if upper:
+            lo[ax] = mid; r -= half
+        else:
+            hi[ax] = mid
+        size = half
+    return lo, hi, path
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def recorded_traffic(workload):
+    """DRAM bytes per launch of the cast kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(workload)
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own samplers (oracle/_ref) or, if absent, the C oracle port
+# ------------------------------------------------------------------------------------------------
+def cpu_render_sample(kind, n=256, res=512, threads=0, repeats=1):
+    from oracle import oracle as O
+    from tests.common import vertex_centre
+    from yt_b200.synthetic import host_cells
+    if O.ref_available():
+        S, G = O.load_ref()
+        G = G  # partitioned_grid module
+        label = "reference"
+    else:
+        S, G, label = O, O, "port"
+    cells = host_cells(n, SEED)
+    data = cells if kind == "proj" else vertex_centre(cells)
+    cam = bench_camera(res)
+    threads = threads or os.cpu_count()
+    pg = G.PartitionedGrid(0, [np.ascontiguousarray(data)], np.ones((n, n, n), "uint8"), np.zeros(3), np.ones(3),
+                           np.array([n] * 3, "int64"))
+    best = None
+    for _ in range(repeats):
+        img = np.zeros((res, res, 4))
+        args, kwargs = sampler_call_args(cam, img, None)
+        if kind == "vr":
+            s = S.VolumeRenderSampler(*args, bench_tf(), N_SAMPLES, **kwargs)
+        else:
+            s = S.ProjectionSampler(*args, N_SAMPLES, **kwargs)
+        t0 = time.perf_counter()
+        s(pg, num_threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    # exact sample count of the sample frame from the C oracle's counter
+    img = np.zeros((res, res, 4))
+    args, kwargs = sampler_call_args(cam, img, None)
+    oc = (O.VolumeRenderSampler(*args, bench_tf(), N_SAMPLES, **kwargs) if kind == "vr" else O.ProjectionSampler(*args, N_SAMPLES, **kwargs))
+    oc(O.PartitionedGrid(0, [np.ascontiguousarray(data)], np.ones((n, n, n), "uint8"), np.zeros(3), np.ones(3), np.array([n] * 3, "int64")),
+       num_threads=0)
+    samples = oc.cells * (N_SAMPLES if kind == "vr" else 1)
+    return {"seconds": best, "samples": samples, "kind": label, "cores": threads,
+            "sample": "%d^3 brick @ %d^2, same view/tables/n_samples=%d, best of %d" % (n, res, N_SAMPLES, repeats)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, res, kind = WORKLOADS[args.workload]
+    times = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_render_sample(kind, args.cpu_size, args.cpu_res, threads=0, repeats=1)
+        if i >= args.warmup:
+            times.append(info["seconds"])
+    ms = 1e3 * float(np.mean(times))
+    gs = info["samples"] / (ms * 1e-3) / 1e9
+    line = {"impl": "reference", "metric": "Gsamples/s", "value": gs, "unit": "Gsamples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "step": "bounded CPU sample of the workload: " + info["sample"]},
+            "cpu_baseline": {"value": gs, "unit": "Gsamples/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+            "e2e": {"value": gs, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from yt_b200 import _lib as L
+    from yt_b200 import device as D
+    from yt_b200 import synthetic
+    from yt_b200.parallel import BinarySwap
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with --nproc-per-node %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, res, kind = WORKLOADS[args.workload]
+    stream = torch.cuda.Stream(device=dev)
+    ctx = D.Context(local, stream=stream.cuda_stream)
+    kcode = L.VOLUME_RENDER if kind == "vr" else L.PROJECTION
+
+    with torch.cuda.stream(stream):
+        # ---- this rank's convex sub-volume of the single grid, resident in HBM -------------------
+        lo, hi, path = kd_slab(n, rank, world)
+        if kind == "vr":
+            vol = synthetic.vertex_slab(n, lo, hi, SEED, dev)
+            bricks = D.BrickSet(ctx, 1, 1, L.VERTEX_CENTRED, L.STORE_F32)
+        else:
+            vol = synthetic.cell_slab(n, lo, hi, SEED, dev)
+            bricks = D.BrickSet(ctx, 1, 1, L.CELL_CENTRED, L.STORE_F32)
+        dims = [hi[a] - lo[a] for a in range(3)]
+        le = [lo[a] / n for a in range(3)]
+        re = [hi[a] / n for a in range(3)]
+        bricks.attach(0, [vol.data_ptr()], 0, le, re, dims, keep=vol)
+        bricks.commit()
+        order = np.zeros(1, dtype=np.int64)
+        tf = D.TransferTables(ctx, bench_tf()) if kind == "vr" else None
+        cam = bench_camera(res)
+        img_host = D.pinned_empty((res, res, 4))
+        zb_host = D.pinned_empty((res, res))
+        img_host[:] = 0.0
+        zb_host[:] = 1.0
+        from yt_b200 import image_samplers as S
+        sargs, skw = sampler_call_args(cam, img_host, zb_host)
+        skw["context"] = ctx
+        sampler = (S.VolumeRenderSampler(*sargs, bench_tf(), N_SAMPLES, **skw) if kind == "vr"
+                   else S.ProjectionSampler(*sargs, N_SAMPLES, **skw))
+        frame = sampler._frame
+        swap = BinarySwap(ctx, res, res, path, cam.lens.viewpoint, rank, world) if world > 1 else None
+        partial = torch.empty((res, res, 8), dtype=torch.float64, device=dev) if world > 1 else None
+        stream.synchronize()
+
+        # ---- exact work per frame ----------------------------------------------------------------
+        frame.clear()
+        st = frame.count(kcode, bricks, order, N_SAMPLES)
+        my_samples = int(st.n_samples)
+        if world > 1:
+            t = torch.tensor([my_samples], dtype=torch.int64, device=dev)
+            dist.all_reduce(t)
+            total_samples = int(t.item())
+        else:
+            total_samples = my_samples
+
+        def frame_device():
+            if world == 1:
+                frame.clear()
+                frame.cast(kcode, bricks, order, tf=tf, n_samples=N_SAMPLES)
+            else:
+                frame.clear()
+                frame.cast_partial(kcode, bricks, order, partial.data_ptr(), tf=tf, n_samples=N_SAMPLES)
+                swap.composite(partial, frame)
+
+        def frame_e2e():
+            if world == 1:
+                frame.render(kcode, bricks, order, img_host, zbuffer=zb_host, tf=tf, n_samples=N_SAMPLES)
+            else:
+                frame.upload(img_host, zb_host)
+                frame.cast_partial(kcode, bricks, order, partial.data_ptr(), tf=tf, n_samples=N_SAMPLES)
+                swap.composite(partial, frame)
+                if rank == 0:
+                    frame.download(img_host)
+                else:
+                    ctx.synchronize()
+
+        def timed(fn, steps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
+        for _ in range(max(args.warmup, 3)):
+            frame_device()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        ms_total = timed(frame_device, args.steps)
+        clk = clocks.stop() if rank == 0 else None
+        ms_step = ms_total / args.steps
+
+        # kernel-only duration of the dominant (cast) kernel, CUDA events on its stream
+        kt = []
+        for _ in range(min(args.steps, 5)):
+            if world == 1:
+                frame.clear()
+                s = frame.cast(kcode, bricks, order, tf=tf, n_samples=N_SAMPLES, timed=True)
+            else:
+                s = frame.cast_partial(kcode, bricks, order, partial.data_ptr(), tf=tf, n_samples=N_SAMPLES, timed=True)
+            kt.append(s.kernel_ms)
+        kernel_ms = float(np.mean(kt))
+
+        for _ in range(2):
+            frame_e2e()
+        ms_e2e = timed(frame_e2e, args.steps) / args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src, sm_max = measured_peak()
+    elem = 4
+    c = 1 if kind == "vr" else 0
+    my_elems = float(np.prod([hi[a] - lo[a] + c for a in range(3)]))
+    alg_bytes = my_elems * elem + 2.0 * res * res * 32 + (res * res * 8 if True else 0)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    gs = total_samples / (ms_step * 1e-3) / 1e9
+    gs_e2e = total_samples / (ms_e2e * 1e-3) / 1e9
+    launches_per_step = 2 if world == 1 else 2 + swap.launches_per_composite
+    line = {
+        "metric": "Gsamples/s", "value": gs, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 samples / f64 traversal", "data": "synthetic",
+        "config": {"workload": args.workload, "cells": [n, n, n], "image": [res, res], "sampler": kind,
+                   "n_samples": N_SAMPLES if kind == "vr" else 1, "lens": "plane-parallel", "view": "default corner camera, width 1.5",
+                   "samples_per_frame": total_samples, "parallelism": "kd%d" % world,
+                   "l2": "brick (%.2f GB per rank) larger than L2; no flush needed" % (my_elems * elem / 1e9)},
+        "ms_per_frame": ms_step,
+        "e2e": {"value": gs_e2e, "unit": "Gsamples/s", "ms_per_frame": ms_e2e,
+                "h2d_bytes_per_step": res * res * 40, "d2h_bytes_per_step": res * res * 32,
+                "note": "host image+zbuffer in, host image out through ytb200_render; bricks device-resident across frames"},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": recorded_traffic(args.workload), "peak_source": peak_src, "kernel": "cast_kernel",
+                     "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
+                     "note": "volume-render cast is instruction-issue bound (7.7 samples per HBM byte), see `issue`"},
+        "issue": {"samples_per_s_per_sm": total_samples / world / (kernel_ms * 1e-3) / ctx.sm_count,
+                  "lane_slots_per_sample_at_sm_clock": (ctx.sm_count * 128 * (clk["sm_mhz"] or sm_max) * 1e6) / (my_samples / (kernel_ms * 1e-3))
+                  if clk else None},
+    }
+    if world == 1 and not args.no_cpu:
+        info = cpu_render_sample(kind, args.cpu_size, args.cpu_res, threads=0, repeats=2)
+        v = info["samples"] / info["seconds"] / 1e9
+        line["cpu_baseline"] = {"value": v, "unit": "Gsamples/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="northstar_vr_1024c_2048px", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-size", type=int, default=256)
+    ap.add_argument("--cpu-res", type=int, default=512)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+"""Object-space multi-GPU rendering: kd partition + ordered binary-swap compositing.
+
+Replaces ``AMRKDTree.reduce_tree_images`` (yt/utilities/amr_kdtree/amr_kdtree.py:297-323,
+amr_kdtools.py:6-50), which tree-reduces *full* fp64 images to one rank over MPI.  Here every
+rank renders its convex kd subtree into a per-pixel affine partial ``C -> A + B*C`` (SURVEY.md
+A.4), and log2(P) rounds of pairwise half-image exchanges (``torch.distributed`` P2P over
+NCCL/NVLink) with our compose kernel in between leave each rank with a fully composited 1/P
+strip; strips are then gathered on rank 0.  Per-GPU traffic is (1 - 1/P) of one partial image.
+
+Order: the partner pair of round j are the two children of the kd split at depth k-1-j.  Which
+child is applied first follows the reference's traversal rule (amr_kdtools.pyx:708-755):
+``viewpoint[dim] <= pos`` -> the upper child is farther and therefore composited first.
+"""
+import numpy as np
+
+
+def bit_reverse(x, bits):
+    r = 0
+    for _ in range(bits):
+        r = (r << 1) | (x & 1)
+        x >>= 1
+    return r
+
+
+def plan_binary_swap(rank, world, n_pixels, path, viewpoint):
+    """Pure schedule: list of rounds and the final strip of `rank`.
+
+    path: [(axis, split_pos, is_upper)] from the root split to this rank's leaf (len = log2(world)).
+    Returns (rounds, (p0, p1)); each round is a dict with the partner, the pixel range kept
+    ("keep"), the range sent ("send") and whether this rank's content is applied first ("earlier").
+    """
+    k = int(round(np.log2(world))) if world > 1 else 0
+    if (1 << k) != world:
+        raise ValueError("binary swap needs a power-of-two number of ranks (got %d)" % world)
+    if len(path) != k:
+        raise ValueError("kd path length %d does not match log2(world)=%d" % (len(path), k))
+    p0, p1 = 0, int(n_pixels)
+    rounds = []
+    for j in range(k):
+        ax, pos, upper = path[k - 1 - j]
+        assert bool(upper) == bool((rank >> j) & 1), "rank bits must follow the kd path"
+        mid = p0 + (p1 - p0) // 2
+        keep_lower = ((rank >> j) & 1) == 0
+        keep = (p0, mid) if keep_lower else (mid, p1)
+        send = (mid, p1) if keep_lower else (p0, mid)
+        upper_first = bool(viewpoint[ax] <= pos)
+        rounds.append({"partner": rank ^ (1 << j), "keep": keep, "send": send,
+                       "earlier": bool(upper) == upper_first, "axis": ax, "pos": pos})
+        p0, p1 = keep
+    return rounds, (p0, p1)
+
+
+def strip_bounds(world, n_pixels):
+    """Final strip [p0, p1) of every rank (depends only on the rank bits)."""
+    k = int(round(np.log2(world))) if world > 1 else 0
+    out = []
+    for r in range(world):
+        p0, p1 = 0, int(n_pixels)
+        for j in range(k):
+            mid = p0 + (p1 - p0) // 2
+            p0, p1 = (p0, mid) if ((r >> j) & 1) == 0 else (mid, p1)
+        out.append((p0, p1))
+    return out
+
+
+class _DevArray:
+    """Zero-copy view of raw device memory for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class BinarySwap:
+    """Executes the schedule.  `compose(earlier, later, out)` and `apply(partial, image)` default to the
+    CUDA kernels behind the C ABI; tests inject torch-CPU versions to exercise the schedule over gloo."""
+
+    def __init__(self, ctx, nx, ny, path, viewpoint, rank, world, compose=None, apply=None, group=None):
+        import torch
+        self.torch = torch
+        self.ctx, self.nx, self.ny, self.rank, self.world, self.group = ctx, nx, ny, rank, world, group
+        self.npx = nx * ny
+        self.rounds, self.strip = plan_binary_swap(rank, world, self.npx, path, viewpoint)
+        self.strips = strip_bounds(world, self.npx)
+        self._compose = compose or self._compose_cuda
+        self._apply = apply or self._apply_cuda
+        self._recv = None
+        self.launches_per_composite = len(self.rounds) + 1
+
+    # -- CUDA kernels through the C ABI ---------------------------------------------------------------
+    def _compose_cuda(self, earlier, later, out):
+        from . import _lib as L
+        L.check(L.load().ytb200_partial_compose(self.ctx.handle, earlier.data_ptr(), later.data_ptr(), out.data_ptr(), out.shape[0]))
+
+    def _apply_cuda(self, partial, image):
+        from . import _lib as L
+        L.check(L.load().ytb200_partial_apply(self.ctx.handle, partial.data_ptr(), image.data_ptr(), image.shape[0]))
+
+    def _exchange(self, send, recv, partner):
+        dist = self.torch.distributed
+        ops = [dist.P2POp(dist.isend, send, partner, group=self.group), dist.P2POp(dist.irecv, recv, partner, group=self.group)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def composite_tensors(self, partial, image):
+        """partial: (npx, 8) tensor of this rank; image: (npx, 4) tensor holding the initial colours C_0
+        (only this rank's final strip is read).  Returns the strip (p0, p1) now final in `image`."""
+        torch = self.torch
+        cur = partial.view(self.npx, 8)
+        if self._recv is None or self._recv.device != cur.device:
+            self._recv = torch.empty((max(self.npx // 2 + 1, 1), 8), dtype=cur.dtype, device=cur.device)
+        for rd in self.rounds:
+            k0, k1 = rd["keep"]
+            s0, s1 = rd["send"]
+            recv = self._recv[: k1 - k0]
+            self._exchange(cur[s0:s1], recv, rd["partner"])
+            mine = cur[k0:k1]
+            if rd["earlier"]:
+                self._compose(mine, recv, mine)
+            else:
+                self._compose(recv, mine, mine)
+        p0, p1 = self.strip
+        self._apply(cur[p0:p1], image[p0:p1])
+        return p0, p1
+
+    def gather_strips(self, image, dst=0):
+        """Collect every rank's final strip of `image` (npx, 4) on rank `dst`."""
+        dist = self.torch.distributed
+        if self.world == 1:
+            return
+        ops = []
+        if self.rank == dst:
+            for r, (p0, p1) in enumerate(self.strips):
+                if r != dst and p1 > p0:
+                    ops.append(dist.P2POp(dist.irecv, image[p0:p1], r, group=self.group))
+        else:
+            p0, p1 = self.strip
+            if p1 > p0:
+                ops.append(dist.P2POp(dist.isend, image[p0:p1], dst, group=self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    # -- frame-level convenience used by the bench and the scene mirror -----------------------------------
+    def composite(self, partial, frame):
+        """Compose this rank's partial with all others and leave the final image in rank 0's frame.
+        The frame's device image must already hold the initial colours C_0 (``frame.clear()`` or
+        ``frame.upload()``), exactly what it held when the partial was cast."""
+        image = self.torch.as_tensor(_DevArray(frame.device_image, (self.npx, 4)), device=partial.device)
+        self.composite_tensors(partial, image)
+        self.gather_strips(image, 0)
