@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libytb200.so")
+LIB_PATH = os.environ.get("YTB200_LIB") or os.path.join(HERE, "libytb200.so")  # override: kernel experiments only
 
 PROJECTION, INTERPOLATED_PROJECTION, VOLUME_RENDER = 0, 1, 2
 LENS_PLANE_PARALLEL, LENS_PERSPECTIVE, LENS_GENERIC = 0, 1, 2

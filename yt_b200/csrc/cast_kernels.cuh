@@ -11,6 +11,9 @@
 namespace ytb {
 
 constexpr int TILE_I = 16, TILE_J = 16, CTA_THREADS = 256;
+#ifndef YTB_MIN_BLOCKS
+#define YTB_MIN_BLOCKS 2
+#endif
 enum { KIND_PROJ = 0, KIND_IPROJ = 1, KIND_VR = 2 };
 enum { TFM_NONE = 0, TFM_GENERAL = 1, TFM_COLOUR = 2 };
 
@@ -35,7 +38,7 @@ struct CellSampler {
     const DevTF *tf;
     TFShared64 t64;
     const float2 *pairs;
-    const float4 *colour;
+    ColourTable ct;
     // accumulators
     double acc[4];   // PROJ / IPROJ / EXACT VR
     double B64[4];
@@ -147,16 +150,14 @@ struct CellSampler {
                 acc[0] = fma(sum, dt64, acc[0]);
             } else {
                 if (TFM == TFM_COLOUR) {
-                    const float b0h = tf->b0_hi[0], b0l = tf->b0_lo[0], b1 = tf->b1_f[0], idb = tf->idbin_f[0];
-                    const int nb2 = tf->nbins[0] - 2;
                     if (tf->grey) {
                         for (int s = 0; s < n_samples; s++) {
-                            eval_colour32<PARTIAL, true>(colour, b0h, b0l, b1, idb, nb2, dt, trilinear(c, x, y, z), rgba, B);
+                            eval_colour32<PARTIAL, true>(ct, dt, trilinear(c, x, y, z), rgba, B);
                             x += sxs; y += sys; z += szs;
                         }
                     } else {
                         for (int s = 0; s < n_samples; s++) {
-                            eval_colour32<PARTIAL, false>(colour, b0h, b0l, b1, idb, nb2, dt, trilinear(c, x, y, z), rgba, B);
+                            eval_colour32<PARTIAL, false>(ct, dt, trilinear(c, x, y, z), rgba, B);
                             x += sxs; y += sys; z += szs;
                         }
                     }
@@ -233,7 +234,7 @@ __device__ __forceinline__ void make_ray(const DevCamera &cam, int vi, int vj, d
 }
 
 template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, YTB_MIN_BLOCKS)
 cast_kernel(const __grid_constant__ CastParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -244,7 +245,7 @@ cast_kernel(const __grid_constant__ CastParams p)
 
     CellSampler<KIND, EXACT, TFM, PARTIAL, NF1, T> smp;
     smp.tf = &p.tf;
-    smp.pairs = nullptr; smp.colour = nullptr;
+    smp.pairs = nullptr;
     smp.t64.values = smp.t64.d0 = smp.t64.dy = nullptr;
     // ---- stage the transfer-function tables into shared memory -------------------------------
     if (KIND == KIND_VR) {
@@ -256,10 +257,14 @@ cast_kernel(const __grid_constant__ CastParams p)
             }
             smp.t64.values = sv; smp.t64.d0 = sv + n; smp.t64.dy = sv + 2 * n;
         } else if (TFM == TFM_COLOUR) {
+            // replicate each bin's (r,g,b,a) row ncopy times: row stride = ncopy*16 B, copy k in bank group k
             float4 *sc = reinterpret_cast<float4 *>(smem_raw);
-            const int n = 2 * p.tf.nbins[0];
-            for (int i = tid; i < n; i += CTA_THREADS) sc[i] = p.tf.colour[i];
-            smp.colour = sc;
+            const int nb = p.tf.nbins[0], sh = p.tf.colour_copy_shift, ncopy = 1 << sh;
+            for (int i = tid; i < nb * ncopy; i += CTA_THREADS) sc[i] = p.tf.colour[i >> sh];
+            smp.ct.base = (unsigned)__cvta_generic_to_shared(sc) + (unsigned)(lane & (ncopy - 1)) * 16u;
+            smp.ct.row_shift = 4 + sh;
+            smp.ct.b0_hi = p.tf.b0_hi[0]; smp.ct.b0_lo = p.tf.b0_lo[0]; smp.ct.b1 = p.tf.b1_f[0];
+            smp.ct.idbin = p.tf.idbin_f[0]; smp.ct.nbins_m2 = nb - 2;
         } else {
             float2 *sp = reinterpret_cast<float2 *>(smem_raw);
             const int n = p.tf.total_bins;

@@ -54,8 +54,9 @@ struct DevTF {
     // fp32 (FAST): (value, next-value - value) pairs; bounds split hi/lo so x-b0 keeps fp64-ish accuracy
     float b0_hi[YTB_MAX_TABLES], b0_lo[YTB_MAX_TABLES], b1_f[YTB_MAX_TABLES], idbin_f[YTB_MAX_TABLES];
     const float2 *pairs;
-    // colour_fast payload: per bin (r,g,b,a) values and (dr,dg,db,da) increments
-    const float4 *colour;  // 2*nbins float4: [2*bin] = values, [2*bin+1] = increments
+    // colour_fast payload: one (r,g,b,a) row per bin; replicated 2^colour_copy_shift times in smem
+    const float4 *colour;
+    int colour_copy_shift;
 };
 
 struct CastParams {

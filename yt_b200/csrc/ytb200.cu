@@ -369,17 +369,13 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
     rc |= to_device(t, dy, &d.dy);
     rc |= to_device(t, pairs, &d.pairs);
     if (colour) {
-        std::vector<float4> col(2 * (size_t)nbins[0]);
-        for (int j = 0; j < nbins[0]; j++) {
-            float v[4], dv[4];
-            for (int c = 0; c < 4; c++) {
-                v[c] = (float)y[c][j];
-                dv[c] = j < nbins[0] - 1 ? (float)(y[c][j + 1] - y[c][j]) : 0.f;
-            }
-            col[2 * j] = make_float4(v[0], v[1], v[2], v[3]);
-            col[2 * j + 1] = make_float4(dv[0], dv[1], dv[2], dv[3]);
-        }
+        std::vector<float4> col((size_t)nbins[0]);
+        for (int j = 0; j < nbins[0]; j++)
+            col[j] = make_float4((float)y[0][j], (float)y[1][j], (float)y[2][j], (float)y[3][j]);
         rc |= to_device(t, col, &d.colour);
+        // bank-conflict-free replication factor, capped so the table stays <= 64 KiB of shared memory
+        d.colour_copy_shift = nbins[0] <= 512 ? 3 : nbins[0] <= 1024 ? 2 : nbins[0] <= 2048 ? 1 : 0;
+        if (nbins[0] > 4096) d.colour_fast = 0;
     }
     if (rc) { ytb200_tf_destroy(t); return rc; }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -627,7 +623,7 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
         if (kind == YTB200_VOLUME_RENDER) {
             const bool colour = !exact && nf1 && tf->d.colour_fast;
             if (exact) smem = (size_t)tf->d.total_bins * 3 * sizeof(double);
-            else if (colour) smem = (size_t)tf->d.nbins[0] * 2 * sizeof(float4);
+            else if (colour) smem = ((size_t)tf->d.nbins[0] << tf->d.colour_copy_shift) * sizeof(float4);
             else smem = (size_t)tf->d.total_bins * sizeof(float2);
             if (smem > 200 * 1024) return fail(E_UNSUPPORTED, "transfer function tables (%zu B) exceed shared memory", smem);
             if (colour) e = launch_kind<KIND_VR, TFM_COLOUR>(p, grid, smem, st, exact, f64, partial != nullptr, nf1);
