@@ -39,6 +39,7 @@ struct CellSampler {
     TFShared64 t64;
     const float2 *pairs;
     ColourTable ct;
+    ColourAcc ca;
     // accumulators
     double acc[4];   // PROJ / IPROJ / EXACT VR
     double B64[4];
@@ -150,17 +151,10 @@ struct CellSampler {
                 acc[0] = fma(sum, dt64, acc[0]);
             } else {
                 if (TFM == TFM_COLOUR) {
-                    if (tf->grey) {
-                        for (int s = 0; s < n_samples; s++) {
-                            eval_colour32<PARTIAL, true>(ct, dt, trilinear(c, x, y, z), rgba, B);
-                            x += sxs; y += sys; z += szs;
-                        }
-                    } else {
-                        for (int s = 0; s < n_samples; s++) {
-                            eval_colour32<PARTIAL, false>(ct, dt, trilinear(c, x, y, z), rgba, B);
-                            x += sxs; y += sys; z += szs;
-                        }
-                    }
+                    CornersP cp;
+                    load_corners_p(cp, (const T *)br->data[0] + offset, sx, sy);
+                    if (tf->grey) colour_cell_run<PARTIAL, true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+                    else colour_cell_run<PARTIAL, false>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
                 } else {
                     float dvs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     for (int s = 0; s < n_samples; s++) {
@@ -257,12 +251,11 @@ cast_kernel(const __grid_constant__ CastParams p)
             }
             smp.t64.values = sv; smp.t64.d0 = sv + n; smp.t64.dy = sv + 2 * n;
         } else if (TFM == TFM_COLOUR) {
-            // replicate each bin's (r,g,b,a) row ncopy times: row stride = ncopy*16 B, copy k in bank group k
+            // replicate each bin's (r,g,b,a) row COLOUR_COPIES times: copy k sits in 16-byte bank group k
             float4 *sc = reinterpret_cast<float4 *>(smem_raw);
-            const int nb = p.tf.nbins[0], sh = p.tf.colour_copy_shift, ncopy = 1 << sh;
-            for (int i = tid; i < nb * ncopy; i += CTA_THREADS) sc[i] = p.tf.colour[i >> sh];
-            smp.ct.base = (unsigned)__cvta_generic_to_shared(sc) + (unsigned)(lane & (ncopy - 1)) * 16u;
-            smp.ct.row_shift = 4 + sh;
+            const int nb = p.tf.nbins[0];
+            for (int i = tid; i < nb * COLOUR_COPIES; i += CTA_THREADS) sc[i] = p.tf.colour[i / COLOUR_COPIES];
+            smp.ct.base = (unsigned)__cvta_generic_to_shared(sc) + (unsigned)(lane & (COLOUR_COPIES - 1)) * 16u;
             smp.ct.b0_hi = p.tf.b0_hi[0]; smp.ct.b0_lo = p.tf.b0_lo[0]; smp.ct.b1 = p.tf.b1_f[0];
             smp.ct.idbin = p.tf.idbin_f[0]; smp.ct.nbins_m2 = nb - 2;
         } else {
@@ -299,6 +292,8 @@ cast_kernel(const __grid_constant__ CastParams p)
         smp.acc[c] = init[c]; smp.B64[c] = 1.0;
         smp.rgba[c] = (float)init[c]; smp.B[c] = 1.f;
     }
+    smp.ca.c01 = make_float2((float)init[0], (float)init[1]); smp.ca.c2 = (float)init[2]; smp.ca.c3 = (float)init[3];
+    smp.ca.b01 = make_float2(1.f, 1.f); smp.ca.b2 = 1.f; smp.ca.b3 = 1.f;
     smp.n_samples = p.n_samples;
     smp.inv_ns = 1.0 / (double)p.n_samples;
     smp.n_cells = 0;
@@ -343,6 +338,10 @@ cast_kernel(const __grid_constant__ CastParams p)
     if (!active) return;
     double out[4], Bout[4];
     if (KIND == KIND_VR && !EXACT) {
+        if (TFM == TFM_COLOUR) {
+            smp.rgba[0] = smp.ca.c01.x; smp.rgba[1] = smp.ca.c01.y; smp.rgba[2] = smp.ca.c2; smp.rgba[3] = smp.ca.c3;
+            smp.B[0] = smp.ca.b01.x; smp.B[1] = smp.ca.b01.y; smp.B[2] = smp.ca.b2; smp.B[3] = smp.ca.b3;
+        }
 #pragma unroll
         for (int c = 0; c < 4; c++) { out[c] = (double)smp.rgba[c]; Bout[c] = (double)smp.B[c]; }
         if (!PARTIAL && !p.tf.grey) out[3] = init[3];  // non-grey never touches alpha (H9)

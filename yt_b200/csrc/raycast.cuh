@@ -306,10 +306,11 @@ __device__ __forceinline__ void eval_transfer32(const DevTF &tf, const float2 *p
 // touch 8 distinct bank groups whatever their bins are: 4 wavefronts per load, the minimum.
 struct ColourTable {
     unsigned base;     // shared-space byte address of this lane's copy of bin 0
-    int row_shift;     // log2(bytes between consecutive bins) = 4 + log2(NCOPY)
     float b0_hi, b0_lo, b1, idbin;
     int nbins_m2;
 };
+constexpr int COLOUR_COPIES = 8;                      // replication factor
+constexpr unsigned COLOUR_ROW_BYTES = COLOUR_COPIES * 16;  // bytes between consecutive bins
 
 __device__ __forceinline__ float4 lds128(unsigned addr)
 {
@@ -318,37 +319,84 @@ __device__ __forceinline__ float4 lds128(unsigned addr)
     return v;
 }
 
-template <bool PARTIAL, bool GREY>
-__device__ __forceinline__ void eval_colour32(const ColourTable &ct, float dt, float x, float (&rgba)[4], float (&B)[4])
+// sm_100 packed fp32 (FFMA2/FMUL2): two lanes of fp32 per issue slot.  The cast kernel is
+// instruction-issue bound (ncu round 1: 82 % issue-active, 69 instr/sample), so halving the issue
+// slots of the paired arithmetic is the lever.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 bcast2(float a) { return make_float2(a, a); }
+
+// The 8 corners of a cell packed for paired z- and y-lerps.
+struct CornersP {
+    float2 p0, d0;  // (c000, c100) and their z-increments (c001-c000, c101-c100)
+    float2 p1, d1;  // (c010, c110) and their z-increments
+};
+
+template <typename T>
+__device__ __forceinline__ void load_corners_p(CornersP &c, const T *d, int sx, int sy)
 {
-    const float u = (x - ct.b0_hi) - ct.b0_lo;
-    // FIT_get_value's rejects (out of bounds, 0, NaN, inf) zero every table -> identity map; done
-    // by zeroing alpha instead of branching (RGB are weighted by alpha).
-    const bool valid = (u > 0.f) && (x < ct.b1) && (x != 0.f);
-    const float fb = u * ct.idbin;
-    int bin = (int)fb;                       // NaN -> 0
-    bin = max(0, min(bin, ct.nbins_m2));
-    const float fr = valid ? fb - (float)bin : 0.f;  // keeps NaN out of the (zero-weighted) RGB products
-    const unsigned a0 = ct.base + ((unsigned)bin << ct.row_shift);
-    const float4 v = lds128(a0), w = lds128(a0 + (1u << ct.row_shift));
-    const float ta_ = valid ? fmaf(fr, w.w - v.w, v.w) : 0.f;
-    const float tr = fmaf(fr, w.x - v.x, v.x) * ta_;
-    const float tg = fmaf(fr, w.y - v.y, v.y) * ta_;
-    const float tb = fmaf(fr, w.z - v.z, v.z) * ta_;
-    if (GREY) {
-        const float ta = fmaxf(fmaf(-dt, ta_, 1.f), 0.f);
-        rgba[0] = fmaf(ta, rgba[0], dt * tr);
-        rgba[1] = fmaf(ta, rgba[1], dt * tg);
-        rgba[2] = fmaf(ta, rgba[2], dt * tb);
-        rgba[3] = fmaf(ta, rgba[3], dt * ta_);
-        if (PARTIAL) { B[0] *= ta; B[1] *= ta; B[2] *= ta; B[3] *= ta; }
-    } else {
-        const float t0 = dt * tr, t1 = dt * tg, t2 = dt * tb;
-        const float a0_ = fmaxf(1.f - t0, 0.f), a1_ = fmaxf(1.f - t1, 0.f), a2_ = fmaxf(1.f - t2, 0.f);
-        rgba[0] = fmaf(a0_, rgba[0], t0);
-        rgba[1] = fmaf(a1_, rgba[1], t1);
-        rgba[2] = fmaf(a2_, rgba[2], t2);
-        if (PARTIAL) { B[0] *= a0_; B[1] *= a1_; B[2] *= a2_; }
+    const float a0 = (float)__ldg(d), a1 = (float)__ldg(d + 1);
+    const float b0 = (float)__ldg(d + sy), b1 = (float)__ldg(d + sy + 1);
+    const float e0 = (float)__ldg(d + sx), e1 = (float)__ldg(d + sx + 1);
+    const float f0 = (float)__ldg(d + sx + sy), f1 = (float)__ldg(d + sx + sy + 1);
+    c.p0 = make_float2(a0, e0); c.d0 = make_float2(a1 - a0, e1 - e0);
+    c.p1 = make_float2(b0, f0); c.d1 = make_float2(b1 - b0, f1 - f0);
+}
+
+// Accumulators of one ray on the ColorTransferFunction path: colour C and (PARTIAL) transmittance B.
+struct ColourAcc {
+    float2 c01; float c2, c3;
+    float2 b01; float b2, b3;
+};
+
+// All n_samples samples of one cell: trilinear value -> 4-table lookup -> composite
+// (image_samplers.pyx:480-487 + field_interpolation_tables.pxd:66-110, fp32).
+template <bool PARTIAL, bool GREY>
+__device__ __forceinline__ void colour_cell_run(const CornersP &c, const ColourTable &ct, int n_samples, float x, float y, float z,
+                                                float sx, float sy, float sz, float dt, ColourAcc &A)
+{
+    const float2 neg1 = make_float2(-1.f, -1.f), one2 = make_float2(1.f, 1.f);
+    float2 zz = bcast2(z), yy = bcast2(y);
+    const float2 szz = bcast2(sz), syy = bcast2(sy);
+#pragma unroll 2
+    for (int s = 0; s < n_samples; s++) {
+        // trilinear (fixed_interpolator.cpp:34-52): z pairs, y pair, x
+        const float2 va = fma2(zz, c.d0, c.p0);        // (v00, v10)
+        const float2 vb = fma2(zz, c.d1, c.p1);        // (v01, v11)
+        const float2 v = fma2(yy, fma2(va, neg1, vb), va);  // (v0, v1)
+        const float val = fmaf(x, v.y - v.x, v.x);
+        zz = add2(zz, szz); yy = add2(yy, syy); x += sx;
+        // FIT_get_value for the 4 tables at once; rejects (out of bounds, 0, NaN, inf) zero alpha,
+        // which zeroes the alpha-weighted RGB too -> identity map, no branch.
+        const float u = (val - ct.b0_hi) - ct.b0_lo;
+        const bool valid = (u > 0.f) && (val < ct.b1) && (val != 0.f);
+        const float fb = u * ct.idbin;
+        int bin = (int)fb;  // NaN -> 0
+        bin = max(0, min(bin, ct.nbins_m2));
+        const float fr = valid ? fb - (float)bin : 0.f;
+        const unsigned addr = ct.base + (unsigned)bin * COLOUR_ROW_BYTES;
+        const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
+        const float2 fr2 = bcast2(fr);
+        const float2 rg = fma2(fr2, fma2(make_float2(t0.x, t0.y), neg1, make_float2(t1.x, t1.y)), make_float2(t0.x, t0.y));
+        const float2 ba = fma2(fr2, fma2(make_float2(t0.z, t0.w), neg1, make_float2(t1.z, t1.w)), make_float2(t0.z, t0.w));
+        const float adt = (valid ? ba.y : 0.f) * dt;   // dt * alpha-table value
+        const float2 e01 = mul2(rg, bcast2(adt));      // dt * T_r, dt * T_g (RGB weighted by alpha)
+        const float e2 = ba.x * adt;
+        if (GREY) {
+            const float ta = fmaxf(1.f - adt, 0.f);
+            A.c01 = fma2(bcast2(ta), A.c01, e01);
+            A.c2 = fmaf(ta, A.c2, e2);
+            A.c3 = fmaf(ta, A.c3, adt);
+            if (PARTIAL) { A.b01 = mul2(A.b01, bcast2(ta)); A.b2 *= ta; A.b3 *= ta; }
+        } else {
+            float2 a01 = fma2(e01, neg1, one2);
+            a01.x = fmaxf(a01.x, 0.f); a01.y = fmaxf(a01.y, 0.f);
+            const float a2 = fmaxf(1.f - e2, 0.f);
+            A.c01 = fma2(a01, A.c01, e01);
+            A.c2 = fmaf(a2, A.c2, e2);
+            if (PARTIAL) { A.b01 = mul2(A.b01, a01); A.b2 *= a2; }
+        }
     }
 }
 

@@ -373,9 +373,9 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
         for (int j = 0; j < nbins[0]; j++)
             col[j] = make_float4((float)y[0][j], (float)y[1][j], (float)y[2][j], (float)y[3][j]);
         rc |= to_device(t, col, &d.colour);
-        // bank-conflict-free replication factor, capped so the table stays <= 64 KiB of shared memory
-        d.colour_copy_shift = nbins[0] <= 512 ? 3 : nbins[0] <= 1024 ? 2 : nbins[0] <= 2048 ? 1 : 0;
-        if (nbins[0] > 4096) d.colour_fast = 0;
+        // the fast path replicates every row 8x in shared memory (bank-conflict-free): <= 64 KiB
+        d.colour_copy_shift = 3;
+        if (nbins[0] > 512) d.colour_fast = 0;
     }
     if (rc) { ytb200_tf_destroy(t); return rc; }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
