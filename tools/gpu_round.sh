@@ -1,0 +1,20 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench lines, ncu launch list and one full capture of the cast kernel.
+# Usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag>
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
+tail -3 $OUT/pytest_gpu.log
+timeout 600 python bench.py > $OUT/bench_northstar.json 2> $OUT/bench_northstar.err; tail -c 3000 $OUT/bench_northstar.json
+timeout 300 python bench.py --workload cfg3_proj_1024c_2048px --no-cpu > $OUT/bench_cfg3.json 2> $OUT/bench_cfg3.err; tail -c 1500 $OUT/bench_cfg3.json
+timeout 300 python bench.py --workload cfg2_vr_512c_1024px --no-cpu > $OUT/bench_cfg2.json 2> $OUT/bench_cfg2.err; tail -c 1500 $OUT/bench_cfg2.json
+timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; tail -c 1000 $OUT/bench_reference.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'cast_kernel|count_kernel|extent_kernel|fill_f64|compose_kernel|apply_kernel|f64_to_f32' -c 400 --csv --log-file $OUT/launches_northstar.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/ncu_launch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:cast_kernel -s 2 -c 1 -o $OUT/prof_vr \
+    python bench.py --steps 1 --warmup 3 --no-cpu > $OUT/ncu_full_vr.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:cast_kernel -s 2 -c 1 -o $OUT/prof_proj \
+    python bench.py --workload cfg3_proj_1024c_2048px --steps 1 --warmup 3 --no-cpu > $OUT/ncu_full_proj.log 2>&1
+ls -la $OUT
