@@ -152,6 +152,28 @@ int ytb200_render(ytb200_frame *f, int kind, const ytb200_brickset *set, const i
                   const ytb200_tf *tf, int n_samples, int precision, const double *zbuffer_host,
                   double *image_host_inout, ytb200_stats *stats);
 
+/* ---- AMR kd-tree: brick decomposition + view-order traversal, host side -----------------------
+ * Replaces yt/utilities/lib/amr_kdtools.pyx (Node.add_grids/insert_grids/split_grids/
+ * kdtree_get_choices 136-458,756-823; kd_traverse/viewpoint_traverse 102-111,612-622,708-755) and
+ * the Tree wrapper of yt/utilities/amr_kdtree/amr_kdtree.py:63-118.  Node numbering, split choices
+ * and leaf order are the reference's; one call returns the whole ordered leaf list. */
+typedef struct ytb200_kdtree ytb200_kdtree;
+const char *ytb200_kdtree_last_error(void);
+/* Tree.__init__: trunk = Node(None, None, None, left, right, -1, 1); (rank, size) as comm_rank/comm_size */
+int ytb200_kdtree_create(const double left[3], const double right[3], int rank, int size, ytb200_kdtree **out);
+int ytb200_kdtree_destroy(ytb200_kdtree *t);
+/* Tree.add_grids for one refinement level: gles/gres are (n,3) C-order, gids the grid ids */
+int ytb200_kdtree_add_grids(ytb200_kdtree *t, int64_t n, const double *gles, const double *gres, const int64_t *gids);
+int64_t ytb200_kdtree_node_count(const ytb200_kdtree *t);
+/* Dump every node (arrays of node_count entries; any pointer may be NULL): heap node_id, grid id
+ * (-1 none), child indices (-1 none), split (dim -1 / pos NaN for leaves), edges (n,3). */
+int ytb200_kdtree_nodes(const ytb200_kdtree *t, int64_t *node_id, int64_t *grid, int32_t *left, int32_t *right,
+                        int32_t *split_dim, double *split_pos, double *left_edge, double *right_edge);
+/* Node.kd_traverse(viewpoint): indices (into the node dump) of the leaves that carry a grid, farthest
+ * from `viewpoint` first; viewpoint NULL = depth-first left-to-right.  Returns the count (or <0);
+ * `out` may be NULL to query the count. */
+int64_t ytb200_kdtree_traverse(const ytb200_kdtree *t, const double *viewpoint, int32_t *out, int64_t cap);
+
 /* Pinned host memory for the image / z-buffer (cudaHostAlloc). */
 int ytb200_host_alloc(int64_t bytes, void **out);
 int ytb200_host_free(void *p);

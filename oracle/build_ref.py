@@ -10,6 +10,7 @@ Cython extension modules that make up yt's software ray caster:
     yt/utilities/lib/lenses.pyx              (extent + ray generation)
     yt/utilities/lib/_octree_raytracing.pyx  (cimported by image_samplers.pyx:34)
     yt/utilities/lib/amr_kdtools.pyx         (kd-tree Node, view-order traversal)
+    yt/utilities/lib/interpolators.pyx       (ghost_zone_interpolate: no-ghost vertex centring)
   + yt/utilities/lib/fixed_interpolator.cpp  (offset_interpolate)
 
 Outputs (``.so`` files, generated C++ and object files) go ONLY under
@@ -28,7 +29,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 
 MODS = ["image_samplers", "grid_traversal", "partitioned_grid", "lenses",
-        "_octree_raytracing", "amr_kdtools"]
+        "_octree_raytracing", "amr_kdtools", "interpolators"]
 NEED_FIXED_INTERP = {"image_samplers", "partitioned_grid"}
 
 

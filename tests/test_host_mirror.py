@@ -1,0 +1,112 @@
+"""Host-side mirror of the scene graph: loaders, vertex centring, default transfer function, wiring.
+No GPU needed (nothing here casts a ray)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import yt_b200 as yt
+from oracle import oracle as O
+from yt_b200 import loaders
+from yt_b200.volume_rendering import ColorTransferFunction, ProjectionTransferFunction, Scene, ZBuffer
+from yt_b200.volume_rendering.image_array import ImageArray
+from yt_b200.volume_rendering.render_source import KDTreeVolumeSource
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("shape", [(8, 8, 8), (5, 9, 3), (2, 2, 2), (16, 4, 7)])
+def test_vertex_centring_matches_reference_ghost_zone_interpolate(shape):
+    ref_dir = os.path.join(os.path.dirname(os.path.abspath(O.__file__)), "_ref")
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    from yt.utilities.lib.interpolators import ghost_zone_interpolate
+    cells = np.random.default_rng(5).random(shape)
+    want = np.zeros(tuple(s + 1 for s in shape))
+    ghost_zone_interpolate(1, cells, np.array([0.5] * 3), want, np.zeros(3))  # grid_patch.py:284-296
+    got = loaders.vertex_centre_no_ghost(cells)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 4e-16 * np.abs(want).max() * 8
+
+
+def test_load_uniform_grid_and_pieces():
+    arr = np.random.default_rng(0).random((12, 8, 10))
+    ds = yt.load_uniform_grid({"density": arr}, arr.shape, nprocs=6, bbox=np.array([[0, 3.0], [-1, 1], [0, 5]]))
+    assert len(ds.index.grids) == 6
+    assert sum(int(np.prod(g.ActiveDimensions)) for g in ds.index.grids) == arr.size
+    total = np.zeros_like(arr)
+    for g in ds.index.grids:
+        lo = g.get_global_startindex()
+        hi = lo + g.ActiveDimensions
+        total[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] += g["density"]
+    assert np.array_equal(total, arr)
+    assert ds.field_info[("stream", "density")].take_log
+    assert ds._resolve(("gas", "density")) == ("stream", "density")
+    lo, hi = ds.all_data().quantities["Extrema"]("density", non_zero=True)
+    assert lo == arr.min() and hi == arr.max()
+
+
+def test_amr_child_mask_and_blocks():
+    from yt_b200 import synthetic
+    g, dims = synthetic.nested_amr_grids(base_cells=16, tile=8, levels=2, seed=1)
+    ds = yt.load_amr_grids(g, dims)
+    covered = sum(int((1 - gr.child_mask).sum()) for gr in ds.index.grids if gr.Level == 0)
+    assert covered == 8 ** 3  # the central half (per axis) of a 16^3 base is refined
+    fine = [gr for gr in ds.index.grids if gr.Level == 1]
+    assert all(gr.Parent is not None for gr in fine)
+    assert all(gr.child_mask.all() for gr in fine)
+
+
+def test_default_transfer_function_follows_the_helper_recipe():
+    arr = np.random.default_rng(1).random((8, 8, 8)) + 0.5
+    ds = yt.load_uniform_grid({"density": arr}, arr.shape)
+    sc = yt.create_scene(ds)
+    src = sc.get_source()
+    assert isinstance(src, KDTreeVolumeSource) and src.log_field and src.num_samples == 10
+    tf = src.transfer_function
+    assert isinstance(tf, ColorTransferFunction) and tf.nbins == 512 and not tf.grey_opacity
+    assert np.allclose(tf.x_bounds, np.log10([arr.min(), arr.max()]))
+    assert len(tf.features) == 10
+    # alpha table rescaled so that its mean is 2 (transfer_function_helper.py:112-114)
+    assert abs(tf.alpha.y.mean() - 2.0) < 1e-12
+    cam = sc.camera
+    assert np.array_equal(cam.position, ds.domain_right_edge) and np.array_equal(cam.focus, ds.domain_center)
+    assert np.allclose(cam.width, 1.5) and cam.resolution == (512, 512)
+    assert cam.lens.lens_type == "plane-parallel"
+    src.set_log(False)
+    assert src._transfer_function is None and not src._volume_valid
+    src.set_transfer_function(ProjectionTransferFunction())
+    assert src.sampler_type == "projection"
+    with pytest.raises(RuntimeError):
+        src.set_transfer_function("viridis")
+
+
+def test_zbuffer_merge_and_image_rescale(tmp_path):
+    rng = np.random.default_rng(2)
+    a = ZBuffer(rng.random((6, 5, 4)), rng.random((6, 5)))
+    b = ZBuffer(rng.random((6, 5, 4)), rng.random((6, 5)))
+    c = a + b
+    near = a.z < b.z
+    assert np.array_equal(c.rgba[near], a.rgba[near]) and np.array_equal(c.rgba[~near], b.rgba[~near])
+    assert np.array_equal(c.z, np.minimum(a.z, b.z))
+    im = ImageArray(rng.random((7, 9, 4)) * 3.0)
+    r = im.rescale(inline=False)
+    assert abs(np.asarray(r[:, :, :3]).sum(axis=2).max() - 1.0) < 1e-12 or np.asarray(r).max() == 1.0
+    assert np.asarray(r[:, :, 3]).max() == 1.0
+    fn = im.write_png(str(tmp_path / "x.png"), sigma_clip=2.0)
+    data = open(fn, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n" and b"IEND" in data[-12:]
+
+
+def test_scene_bookkeeping():
+    arr = np.random.default_rng(3).random((4, 4, 4)) + 0.1
+    ds = yt.load_uniform_grid({"density": arr}, arr.shape)
+    sc = Scene()
+    src = yt.create_volume_source(ds, "density")
+    sc.add_source(src)
+    sc.add_camera(ds, lens_type="perspective")
+    assert sc.get_source(0) is src and sc["source_00"] is src
+    assert list(k for k, _ in sc.transparent_sources) == ["source_00"] and list(sc.opaque_sources) == []
+    assert sc.camera.lens.lens_type == "perspective"
+    with pytest.raises(RuntimeError):
+        sc.add_camera(ds, lens_type="no-such-lens")

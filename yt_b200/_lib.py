@@ -77,6 +77,13 @@ SIGNATURES = {
     "ytb200_partial_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "ytb200_render": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, i64p, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p, C.POINTER(Stats)]),
+    "ytb200_kdtree_last_error": (C.c_char_p, []),
+    "ytb200_kdtree_create": (C.c_int, [dp, dp, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "ytb200_kdtree_destroy": (C.c_int, [C.c_void_p]),
+    "ytb200_kdtree_add_grids": (C.c_int, [C.c_void_p, C.c_int64, dp, dp, i64p]),
+    "ytb200_kdtree_node_count": (C.c_int64, [C.c_void_p]),
+    "ytb200_kdtree_nodes": (C.c_int, [C.c_void_p, i64p, i64p, i32p, i32p, i32p, dp, dp, dp]),
+    "ytb200_kdtree_traverse": (C.c_int64, [C.c_void_p, dp, i32p, C.c_int64]),
     "ytb200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "ytb200_host_free": (C.c_int, [C.c_void_p]),
 }

@@ -3,7 +3,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "ytb200.cu")
+SRC = [os.path.join(HERE, "csrc", "ytb200.cu"), os.path.join(HERE, "csrc", "kdtree.cpp")]
 OUT = os.path.join(HERE, "libytb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -12,7 +12,7 @@ FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-li
 
 def sources():
     d = os.path.join(HERE, "csrc")
-    return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cu", ".cuh"))] + [
+    return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cu", ".cuh", ".cpp"))] + [
         os.path.join(os.path.dirname(HERE), "include", "ytb200.h")]
 
 
@@ -23,7 +23,7 @@ def is_current():
 def build(force=False, verbose=False):
     if is_current() and not force:
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
     subprocess.check_call(cmd)
     return OUT
 

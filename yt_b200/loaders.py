@@ -1,0 +1,289 @@
+"""In-memory ("stream") grid datasets: ``load_uniform_grid`` / ``load_amr_grids``.
+
+Only what feeds the ray caster is restated from the reference: the grid hierarchy
+(yt/loaders.py:204-448 uniform, 450-688 AMR; yt/frontends/stream), the no-ghost vertex
+centring that turns cell data into brick data (grid_patch.py:270-296 ->
+interpolators.pyx:177-227) and the child mask used by the off-axis projection loop
+(off_axis_projection.py:506-515).  Everything is in ``code_length``; there is no unit system.
+"""
+import numpy as np
+
+#: stream fields the reference renders in log space by default (their FieldInfo.take_log)
+LOG_FIELDS = {"density", "dark_matter_density", "temperature", "pressure", "number_density",
+              "thermal_energy", "metal_density", "entropy"}
+
+
+class FieldInfo:
+    def __init__(self, name, take_log, units=""):
+        self.name, self.take_log, self.units = name, bool(take_log), units
+
+    def get_label(self):
+        return self.name[1]
+
+
+def vertex_centre_no_ghost(cells):
+    """ghost_zone_interpolate(rf=1, input_left=0.5, output_left=0) of interpolators.pyx:177-227:
+    trilinear interpolation of cell centres onto vertices, linearly extrapolated at the faces."""
+    out = np.asarray(cells, dtype="float64")
+    for ax in range(3):
+        n = out.shape[ax]
+        r = np.arange(n + 1, dtype="float64") - 0.5
+        i = np.clip(np.trunc(r).astype("int64"), 0, max(n - 2, 0))
+        xp = r - i
+        lo = np.take(out, i, axis=ax)
+        hi = np.take(out, np.minimum(i + 1, n - 1), axis=ax)
+        shape = [1, 1, 1]
+        shape[ax] = n + 1
+        xp = xp.reshape(shape)
+        out = lo * (1.0 - xp) + hi * xp
+    return np.ascontiguousarray(out)
+
+
+class Grid:
+    """One grid patch (AMRGridPatch): cell-centred fields on ``ActiveDimensions`` cells."""
+    _id_offset = 0
+
+    def __init__(self, gid, level, left_edge, right_edge, dims, fields, ds):
+        self.id = int(gid)
+        self.Level = int(level)
+        self.LeftEdge = np.array(left_edge, dtype="float64")
+        self.RightEdge = np.array(right_edge, dtype="float64")
+        self.ActiveDimensions = np.array(dims, dtype="int32")
+        self.dds = (self.RightEdge - self.LeftEdge) / self.ActiveDimensions
+        self.fields = fields
+        self.ds = ds
+        self.Children = []
+        self.Parent = None
+        self._child_mask = None
+
+    def __getitem__(self, field):
+        return self.fields[self.ds._resolve(field)]
+
+    def clear_data(self):
+        pass
+
+    def get_global_startindex(self):
+        return np.rint((self.LeftEdge - self.ds.domain_left_edge) / self.dds).astype("int64")
+
+    @property
+    def child_mask(self):
+        """1 where a cell is not covered by a finer grid (grid_patch.py child_mask)."""
+        if self._child_mask is None:
+            m = np.ones(tuple(self.ActiveDimensions), dtype="uint8")
+            for c in self.Children:
+                lo = np.clip(np.rint((c.LeftEdge - self.LeftEdge) / self.dds).astype("int64"), 0, self.ActiveDimensions)
+                hi = np.clip(np.rint((c.RightEdge - self.LeftEdge) / self.dds).astype("int64"), 0, self.ActiveDimensions)
+                m[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = 0
+            self._child_mask = m
+        return self._child_mask
+
+    def get_vertex_centered_data(self, fields, smoothed=True, no_ghost=False):
+        if not no_ghost:
+            raise NotImplementedError("ghost-zone vertex centring is not part of the B200 hot path yet (SURVEY.md 8f rank 1); "
+                                      "use no_ghost=True (VolumeSource.use_ghost_zones = False, the reference default)")
+        return {f: vertex_centre_no_ghost(self[f]) for f in set(fields)}
+
+    def __repr__(self):
+        return "Grid_%04d (%s)" % (self.id, tuple(self.ActiveDimensions))
+
+
+class GridIndex:
+    def __init__(self, grids):
+        self.grids = np.empty(len(grids), dtype=object)
+        for i, g in enumerate(grids):
+            self.grids[i] = g
+        self.max_level = max(g.Level for g in grids)
+        self.num_grids = len(grids)
+
+    def get_smallest_dx(self):
+        return min(g.dds.min() for g in self.grids)
+
+    def select_grids(self, level):
+        return [g for g in self.grids if g.Level == level]
+
+
+class _Quantities(dict):
+    def __init__(self, src):
+        super().__init__()
+        self["Extrema"] = src._extrema
+
+
+class AllData:
+    """``ds.all_data()``: the whole domain as a data source (no selector: every cell is in)."""
+    selector = None
+
+    def __init__(self, ds):
+        self.ds = self.pf = ds
+        self.quantities = _Quantities(self)
+
+    @property
+    def blocks(self):
+        for g in self.ds.index.grids:
+            yield g, g.child_mask.astype(bool)
+
+    def _determine_fields(self, fields):
+        if isinstance(fields, (str, tuple)):
+            fields = [fields]
+        return [self.ds._resolve(f) for f in fields]
+
+    def _extrema(self, field, non_zero=False):
+        key = self.ds._resolve(field)
+        lo, hi = np.inf, -np.inf
+        for g, mask in self.blocks:
+            v = g.fields[key][mask]
+            if non_zero:
+                v = v[v > 0]
+            if v.size:
+                lo, hi = min(lo, v.min()), max(hi, v.max())
+        return np.float64(lo), np.float64(hi)
+
+    def all_data(self):
+        return self
+
+    def __repr__(self):
+        return "YTRegion (%s)" % self.ds
+
+
+class StreamDataset:
+    """The slice of ``yt.frontends.stream.StreamDataset`` the volume renderer touches."""
+
+    def __init__(self, grids_spec, domain_dimensions, bbox, refine_by=2, periodicity=(True, True, True), name="stream"):
+        self.domain_dimensions = np.array(domain_dimensions, dtype="int64")
+        bbox = np.array(bbox, dtype="float64")
+        self.domain_left_edge = bbox[:, 0].copy()
+        self.domain_right_edge = bbox[:, 1].copy()
+        self.domain_width = self.domain_right_edge - self.domain_left_edge
+        self.domain_center = 0.5 * (self.domain_left_edge + self.domain_right_edge)
+        self.refine_by = refine_by
+        self.periodicity = tuple(periodicity)
+        self.basename = name
+        self.field_info = {}
+        self.field_list = []
+        grids = []
+        for gid, spec in enumerate(grids_spec):
+            fields = {}
+            for k, v in spec["fields"].items():
+                key = k if isinstance(k, tuple) else ("stream", k)
+                arr = np.ascontiguousarray(v, dtype="float64")
+                if arr.shape != tuple(int(d) for d in spec["dimensions"]):
+                    raise RuntimeError("field %s has shape %s, grid dimensions are %s" % (k, arr.shape, tuple(spec["dimensions"])))
+                fields[key] = arr
+                if key not in self.field_info:
+                    self.field_info[key] = FieldInfo(key, key[1] in LOG_FIELDS)
+                    self.field_list.append(key)
+            grids.append(Grid(gid, spec["level"], spec["left_edge"], spec["right_edge"], spec["dimensions"], fields, self))
+        self.index = GridIndex(grids)
+        self._link_children()
+        self.derived_field_list = list(self.field_list)
+        self.default_field = self._pick_default()
+        self.unit_registry = None
+
+    # -- field names: "density", ("gas", "density") and ("stream", "density") all name the same array -------
+    def _resolve(self, field):
+        if isinstance(field, tuple) and field in self.field_info:
+            return field
+        name = field[1] if isinstance(field, tuple) else field
+        hits = [k for k in self.field_list if k[1] == name]
+        if len(hits) != 1:
+            raise KeyError("Could not find field %r in %s." % (field, self))
+        return hits[0]
+
+    def _get_field_info(self, field):
+        return self.field_info[self._resolve(field)]
+
+    def _pick_default(self):
+        for k in self.field_list:
+            if k[1] == "density":
+                return k
+        return self.field_list[0]
+
+    def _link_children(self):
+        """Parent/child links: a grid one level finer whose box lies inside the coarser one."""
+        by_level = {}
+        for g in self.index.grids:
+            by_level.setdefault(g.Level, []).append(g)
+        for lvl, gs in by_level.items():
+            for g in gs:
+                for c in by_level.get(lvl + 1, []):
+                    eps = 1e-12 * self.domain_width
+                    if np.all(c.LeftEdge >= g.LeftEdge - eps) and np.all(c.RightEdge <= g.RightEdge + eps):
+                        g.Children.append(c)
+                        c.Parent = g
+
+    def all_data(self):
+        return AllData(self)
+
+    def __repr__(self):
+        return self.basename
+
+
+def _split_counts(shape, nprocs):
+    """Processor grid for ``nprocs`` pieces: repeatedly halve (or divide by the smallest prime factor) the
+    axis with the most cells per piece.  (The reference balances surface/volume in decompose.py:get_psize;
+    any cell-aligned split yields the same image -- SURVEY.md finding 6.)"""
+    psize = [1, 1, 1]
+    n = int(nprocs)
+    f = 2
+    factors = []
+    while n > 1:
+        while n % f == 0:
+            factors.append(f)
+            n //= f
+        f += 1
+    for f in sorted(factors, reverse=True):
+        ax = int(np.argmax([shape[a] / psize[a] for a in range(3)]))
+        psize[ax] *= f
+    return psize
+
+
+def load_uniform_grid(data, domain_dimensions, length_unit=None, bbox=None, nprocs=1, sim_time=0.0,
+                      periodicity=(True, True, True), geometry="cartesian", **kwargs):
+    """One level-0 grid (or ``nprocs`` cell-aligned pieces of it) holding ``data`` (loaders.py:204-448)."""
+    if geometry != "cartesian":
+        raise NotImplementedError("only cartesian geometry reaches the ray caster")
+    dims = np.array(domain_dimensions, dtype="int64")
+    if bbox is None:
+        bbox = np.array([[0.0, 1.0], [0.0, 1.0], [0.0, 1.0]])
+    bbox = np.array(bbox, dtype="float64")
+    le, re = bbox[:, 0], bbox[:, 1]
+    fields = {}
+    for k, v in data.items():
+        if isinstance(v, tuple):  # (array, units)
+            v = v[0]
+        fields[k] = np.asarray(v)
+    specs = []
+    if nprocs == 1:
+        specs.append({"level": 0, "left_edge": le, "right_edge": re, "dimensions": dims, "fields": fields})
+    else:
+        psize = _split_counts(dims, nprocs)
+        edges = [np.linspace(0, dims[a], psize[a] + 1).astype("int64") for a in range(3)]
+        dds = (re - le) / dims
+        for i in range(psize[0]):
+            for j in range(psize[1]):
+                for k in range(psize[2]):
+                    lo = np.array([edges[0][i], edges[1][j], edges[2][k]])
+                    hi = np.array([edges[0][i + 1], edges[1][j + 1], edges[2][k + 1]])
+                    sub = {f: v[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] for f, v in fields.items()}
+                    specs.append({"level": 0, "left_edge": le + lo * dds, "right_edge": le + hi * dds,
+                                  "dimensions": hi - lo, "fields": sub})
+    return StreamDataset(specs, dims, bbox, periodicity=periodicity, name="UniformGridData")
+
+
+def load_amr_grids(grid_data, domain_dimensions, bbox=None, sim_time=0.0, length_unit=None, periodicity=(True, True, True),
+                   geometry="cartesian", refine_by=2, **kwargs):
+    """A hierarchy of grid patches given as dicts with ``left_edge``, ``right_edge``, ``level``,
+    ``dimensions`` and one array per field (loaders.py:450-688)."""
+    if geometry != "cartesian":
+        raise NotImplementedError("only cartesian geometry reaches the ray caster")
+    dims = np.array(domain_dimensions, dtype="int64")
+    if bbox is None:
+        bbox = np.array([[0.0, 1.0], [0.0, 1.0], [0.0, 1.0]])
+    specs = []
+    for g in grid_data:
+        g = dict(g)
+        spec = {"left_edge": g.pop("left_edge"), "right_edge": g.pop("right_edge"), "level": g.pop("level"),
+                "dimensions": g.pop("dimensions")}
+        g.pop("number_of_particles", None)
+        spec["fields"] = {k: (v[0] if isinstance(v, tuple) else v) for k, v in g.items()}
+        specs.append(spec)
+    return StreamDataset(specs, dims, bbox, refine_by=refine_by, periodicity=periodicity, name="AMRGridData")

@@ -70,3 +70,30 @@ def cell_slab(n, lo, hi, seed, device):
 def host_cells(n, seed):
     """Small host-side fp64 volume for the CPU baseline sample (numpy generator; not the device field)."""
     return np.random.default_rng(seed).random((n, n, n))
+
+
+def nested_amr_grids(base_cells=32, tile=8, levels=4, seed=0, refine_by=2, field="density"):
+    """Host-side nested-box AMR hierarchy in ``load_amr_grids`` form (BASELINE.json config 4).
+
+    Level 0 tiles the unit domain (``base_cells``^3 cells) with ``tile``^3-cell grids; every finer
+    level refines the central half (per axis) of the previous level's region, again tiled by
+    ``tile``^3-cell grids aligned to parent cell edges.  Data are U[0,1) * 2^level from
+    ``default_rng(seed)`` drawn grid by grid."""
+    rng = np.random.default_rng(seed)
+    out = []
+    lo, hi = 0.0, 1.0
+    for lvl in range(levels):
+        n = base_cells * refine_by ** lvl          # cells across the whole domain at this level
+        dx = 1.0 / n
+        c0, c1 = int(round(lo * n)), int(round(hi * n))
+        for i in range(c0, c1, tile):
+            for j in range(c0, c1, tile):
+                for k in range(c0, c1, tile):
+                    dims = [min(tile, c1 - i), min(tile, c1 - j), min(tile, c1 - k)]
+                    out.append({"left_edge": np.array([i, j, k]) * dx,
+                                "right_edge": (np.array([i, j, k]) + dims) * dx,
+                                "level": lvl, "dimensions": np.array(dims, dtype="int64"),
+                                field: rng.random(tuple(dims)) * 2.0 ** lvl + 0.05})
+        q = (hi - lo) / 4.0
+        lo, hi = lo + q, hi - q
+    return out, [base_cells] * 3

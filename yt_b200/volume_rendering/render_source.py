@@ -1,0 +1,287 @@
+"""Render sources -- yt/visualization/volume_rendering/render_source.py.
+
+``VolumeSource`` / ``KDTreeVolumeSource`` (209-616) with the reference's properties, setters and
+``render``/``finalize_image`` contract.  The brick loop of ``render`` (594-597,
+``for brick in volume.traverse(viewpoint): sampler(brick)``) is handed to the device as ONE launch:
+all kd-tree leaves are kept resident as a brick table and only the view order is recomputed per
+frame (``batched=True``, the default); ``batched=False`` drives the sampler brick by brick exactly
+like the reference does.
+"""
+import abc
+
+import numpy as np
+
+from ..amr_kdtree import AMRKDTree
+from .transfer_function_helper import TransferFunctionHelper
+from .transfer_functions import ColorTransferFunction, ProjectionTransferFunction, TransferFunction
+from .utils import data_source_or_all, new_interpolated_projection_sampler, new_projection_sampler, new_volume_render_sampler
+from .zbuffer_array import ZBuffer
+
+
+def invalidate_volume(f):
+    def wrapper(*args, **kwargs):
+        ret = f(*args, **kwargs)
+        obj = args[0]
+        if isinstance(obj._transfer_function, ProjectionTransferFunction):
+            obj.sampler_type = "projection"
+            obj._log_field = False
+            obj._use_ghost_zones = False
+        del obj.volume
+        obj._volume_valid = False
+        return ret
+    return wrapper
+
+
+def validate_volume(f):
+    def wrapper(*args, **kwargs):
+        obj = args[0]
+        fields = [obj.field]
+        log_fields = [obj.log_field]
+        if obj.weight_field is not None:
+            fields.append(obj.weight_field)
+            log_fields.append(obj.log_field)
+        if not obj._volume_valid:
+            obj.volume.set_fields(fields, log_fields, no_ghost=(not obj.use_ghost_zones))
+        obj._volume_valid = True
+        return f(*args, **kwargs)
+    return wrapper
+
+
+class RenderSource(abc.ABC):
+    volume_method = None
+
+    def __init__(self):
+        self.opaque = False
+        self.zbuffer = None
+
+    @abc.abstractmethod
+    def render(self, camera, zbuffer=None):
+        pass
+
+    @abc.abstractmethod
+    def _validate(self):
+        pass
+
+
+class OpaqueSource(RenderSource):
+    def __init__(self):
+        super().__init__()
+        self.opaque = True
+
+    def set_zbuffer(self, zbuffer):
+        self.zbuffer = zbuffer
+
+
+def create_volume_source(data_source, field):
+    data_source = data_source_or_all(data_source)
+    if hasattr(data_source.ds.index, "grids"):
+        return KDTreeVolumeSource(data_source, field)
+    raise NotImplementedError("only grid (kd-tree) datasets are on the B200 hot path")
+
+
+class VolumeSource(RenderSource, abc.ABC):
+    _image = None
+    data_source = None
+
+    def __init__(self, data_source, field):
+        super().__init__()
+        self.data_source = data_source_or_all(data_source)
+        field = self.data_source._determine_fields(field)[0]
+        self.current_image = None
+        self.check_nans = False
+        self.num_threads = 0
+        self.num_samples = 10
+        self.sampler_type = "volume-render"
+        self.batched = True
+        self._volume_valid = False
+        self._volume = None
+        self._transfer_function = None
+        self._field = field
+        self._log_field = self.data_source.ds.field_info[field].take_log
+        self._use_ghost_zones = False
+        self._weight_field = None
+        self.tfh = TransferFunctionHelper(self.data_source.pf)
+        self.tfh.set_field(self.field)
+
+    # -- transfer function ------------------------------------------------------------------------------
+    @property
+    def transfer_function(self):
+        if self._transfer_function is not None:
+            return self._transfer_function
+        if self.tfh.tf is not None:
+            self._transfer_function = self.tfh.tf
+            return self._transfer_function
+        self.tfh.set_field(self.field)
+        self.tfh.set_log(self.log_field)
+        self.tfh.build_transfer_function()
+        self.tfh.setup_default()
+        self._transfer_function = self.tfh.tf
+        return self._transfer_function
+
+    @transfer_function.setter
+    def transfer_function(self, value):
+        self.tfh.tf = None
+        valid_types = (TransferFunction, ColorTransferFunction, ProjectionTransferFunction, type(None))
+        if not isinstance(value, valid_types):
+            raise RuntimeError("transfer_function not a valid type, received object of type %s" % type(value))
+        if isinstance(value, ProjectionTransferFunction):
+            self.sampler_type = "projection"
+            if self._volume is not None:
+                self._volume_valid = False
+        self._transfer_function = value
+
+    # -- volume ---------------------------------------------------------------------------------------------
+    @property
+    def volume(self):
+        return self._get_volume()
+
+    @volume.setter
+    def volume(self, value):
+        assert isinstance(value, AMRKDTree)
+        self._field = value.fields
+        self._log_field = value.log_fields
+        self._volume = value
+        assert self._volume_valid
+
+    @volume.deleter
+    def volume(self):
+        self._volume = None
+
+    @property
+    def field(self):
+        return self._field
+
+    @field.setter
+    @invalidate_volume
+    def field(self, value):
+        field = self.data_source._determine_fields(value)
+        if len(field) > 1:
+            raise RuntimeError("VolumeSource.field can only be a single field but received multiple fields: %s" % field)
+        field = field[0]
+        if self._field != field:
+            log_field = self.data_source.ds.field_info[field].take_log
+            self.tfh.bounds = None
+        else:
+            log_field = self._log_field
+        self._log_field = log_field
+        self._field = field
+        self.transfer_function = None
+        self.tfh.set_field(field)
+        self.tfh.set_log(log_field)
+
+    @property
+    def log_field(self):
+        return self._log_field
+
+    @log_field.setter
+    @invalidate_volume
+    def log_field(self, value):
+        self.transfer_function = None
+        self.tfh.set_log(value)
+        self._log_field = value
+
+    @property
+    def use_ghost_zones(self):
+        return self._use_ghost_zones
+
+    @use_ghost_zones.setter
+    @invalidate_volume
+    def use_ghost_zones(self, value):
+        self._use_ghost_zones = value
+
+    @property
+    def weight_field(self):
+        return self._weight_field
+
+    @weight_field.setter
+    @invalidate_volume
+    def weight_field(self, value):
+        self._weight_field = value
+
+    def set_transfer_function(self, transfer_function):
+        self.transfer_function = transfer_function
+        return self
+
+    def _validate(self):
+        if self.data_source is None:
+            raise RuntimeError("Data source not initialized")
+
+    def set_volume(self, volume):
+        self.volume = volume
+        return self
+
+    def set_field(self, field):
+        self.field = field
+        return self
+
+    def set_log(self, log_field):
+        self.log_field = log_field
+        return self
+
+    def set_weight_field(self, weight_field):
+        self.weight_field = weight_field
+        return self
+
+    def set_use_ghost_zones(self, use_ghost_zones):
+        self.use_ghost_zones = use_ghost_zones
+        return self
+
+    def set_sampler(self, camera, interpolated=True):
+        if self.sampler_type == "volume-render":
+            sampler = new_volume_render_sampler(camera, self)
+        elif self.sampler_type == "projection" and interpolated:
+            sampler = new_interpolated_projection_sampler(camera, self)
+        elif self.sampler_type == "projection":
+            sampler = new_projection_sampler(camera, self)
+        else:
+            raise NotImplementedError("%s not implemented yet" % self.sampler_type)
+        self.sampler = sampler
+        assert self.sampler is not None
+
+    @abc.abstractmethod
+    def _get_volume(self):
+        pass
+
+    def finalize_image(self, camera, image):
+        image = image.reshape(*camera.resolution, 4)
+        if not self.transfer_function.grey_opacity:
+            image[:, :, 3] = 1
+        return image
+
+    def __repr__(self):
+        return "<Volume Source>:%s transfer_function:%s" % (self.data_source, self._transfer_function)
+
+
+class KDTreeVolumeSource(VolumeSource):
+    volume_method = "KDTree"
+
+    def _get_volume(self):
+        if self._volume is None:
+            self._volume = AMRKDTree(self.data_source.ds, data_source=self.data_source)
+        return self._volume
+
+    @validate_volume
+    def render(self, camera, zbuffer=None):
+        self.zbuffer = zbuffer
+        self.set_sampler(camera)
+        assert self.sampler is not None
+        if self.check_nans:
+            for brick in self.volume.bricks:
+                for data in brick.my_data:
+                    if np.any(np.isnan(data)):
+                        raise RuntimeError
+        if self.batched:
+            bricks = self.volume.device_bricks(self.sampler._ctx, self.sampler._storage)
+            self.sampler.cast_bricks(bricks, self.volume.view_order(camera.lens.viewpoint))
+        else:
+            for brick in self.volume.traverse(camera.lens.viewpoint):
+                self.sampler(brick, num_threads=self.num_threads)
+        self.current_image = self.finalize_image(camera, self.sampler.aimage)
+        if zbuffer is None:
+            self.zbuffer = ZBuffer(self.current_image, np.full(self.current_image.shape[:2], np.inf))
+        return self.current_image
+
+    def finalize_image(self, camera, image):
+        if self._volume is not None:
+            image = self.volume.reduce_tree_images(image, camera.lens.viewpoint, use_opacity=self.transfer_function.grey_opacity)
+        return super().finalize_image(camera, image)
