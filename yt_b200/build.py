@@ -29,4 +29,13 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    print(build(force=True, verbose="-v" in sys.argv))
+
+
+def build_variant(tag, defines, verbose=False):
+    """Kernel experiments: libytb200_<tag>.so with extra -D flags (select with YTB200_LIB=<path>)."""
+    out = os.path.join(HERE, "libytb200_%s.so" % tag)
+    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SRC
+    subprocess.check_call(cmd)
+    return out

@@ -14,38 +14,39 @@ constexpr int TILE_I = 16, TILE_J = 16, CTA_THREADS = 256;
 #ifndef YTB_MIN_BLOCKS
 #define YTB_MIN_BLOCKS 2
 #endif
+#ifndef YTB_MIN_BLOCKS_PROJ
+#define YTB_MIN_BLOCKS_PROJ 3   // the projection cast is load-latency bound: occupancy pays (ncu r01c)
+#endif
 enum { KIND_PROJ = 0, KIND_IPROJ = 1, KIND_VR = 2 };
-enum { TFM_NONE = 0, TFM_GENERAL = 1, TFM_COLOUR = 2 };
+// transfer-function mode of the FAST path.  The ColorTransferFunction fast path is specialised on
+// grey_opacity and on "0 lies strictly inside the table bounds" (both uniform per launch).
+//   TFM_COLOUR | GREY         grey_opacity
+//   TFM_COLOUR | ZERO_INSIDE  b0 < 0 < b1: cells whose 8 corners are exactly 0 are rejected (FIT_get_value, isnormal)
+//   TFM_COLOUR | EDGE         the table does not vanish at its bounds: samples within fp32 rounding of a bound
+//                             are flagged and the brick is re-walked carefully (see CarefulSampler)
+enum { TFM_NONE = 0, TFM_GENERAL = 1, TFM_COLOUR = 8, TFM_GREY = 1, TFM_ZERO_INSIDE = 2, TFM_EDGE = 4 };
+__host__ __device__ constexpr bool tfm_is_colour(int tfm) { return tfm >= TFM_COLOUR; }
+__host__ __device__ constexpr bool tfm_grey(int tfm) { return tfm >= TFM_COLOUR && (tfm & TFM_GREY); }
+__host__ __device__ constexpr bool tfm_zero_inside(int tfm) { return tfm >= TFM_COLOUR && (tfm & TFM_ZERO_INSIDE); }
+__host__ __device__ constexpr bool tfm_edge(int tfm) { return tfm >= TFM_COLOUR && (tfm & TFM_EDGE); }
 
 // ---------------------------------------------------------------------------------------------
-// Per-thread sampler state.  KIND/EXACT/TFM/PARTIAL/NF1 are compile-time; T is the storage type.
-//   NF1 : the brick set has exactly one field (corners cached in registers per cell).
+// EXACT sampler: the reference's evaluation order, all fp64, no contraction
+// (image_samplers.pyx:327-343 / 372-402 / 453-487).  Validation mode, not the tuned path.
 // ---------------------------------------------------------------------------------------------
-template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T>
-struct CellSampler {
-    // ray
+template <int KIND, bool PARTIAL>
+struct ExactSampler {
+    const double *ray;   // shared memory: this CTA's rays, component-major [6][CTA_THREADS] (vp then vd)
     double vp[3], vd[3];
-    // per-brick
     const DevBrick *br;
     double dds[3], idds[3], le[3];
-    double o[3], dc[3];  // FAST: ray origin / direction in cell units of this brick
-    int ny, nz;          // cell dims (y,z)
-    int n_fields;
+    int ny, nz, n_fields;
     const unsigned char *mask;
-    // sampler constants
     int n_samples;
-    double inv_ns;
     const DevTF *tf;
     TFShared64 t64;
-    const float2 *pairs;
-    ColourTable ct;
-    ColourAcc ca;
-    // accumulators
-    double acc[4];   // PROJ / IPROJ / EXACT VR
-    double B64[4];
-    float rgba[4];   // FAST VR
-    float B[4];
-    unsigned long long n_cells;
+    int cur[3], stp[3];
+    double acc[4], B64[4];
 
     __device__ __forceinline__ void set_brick(const DevBrick *b)
     {
@@ -53,52 +54,50 @@ struct CellSampler {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             dds[i] = b->dds[i]; idds[i] = b->idds[i]; le[i] = b->le[i];
-            if (!EXACT) { o[i] = (vp[i] - le[i]) * idds[i]; dc[i] = vd[i] * idds[i]; }
+            vp[i] = ray[i * CTA_THREADS + threadIdx.x]; vd[i] = ray[(3 + i) * CTA_THREADS + threadIdx.x];
         }
         ny = b->dims[1]; nz = b->dims[2];
         n_fields = b->n_fields;
         mask = b->mask;
     }
-
-    __device__ __forceinline__ void cell(double enter_t, double exit_t, int ix, int iy, int iz)
+    template <bool MASKED>
+    __device__ __forceinline__ void begin(const int (&c)[3], const int (&s)[3])
     {
+#pragma unroll
+        for (int i = 0; i < 3; i++) { cur[i] = c[i]; stp[i] = s[i]; }
+    }
+    __device__ __forceinline__ void skipped_cell() {}
+    template <bool MASKED>
+    __device__ __forceinline__ void advance(bool is0, bool is1, bool is2)
+    {
+        if (is0) cur[0] += stp[0];
+        if (is1) cur[1] += stp[1];
+        if (is2) cur[2] += stp[2];
+    }
+    template <bool MASKED>
+    __device__ __forceinline__ void cell(double enter_t, double exit_t)
+    {
+        const int ix = cur[0], iy = cur[1], iz = cur[2];
         if (KIND == KIND_PROJ) {
             const double dl = dsub(exit_t, enter_t);
             const size_t di = ((size_t)ix * ny + iy) * nz + iz;
             const int nf = n_fields < 4 ? n_fields : 4;
 #pragma unroll
-            for (int f = 0; f < 4; f++) {
-                if (f < nf) {
-                    const double v = (double)__ldg((const T *)br->data[f] + di);
-                    acc[f] = EXACT ? dadd(acc[f], dmul(v, dl)) : fma(v, dl, acc[f]);
-                }
-            }
+            for (int f = 0; f < 4; f++)
+                if (f < nf) acc[f] = dadd(acc[f], dmul(((const double *)br->data[f])[di], dl));
             return;
-        } else {
-            if (KIND == KIND_VR && mask != nullptr) {
-                if (mask[((size_t)ix * ny + iy) * nz + iz] != 1) return;
-            }
-            const int sy = nz + 1, sx = (ny + 1) * (nz + 1);
-            const size_t offset = (size_t)ix * sx + (size_t)iy * sy + iz;
-            if (EXACT) {
-                cell_exact(enter_t, exit_t, ix, iy, iz, sx, sy, offset);
-            } else {
-                cell_fast(enter_t, exit_t, ix, iy, iz, sx, sy, offset);
-            }
         }
-    }
-
-    // Reference evaluation order, all fp64 (image_samplers.pyx:372-402 / 453-487).
-    __device__ __forceinline__ void cell_exact(double enter_t, double exit_t, int ix, int iy, int iz, int sx, int sy,
-                                               size_t offset)
-    {
-        const int idx[3] = {ix, iy, iz};
+        if (KIND == KIND_VR && MASKED) {
+            if (mask[((size_t)ix * ny + iy) * nz + iz] != 1) return;
+        }
+        const int sy = nz + 1, sx = (ny + 1) * (nz + 1);
+        const size_t offset = (size_t)ix * sx + (size_t)iy * sy + iz;
         double dp[3], ds[3], dvs[6];
         const double dt = ddiv(dsub(exit_t, enter_t), (double)n_samples);
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             dp[i] = dadd(dmul(dadd(enter_t, dmul(0.5, dt)), vd[i]), vp[i]);
-            dp[i] = dsub(dp[i], dadd(dmul((double)idx[i], dds[i]), le[i]));
+            dp[i] = dsub(dp[i], dadd(dmul((double)cur[i], dds[i]), le[i]));
             dp[i] = dmul(dp[i], idds[i]);
             ds[i] = dmul(dmul(vd[i], idds[i]), dt);
         }
@@ -118,92 +117,243 @@ struct CellSampler {
             for (int i = 0; i < 3; i++) dp[i] = dadd(dp[i], ds[i]);
         }
     }
+};
 
-    // fp64 cell entry, fp32 samples.
-    __device__ __forceinline__ void cell_fast(double enter_t, double exit_t, int ix, int iy, int iz, int sx, int sy,
-                                              size_t offset)
+// Rare path of the ColorTransferFunction cast.  FIT_get_value rejects x <= b0, x >= b1 and x == 0
+// (field_interpolation_tables.pxd:70-71) and the table need not vanish there, so a sample that lands
+// within fp32 rounding of such a threshold must be classified the way the reference classifies it, or
+// a whole sample's emission appears / disappears.  The fast sample loop flags such samples ("doubt");
+// the kernel then re-walks that brick for that ray with this sampler: sample values and validity tests
+// in fp64, in the reference's evaluation order (image_samplers.pyx:472-487, fixed_interpolator.cpp:34-52),
+// followed by the fp32 table lookup / compositing of the fast path.  The re-walk sits outside the hot
+// loop, so its registers cost the fast path nothing.
+template <bool PARTIAL, bool GREY, typename T>
+struct CarefulSampler {
+    const double *ray;
+    const DevBrick *br;
+    const DevTF *tf;
+    unsigned base;
+    int n_samples;
+    int cur[3], stp[3];
+    ColourAcc ca;
+
+    template <bool MASKED>
+    __device__ __forceinline__ void begin(const int (&c)[3], const int (&s)[3])
     {
-        const double dt64 = (exit_t - enter_t) * inv_ns;
+#pragma unroll
+        for (int i = 0; i < 3; i++) { cur[i] = c[i]; stp[i] = s[i]; }
+    }
+    __device__ __forceinline__ void skipped_cell() {}
+    template <bool MASKED>
+    __device__ __forceinline__ void advance(bool is0, bool is1, bool is2)
+    {
+        if (is0) cur[0] += stp[0];
+        if (is1) cur[1] += stp[1];
+        if (is2) cur[2] += stp[2];
+    }
+    template <bool MASKED>
+    __device__ __noinline__ void cell(double enter_t, double exit_t)
+    {
+        const int ny = br->dims[1], nz = br->dims[2];
+        if (MASKED) {
+            if (br->mask[((size_t)cur[0] * ny + cur[1]) * nz + cur[2]] != 1) return;
+        }
+        const int sy = nz + 1, sx = (ny + 1) * (nz + 1);
+        const T *d = (const T *)br->data[0] + ((size_t)cur[0] * sx + (size_t)cur[1] * sy + cur[2]);
+        const double c000 = (double)__ldg(d), c001 = (double)__ldg(d + 1), c010 = (double)__ldg(d + sy), c011 = (double)__ldg(d + sy + 1);
+        const double c100 = (double)__ldg(d + sx), c101 = (double)__ldg(d + sx + 1), c110 = (double)__ldg(d + sx + sy), c111 = (double)__ldg(d + sx + sy + 1);
+        const double dt = ddiv(dsub(exit_t, enter_t), (double)n_samples);
+        const float dtf = (float)((exit_t - enter_t) * (1.0 / (double)n_samples));
+        const double b0 = tf->b0[0], b1 = tf->b1[0], idbin = tf->idbin[0];
+        const float hi = tf->colour_hi;
+        ColourTable ct;
+        ct.base = base;
+        ct.tf = tf;
+        double dp[3], ds[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const double vp = ray[i * CTA_THREADS + threadIdx.x], vd = ray[(3 + i) * CTA_THREADS + threadIdx.x];
+            dp[i] = dadd(dmul(dadd(enter_t, dmul(0.5, dt)), vd), vp);
+            dp[i] = dsub(dp[i], dadd(dmul((double)cur[i], br->dds[i]), br->le[i]));
+            dp[i] = dmul(dp[i], br->idds[i]);
+            ds[i] = dmul(dmul(vd, br->idds[i]), dt);
+        }
+        for (int s = 0; s < n_samples; s++) {
+            double dv = dsub(1.0, dp[2]);
+            double v0 = dadd(dmul(dv, c000), dmul(dp[2], c001)), v1 = dadd(dmul(dv, c010), dmul(dp[2], c011));
+            double v2 = dadd(dmul(dv, c100), dmul(dp[2], c101)), v3 = dadd(dmul(dv, c110), dmul(dp[2], c111));
+            dv = dsub(1.0, dp[1]);
+            v0 = dadd(dmul(dv, v0), dmul(dp[1], v1));
+            v1 = dadd(dmul(dv, v2), dmul(dp[1], v3));
+            dv = dsub(1.0, dp[0]);
+            const double xv = dadd(dmul(dv, v0), dmul(dp[0], v1));
+            const bool valid = !(xv >= b1 || xv <= b0) && is_normal64(xv);
+            float fs = 0.5f;
+            if (valid) fs = fminf(fmaxf((float)fma(xv - b0, idbin, 2.0), 1.5f), hi);
+            colour_sample<PARTIAL, GREY>(ct, fs, dtf, ca);
+#pragma unroll
+            for (int i = 0; i < 3; i++) dp[i] = dadd(dp[i], ds[i]);
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// FAST sampler (the product path): fp64 cell entry, fp32 samples, fp64 sums for the
+// projection family.  It follows the walk with running offsets instead of index arithmetic:
+//   off    element offset of the current cell (cell-centred data: PROJ) or of its low vertex
+//   moff   cell offset into the mask (VR with a non-trivial mask only)
+//   ob[i]  ray origin in cell units minus the current cell index, fp64: the cell-local coordinate of
+//          the point at parameter t is fma(t, dc[i], ob[i])
+// NF1: the brick set has exactly one field (corners cached in registers per cell).
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int TFM, bool PARTIAL, bool NF1, typename T>
+struct FastSampler {
+    const double *ray;   // shared memory: this CTA's rays, component-major [6][CTA_THREADS] (vp then vd)
+    const DevBrick *br;
+    double ob[3], dc[3];
+    float dcf[3];
+    unsigned off, moff;
+    int s0, s1, s2;      // signed element strides of one step along each axis
+    int sx, sy;          // vertex strides (VR / IPROJ)
+    int n_fields;
+    const unsigned char *mask;
+    int n_samples;
+    const CastParams *prm;   // kernel parameters (constant bank)
+    const DevTF *tf;
+    const float2 *pairs;
+    ColourTable ct;
+    ColourAcc ca;
+    bool doubt;      // colour path: a sample of this brick needs the careful re-walk
+    double acc[4];   // PROJ / IPROJ sums
+    float rgba[4];   // general-TF VR
+    float B[4];
+
+    __device__ __forceinline__ void set_brick(const DevBrick *b)
+    {
+        br = b;
+        n_fields = b->n_fields;
+        mask = b->mask;
+    }
+    template <bool MASKED>
+    __device__ __forceinline__ void begin(const int (&c)[3], const int (&s)[3])
+    {
+        const int ny = br->dims[1], nz = br->dims[2];
+        if (KIND == KIND_PROJ) {
+            sx = ny * nz; sy = nz;
+        } else {
+            sx = (ny + 1) * (nz + 1); sy = nz + 1;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const double idds = br->idds[i];
+                dc[i] = ray[(3 + i) * CTA_THREADS + threadIdx.x] * idds;
+                ob[i] = (ray[i * CTA_THREADS + threadIdx.x] - br->le[i]) * idds - (double)c[i];
+                dcf[i] = (float)dc[i];
+            }
+        }
+        off = (unsigned)c[0] * (unsigned)sx + (unsigned)c[1] * (unsigned)sy + (unsigned)c[2];
+        s0 = s[0] * sx; s1 = s[1] * sy; s2 = s[2];
+        moff = 0;
+        if (KIND == KIND_VR && MASKED) moff = ((unsigned)c[0] * (unsigned)ny + (unsigned)c[1]) * (unsigned)nz + (unsigned)c[2];
+    }
+    __device__ __forceinline__ void skipped_cell() {}
+    template <bool MASKED>
+    __device__ __forceinline__ void advance(bool is0, bool is1, bool is2)
+    {
+        off += (unsigned)(is0 ? s0 : (is1 ? s1 : s2));
+        if (KIND != KIND_PROJ) {
+            // ob[i] -= step[i]; the step has the sign of the ray direction on that axis
+            if (is0) ob[0] -= copysign(1.0, dc[0]);
+            if (is1) ob[1] -= copysign(1.0, dc[1]);
+            if (is2) ob[2] -= copysign(1.0, dc[2]);
+        }
+        if (KIND == KIND_VR && MASKED) {
+            const int ny = br->dims[1], nz = br->dims[2];
+            const int m0 = s0 > 0 ? ny * nz : -ny * nz, m1 = s1 > 0 ? nz : -nz;
+            moff += (unsigned)(is0 ? m0 : (is1 ? m1 : s2));
+        }
+    }
+
+    template <bool MASKED>
+    __device__ __forceinline__ void cell(double enter_t, double exit_t)
+    {
+        if (KIND == KIND_PROJ) {
+            const double dl = exit_t - enter_t;
+            const int nf = n_fields < 4 ? n_fields : 4;
+#pragma unroll
+            for (int f = 0; f < 4; f++)
+                if (f < nf) acc[f] = fma((double)__ldg((const T *)br->data[f] + off), dl, acc[f]);
+            return;
+        }
+        if (KIND == KIND_VR && MASKED) {
+            if (mask[moff] != 1) return;
+        }
+        const double dt64 = (exit_t - enter_t) * prm->inv_ns;
         const double tmid = fma(0.5, dt64, enter_t);
-        float x = (float)(fma(tmid, dc[0], o[0]) - (double)ix);
-        float y = (float)(fma(tmid, dc[1], o[1]) - (double)iy);
-        float z = (float)(fma(tmid, dc[2], o[2]) - (double)iz);
-        const float sxs = (float)(dc[0] * dt64), sys = (float)(dc[1] * dt64), szs = (float)(dc[2] * dt64);
-        const float dt = (float)dt64;
-        if (NF1) {
-            Corners c;
-            load_corners(c, (const T *)br->data[0] + offset, sx, sy);
-            if (KIND == KIND_IPROJ) {
-                // the projection family carries the 1e-6 bar: sample in fp64 (contraction allowed)
-                const T *d = (const T *)br->data[0] + offset;
-                const double a0 = (double)__ldg(d), a1 = (double)__ldg(d + 1), b0 = (double)__ldg(d + sy), b1 = (double)__ldg(d + sy + 1);
-                const double e0 = (double)__ldg(d + sx), e1 = (double)__ldg(d + sx + 1), f0 = (double)__ldg(d + sx + sy), f1 = (double)__ldg(d + sx + sy + 1);
-                double xd = fma(tmid, dc[0], o[0]) - (double)ix, yd = fma(tmid, dc[1], o[1]) - (double)iy, zd = fma(tmid, dc[2], o[2]) - (double)iz;
-                const double sxd = dc[0] * dt64, syd = dc[1] * dt64, szd = dc[2] * dt64;
-                double sum = 0.0;
-                for (int s = 0; s < n_samples; s++) {
-                    const double v00 = fma(zd, a1 - a0, a0), v01 = fma(zd, b1 - b0, b0);
-                    const double v10 = fma(zd, e1 - e0, e0), v11 = fma(zd, f1 - f0, f0);
-                    const double v0 = fma(yd, v01 - v00, v00), v1 = fma(yd, v11 - v10, v10);
-                    sum += fma(xd, v1 - v0, v0);
-                    xd += sxd; yd += syd; zd += szd;
-                }
-                acc[0] = fma(sum, dt64, acc[0]);
-            } else {
-                if (TFM == TFM_COLOUR) {
-                    CornersP cp;
-                    load_corners_p(cp, (const T *)br->data[0] + offset, sx, sy);
-                    if (tf->grey) colour_cell_run<PARTIAL, true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
-                    else colour_cell_run<PARTIAL, false>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
-                } else {
-                    float dvs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const double xd = fma(tmid, dc[0], ob[0]), yd = fma(tmid, dc[1], ob[1]), zd = fma(tmid, dc[2], ob[2]);
+        if (KIND == KIND_IPROJ) {
+            // the projection family carries the 1e-6 bar: sample in fp64 (contraction allowed)
+            const double sxd = dc[0] * dt64, syd = dc[1] * dt64, szd = dc[2] * dt64;
+            const int nf = NF1 ? 1 : (n_fields < 3 ? n_fields : 3);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                if (j < nf) {
+                    const T *d = (const T *)br->data[j] + off;
+                    const double a0 = (double)__ldg(d), a1 = (double)__ldg(d + 1), b0 = (double)__ldg(d + sy), b1 = (double)__ldg(d + sy + 1);
+                    const double e0 = (double)__ldg(d + sx), e1 = (double)__ldg(d + sx + 1), f0 = (double)__ldg(d + sx + sy), f1 = (double)__ldg(d + sx + sy + 1);
+                    double x = xd, y = yd, z = zd, sum = 0.0;
                     for (int s = 0; s < n_samples; s++) {
-                        dvs[0] = trilinear(c, x, y, z);
-                        eval_transfer32<PARTIAL>(*tf, pairs, dt, dvs, rgba, B);
-                        x += sxs; y += sys; z += szs;
+                        const double v00 = fma(z, a1 - a0, a0), v01 = fma(z, b1 - b0, b0);
+                        const double v10 = fma(z, e1 - e0, e0), v11 = fma(z, f1 - f0, f0);
+                        const double v0 = fma(y, v01 - v00, v00), v1 = fma(y, v11 - v10, v10);
+                        sum += fma(x, v1 - v0, v0);
+                        x += sxd; y += syd; z += szd;
                     }
+                    acc[j] = fma(sum, dt64, acc[j]);
                 }
+            }
+            return;
+        }
+        float x = (float)xd, y = (float)yd, z = (float)zd;
+        const float dt = (float)dt64;
+        const float sxs = dcf[0] * dt, sys = dcf[1] * dt, szs = dcf[2] * dt;
+        if (tfm_is_colour(TFM)) {
+            CornersP cp;
+            const bool all_zero = load_corners_rows(cp, (const T *)br->data[0] + off, sx, sy, ct);
+            // exact zeros are rejected by FIT_get_value (isnormal); a sample is exactly 0 essentially only where
+            // the data are (zero padding), i.e. where all 8 corners are: test the cell, not every sample
+            if (tfm_zero_inside(TFM) && all_zero) return;
+            // dt * (largest table product) <= 1: the max(1 - dt*T, 0) clamps cannot fire in this cell
+            float m;
+            if (dt * tf->colour_clamp_bound <= 1.f)
+                m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM)>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+            else
+                m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM)>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+            // some sample sat within fp32 rounding of a table bound (see CarefulSampler)
+            if (tfm_edge(TFM)) doubt = doubt || (m < tf->colour_band);
+        } else if (NF1) {
+            Corners c;
+            load_corners(c, (const T *)br->data[0] + off, sx, sy);
+            float dvs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int s = 0; s < n_samples; s++) {
+                dvs[0] = trilinear(c, x, y, z);
+                eval_transfer32<PARTIAL>(*tf, pairs, dt, dvs, rgba, B);
+                x += sxs; y += sys; z += szs;
             }
         } else {
             // any number of fields: corners re-read (L1) per sample; general but not the tuned path
-            if (KIND == KIND_IPROJ) {
-                double xd = fma(tmid, dc[0], o[0]) - (double)ix, yd = fma(tmid, dc[1], o[1]) - (double)iy, zd = fma(tmid, dc[2], o[2]) - (double)iz;
-                const double sxd = dc[0] * dt64, syd = dc[1] * dt64, szd = dc[2] * dt64;
-                const int nf = n_fields < 3 ? n_fields : 3;
-                double sum[3] = {0.0, 0.0, 0.0};
-                for (int s = 0; s < n_samples; s++) {
+            for (int s = 0; s < n_samples; s++) {
+                float dvs[6];
 #pragma unroll
-                    for (int j = 0; j < 3; j++) {
-                        if (j < nf) {
-                            const T *d = (const T *)br->data[j] + offset;
-                            const double a0 = (double)__ldg(d), a1 = (double)__ldg(d + 1), b0 = (double)__ldg(d + sy), b1 = (double)__ldg(d + sy + 1);
-                            const double e0 = (double)__ldg(d + sx), e1 = (double)__ldg(d + sx + 1), f0 = (double)__ldg(d + sx + sy), f1 = (double)__ldg(d + sx + sy + 1);
-                            const double v00 = fma(zd, a1 - a0, a0), v01 = fma(zd, b1 - b0, b0);
-                            const double v10 = fma(zd, e1 - e0, e0), v11 = fma(zd, f1 - f0, f0);
-                            const double v0 = fma(yd, v01 - v00, v00), v1 = fma(yd, v11 - v10, v10);
-                            sum[j] += fma(xd, v1 - v0, v0);
-                        }
+                for (int j = 0; j < 6; j++) {
+                    dvs[j] = 0.f;
+                    if (j < n_fields) {
+                        Corners c;
+                        load_corners(c, (const T *)br->data[j] + off, sx, sy);
+                        dvs[j] = trilinear(c, x, y, z);
                     }
-                    xd += sxd; yd += syd; zd += szd;
                 }
-#pragma unroll
-                for (int j = 0; j < 3; j++)
-                    if (j < nf) acc[j] = fma(sum[j], dt64, acc[j]);
-            } else {
-                for (int s = 0; s < n_samples; s++) {
-                    float dvs[6];
-#pragma unroll
-                    for (int j = 0; j < 6; j++) {
-                        dvs[j] = 0.f;
-                        if (j < n_fields) {
-                            Corners c;
-                            load_corners(c, (const T *)br->data[j] + offset, sx, sy);
-                            dvs[j] = trilinear(c, x, y, z);
-                        }
-                    }
-                    eval_transfer32<PARTIAL>(*tf, pairs, dt, dvs, rgba, B);
-                    x += sxs; y += sys; z += szs;
-                }
+                eval_transfer32<PARTIAL>(*tf, pairs, dt, dvs, rgba, B);
+                x += sxs; y += sys; z += szs;
             }
         }
     }
@@ -227,38 +377,51 @@ __device__ __forceinline__ void make_ray(const DevCamera &cam, int vi, int vj, d
     }
 }
 
+template <bool EXACT, class A, class B> struct pick_sampler { using type = A; };
+template <class A, class B> struct pick_sampler<false, A, B> { using type = B; };
+
 template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T>
-__global__ void __launch_bounds__(CTA_THREADS, YTB_MIN_BLOCKS)
+__global__ void __launch_bounds__(CTA_THREADS, (KIND == KIND_PROJ && !EXACT) ? YTB_MIN_BLOCKS_PROJ : YTB_MIN_BLOCKS)
 cast_kernel(const __grid_constant__ CastParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_list[CTA_THREADS];
     __shared__ int s_warp_cnt[CTA_THREADS / 32];
+    // the rays of this tile, component-major: only needed when a ray enters a brick, so they live here
+    // instead of in 12 registers per thread
+    __shared__ double s_ray[6 * CTA_THREADS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    CellSampler<KIND, EXACT, TFM, PARTIAL, NF1, T> smp;
+    typename pick_sampler<EXACT, ExactSampler<KIND, PARTIAL>, FastSampler<KIND, TFM, PARTIAL, NF1, T>>::type smp;
     smp.tf = &p.tf;
-    smp.pairs = nullptr;
-    smp.t64.values = smp.t64.d0 = smp.t64.dy = nullptr;
+    smp.ray = s_ray;
     // ---- stage the transfer-function tables into shared memory -------------------------------
-    if (KIND == KIND_VR) {
-        if (EXACT) {
+    if constexpr (EXACT) {
+        smp.t64.values = smp.t64.d0 = smp.t64.dy = nullptr;
+        if (KIND == KIND_VR) {
             double *sv = reinterpret_cast<double *>(smem_raw);
             const int n = p.tf.total_bins;
             for (int i = tid; i < n; i += CTA_THREADS) {
                 sv[i] = p.tf.values[i]; sv[n + i] = p.tf.d0[i]; sv[2 * n + i] = p.tf.dy[i];
             }
             smp.t64.values = sv; smp.t64.d0 = sv + n; smp.t64.dy = sv + 2 * n;
-        } else if (TFM == TFM_COLOUR) {
-            // replicate each bin's (r,g,b,a) row COLOUR_COPIES times: copy k sits in 16-byte bank group k
+        }
+    } else {
+        smp.pairs = nullptr;
+        if (KIND == KIND_VR && tfm_is_colour(TFM)) {
+            // replicate each row COLOUR_COPIES times: copy k sits in 16-byte bank group k (rows are already
+            // padded with the zero / duplicate rows by ytb200_tf_create)
             float4 *sc = reinterpret_cast<float4 *>(smem_raw);
             const int nb = p.tf.nbins[0];
-            for (int i = tid; i < nb * COLOUR_COPIES; i += CTA_THREADS) sc[i] = p.tf.colour[i / COLOUR_COPIES];
-            smp.ct.base = (unsigned)__cvta_generic_to_shared(sc) + (unsigned)(lane & (COLOUR_COPIES - 1)) * 16u;
-            smp.ct.b0_hi = p.tf.b0_hi[0]; smp.ct.b0_lo = p.tf.b0_lo[0]; smp.ct.b1 = p.tf.b1_f[0];
-            smp.ct.idbin = p.tf.idbin_f[0]; smp.ct.nbins_m2 = nb - 2;
-        } else {
+            const int nrows = nb + COLOUR_PAD_ROWS;
+            for (int i = tid; i < nrows * COLOUR_COPIES; i += CTA_THREADS) sc[i] = p.tf.colour[i / COLOUR_COPIES];
+            // colour_cell_run forms the address as float_as_int(2^23 + row) * ROW_BYTES + base: fold the
+            // (wrapping) bias of the exponent bits into base
+            smp.ct.base = (unsigned)__cvta_generic_to_shared(sc) + (unsigned)(lane & (COLOUR_COPIES - 1)) * 16u
+                          - 0x4B000000u * COLOUR_ROW_BYTES;
+            smp.ct.tf = &p.tf;
+        } else if (KIND == KIND_VR) {
             float2 *sp = reinterpret_cast<float2 *>(smem_raw);
             const int n = p.tf.total_bins;
             for (int i = tid; i < n; i += CTA_THREADS) sp[i] = p.tf.pairs[i];
@@ -275,28 +438,31 @@ cast_kernel(const __grid_constant__ CastParams p)
     const size_t pix = (size_t)(active ? vi : 0) * p.cam.ny + (active ? vj : 0);
 
     double max_t = 1.0;
-    double init[4] = {0.0, 0.0, 0.0, 0.0};
-    if (active) {
-        make_ray(p.cam, vi, vj, smp.vp, smp.vd);
-        if (p.zbuffer) { const double z = p.zbuffer[pix]; max_t = fmin(fmax(z, 0.0), 1.0); }
-        if (!PARTIAL) {
-            const double4 px = *reinterpret_cast<const double4 *>(p.image + pix * 4);
-            init[0] = px.x; init[1] = px.y; init[2] = px.z; init[3] = px.w;
+    {
+        double vp[3] = {0.0, 0.0, 0.0}, vd[3] = {0.0, 0.0, 0.0};
+        double init[4] = {0.0, 0.0, 0.0, 0.0};   // initial colours (opaque sources); not kept live through the walk
+        if (active) {
+            make_ray(p.cam, vi, vj, vp, vd);
+            if (p.zbuffer) { const double z = p.zbuffer[pix]; max_t = fmin(fmax(z, 0.0), 1.0); }
+            if (!PARTIAL) {
+                const double4 px = *reinterpret_cast<const double4 *>(p.image + pix * 4);
+                init[0] = px.x; init[1] = px.y; init[2] = px.z; init[3] = px.w;
+            }
         }
-    } else {
 #pragma unroll
-        for (int i = 0; i < 3; i++) { smp.vp[i] = 0.0; smp.vd[i] = 0.0; }
-    }
+        for (int i = 0; i < 3; i++) { s_ray[i * CTA_THREADS + tid] = vp[i]; s_ray[(3 + i) * CTA_THREADS + tid] = vd[i]; }
+        if constexpr (EXACT) {
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        smp.acc[c] = init[c]; smp.B64[c] = 1.0;
-        smp.rgba[c] = (float)init[c]; smp.B[c] = 1.f;
+            for (int c = 0; c < 4; c++) { smp.acc[c] = init[c]; smp.B64[c] = 1.0; }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) { smp.acc[c] = init[c]; smp.rgba[c] = (float)init[c]; smp.B[c] = 1.f; }
+            smp.ca.c01 = make_float2((float)init[0], (float)init[1]); smp.ca.c2 = (float)init[2]; smp.ca.c3 = (float)init[3];
+            smp.ca.b01 = make_float2(1.f, 1.f); smp.ca.b2 = 1.f; smp.ca.b3 = 1.f;
+            smp.prm = &p;
+        }
     }
-    smp.ca.c01 = make_float2((float)init[0], (float)init[1]); smp.ca.c2 = (float)init[2]; smp.ca.c3 = (float)init[3];
-    smp.ca.b01 = make_float2(1.f, 1.f); smp.ca.b2 = 1.f; smp.ca.b3 = 1.f;
     smp.n_samples = p.n_samples;
-    smp.inv_ns = 1.0 / (double)p.n_samples;
-    smp.n_cells = 0;
     __syncthreads();
 
     // ---- walk the ordered brick list; cull bricks whose pixel footprint misses this tile ----
@@ -328,7 +494,38 @@ cast_kernel(const __grid_constant__ CastParams p)
                 BrickGeom g;
                 load_geom(g, br);
                 smp.set_brick(br);
-                walk_brick(g, smp.vp, smp.vd, max_t, smp);
+                double vp[3], vd[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) { vp[i] = s_ray[i * CTA_THREADS + tid]; vd[i] = s_ray[(3 + i) * CTA_THREADS + tid]; }
+                const bool masked = KIND == KIND_VR && br->mask != nullptr;
+                if constexpr (!EXACT && KIND == KIND_VR && tfm_edge(TFM)) {
+                    // accumulators at brick entry, parked in local memory for the (rare) careful re-walk
+                    volatile float entry[8];
+                    entry[0] = smp.ca.c01.x; entry[1] = smp.ca.c01.y; entry[2] = smp.ca.c2; entry[3] = smp.ca.c3;
+                    if (PARTIAL) { entry[4] = smp.ca.b01.x; entry[5] = smp.ca.b01.y; entry[6] = smp.ca.b2; entry[7] = smp.ca.b3; }
+                    smp.doubt = false;
+                    if (masked) walk_brick<true>(g, vp, vd, max_t, smp);
+                    else walk_brick<false>(g, vp, vd, max_t, smp);
+                    if (smp.doubt) {
+                        CarefulSampler<PARTIAL, tfm_grey(TFM), T> cs;
+                        cs.ray = s_ray; cs.br = br; cs.tf = &p.tf; cs.base = smp.ct.base; cs.n_samples = p.n_samples;
+                        cs.ca.c01 = make_float2(entry[0], entry[1]); cs.ca.c2 = entry[2]; cs.ca.c3 = entry[3];
+                        cs.ca.b01 = make_float2(1.f, 1.f); cs.ca.b2 = 1.f; cs.ca.b3 = 1.f;
+                        if (PARTIAL) { cs.ca.b01 = make_float2(entry[4], entry[5]); cs.ca.b2 = entry[6]; cs.ca.b3 = entry[7]; }
+                        // reload geometry and ray so that nothing of them stays live across the fast walk
+                        BrickGeom g2;
+                        load_geom(g2, br);
+                        double vp2[3], vd2[3];
+#pragma unroll
+                        for (int i = 0; i < 3; i++) { vp2[i] = s_ray[i * CTA_THREADS + tid]; vd2[i] = s_ray[(3 + i) * CTA_THREADS + tid]; }
+                        if (masked) walk_brick<true>(g2, vp2, vd2, max_t, cs);
+                        else walk_brick<false>(g2, vp2, vd2, max_t, cs);
+                        smp.ca = cs.ca;
+                    }
+                } else {
+                    if (masked) walk_brick<true>(g, vp, vd, max_t, smp);
+                    else walk_brick<false>(g, vp, vd, max_t, smp);
+                }
             }
         }
         __syncthreads();
@@ -337,17 +534,20 @@ cast_kernel(const __grid_constant__ CastParams p)
     // ---- write back ---------------------------------------------------------------------------------
     if (!active) return;
     double out[4], Bout[4];
-    if (KIND == KIND_VR && !EXACT) {
-        if (TFM == TFM_COLOUR) {
+    if constexpr (EXACT) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) { out[c] = smp.acc[c]; Bout[c] = smp.B64[c]; }
+    } else if (KIND == KIND_VR) {
+        if (tfm_is_colour(TFM)) {
             smp.rgba[0] = smp.ca.c01.x; smp.rgba[1] = smp.ca.c01.y; smp.rgba[2] = smp.ca.c2; smp.rgba[3] = smp.ca.c3;
             smp.B[0] = smp.ca.b01.x; smp.B[1] = smp.ca.b01.y; smp.B[2] = smp.ca.b2; smp.B[3] = smp.ca.b3;
         }
 #pragma unroll
         for (int c = 0; c < 4; c++) { out[c] = (double)smp.rgba[c]; Bout[c] = (double)smp.B[c]; }
-        if (!PARTIAL && !p.tf.grey) out[3] = init[3];  // non-grey never touches alpha (H9)
+        if (!PARTIAL && !p.tf.grey) out[3] = p.image[pix * 4 + 3];  // non-grey never touches alpha (H9)
     } else {
 #pragma unroll
-        for (int c = 0; c < 4; c++) { out[c] = smp.acc[c]; Bout[c] = smp.B64[c]; }
+        for (int c = 0; c < 4; c++) { out[c] = smp.acc[c]; Bout[c] = 1.0; }
     }
     if (PARTIAL) {
         if (KIND == KIND_VR && !p.tf.grey) { out[3] = 0.0; Bout[3] = 1.0; }
@@ -365,10 +565,22 @@ struct CountSampler {
     int ny, nz;
     bool use_mask;
     unsigned long long n;
-    __device__ __forceinline__ void cell(double, double, int ix, int iy, int iz)
+    unsigned moff;
+    int m0, m1, m2;
+    template <bool MASKED>
+    __device__ __forceinline__ void begin(const int (&c)[3], const int (&s)[3])
+    {
+        moff = ((unsigned)c[0] * (unsigned)ny + (unsigned)c[1]) * (unsigned)nz + (unsigned)c[2];
+        m0 = s[0] * ny * nz; m1 = s[1] * nz; m2 = s[2];
+    }
+    __device__ __forceinline__ void skipped_cell() { n++; }
+    template <bool MASKED>
+    __device__ __forceinline__ void advance(bool is0, bool is1, bool is2) { moff += (unsigned)(is0 ? m0 : (is1 ? m1 : m2)); }
+    template <bool MASKED>
+    __device__ __forceinline__ void cell(double, double)
     {
         if (use_mask && mask != nullptr) {
-            if (mask[((size_t)ix * ny + iy) * nz + iz] != 1) return;
+            if (mask[moff] != 1) return;
         }
         n++;
     }
@@ -398,7 +610,7 @@ __global__ void __launch_bounds__(CTA_THREADS) count_kernel(const __grid_constan
             BrickGeom g;
             load_geom(g, br);
             smp.mask = br->mask; smp.ny = br->dims[1]; smp.nz = br->dims[2];
-            walk_brick(g, vp, vd, max_t, smp);
+            walk_brick<false>(g, vp, vd, max_t, smp);
         }
     }
     unsigned long long n = smp.n;

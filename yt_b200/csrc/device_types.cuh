@@ -52,11 +52,15 @@ struct DevTF {
     double b0[YTB_MAX_TABLES], b1[YTB_MAX_TABLES], idbin[YTB_MAX_TABLES];
     const double *values, *d0, *dy;
     // fp32 (FAST): (value, next-value - value) pairs; bounds split hi/lo so x-b0 keeps fp64-ish accuracy
-    float b0_hi[YTB_MAX_TABLES], b0_lo[YTB_MAX_TABLES], b1_f[YTB_MAX_TABLES], idbin_f[YTB_MAX_TABLES];
+    float b0_hi[YTB_MAX_TABLES], b0_lo[YTB_MAX_TABLES], b0_f[YTB_MAX_TABLES], b1_f[YTB_MAX_TABLES], idbin_f[YTB_MAX_TABLES];
     const float2 *pairs;
-    // colour_fast payload: one (r,g,b,a) row per bin; replicated 2^colour_copy_shift times in smem
+    // colour_fast payload: (r,g,b,a) rows [0, 0, y_0 .. y_{n-1}, y_{n-1}]; replicated 2^colour_copy_shift times in smem
     const float4 *colour;
     int colour_copy_shift;
+    // row-coordinate constants of the colour fast path (see ColourTable in raycast.cuh); they stay in the
+    // kernel-parameter constant bank instead of in registers
+    float colour_c0, colour_clamp_bound, colour_lo, colour_hi, colour_mid, colour_half, colour_band, colour_zrow;
+    int colour_zero_inside, colour_edge;
 };
 
 struct CastParams {
@@ -66,6 +70,7 @@ struct CastParams {
     const int4 *extent;     // per order entry: [i0,i1) x [j0,j1) pixel footprint
     int n_order;
     int n_samples;
+    double inv_ns;          // 1 / n_samples
     double *image;          // (nx,ny,4) fp64, in/out
     const double *zbuffer;  // (nx,ny) fp64 or nullptr (== ones)
     double *partial;        // (nx,ny,8) fp64 affine map output, or nullptr

@@ -46,9 +46,19 @@ __device__ __forceinline__ double snap_edge(double v, double le, double re, doub
     return v;
 }
 
-// walk_volume.  `S::cell(enter_t, exit_t, ix, iy, iz)` is the sampler_function.
+// walk_volume.  The sampler S is the reference's sampler_function plus the bookkeeping that lets it
+// follow the walk without index arithmetic:
+//   S::begin<MASKED>(cur, step)        start cell chosen (called once per brick the ray enters)
+//   S::cell<MASKED>(enter_t, exit_t)   == sample(vc, v_pos, v_dir, enter_t, exit_t, cur_ind, data)
+//   S::skipped_cell()                  the reference would sample an out-of-range cell here (see below)
+//   S::advance<MASKED>(is0, is1, is2)  the walk steps along exactly one axis (cur[i] += step[i])
+// MASKED: the brick has a non-trivial cell mask (uniform per brick; keeps mask bookkeeping out of the
+// common instantiation).
+// The stepping loop is branch-free: lanes of a warp step along different axes, so `if (i == 0) ...`
+// would serialise three copies of the step (ncu r01a: BSSY/BSYNC around every step).  The axis choice
+// keeps the reference's tie rule: `tmax0<tmax1 ? (tmax0<tmax2 ? 0 : 2) : (tmax1<tmax2 ? 1 : 2)`.
 // Returns the number of cells visited ("hit").
-template <class S>
+template <bool MASKED, class S>
 __device__ __forceinline__ int walk_brick(const BrickGeom &g, const double (&vp)[3], const double (&vd)[3],
                                           double max_t, S &smp)
 {
@@ -110,21 +120,44 @@ __device__ __forceinline__ int walk_brick(const BrickGeom &g, const double (&vp)
     }
     double enter_t = intersect_t;
     int hit = 0;
-    while (true) {
+    // Rare: a start index the reference leaves unguarded (e.g. cur == dims while stepping down, a ray
+    // entering exactly through an edge).  The reference samples that out-of-range cell over a zero-length
+    // segment and walks on; we walk the same steps without touching memory.
+    while (cur[0] < 0 || cur[0] >= g.dims[0] || cur[1] < 0 || cur[1] >= g.dims[1] || cur[2] < 0 || cur[2] >= g.dims[2]) {
         hit++;
+        smp.skipped_cell();
         int i;
         if (tmax[0] < tmax[1]) i = (tmax[0] < tmax[2]) ? 0 : 2;
         else                   i = (tmax[1] < tmax[2]) ? 1 : 2;
-        const double tm = (i == 0) ? tmax[0] : ((i == 1) ? tmax[1] : tmax[2]);
-        const double exit_t = tm < max_t ? tm : max_t;
-        smp.cell(enter_t, exit_t, cur[0], cur[1], cur[2]);
-        enter_t = tm;
         bool out;
-        if (i == 0)      { cur[0] += step[0]; tmax[0] = dadd(tmax[0], tdelta[0]); out = cur[0] < 0 || cur[0] >= g.dims[0]; }
-        else if (i == 1) { cur[1] += step[1]; tmax[1] = dadd(tmax[1], tdelta[1]); out = cur[1] < 0 || cur[1] >= g.dims[1]; }
-        else             { cur[2] += step[2]; tmax[2] = dadd(tmax[2], tdelta[2]); out = cur[2] < 0 || cur[2] >= g.dims[2]; }
-        if (out || enter_t >= max_t) break;
+        if (i == 0)      { enter_t = tmax[0]; cur[0] += step[0]; tmax[0] = dadd(tmax[0], tdelta[0]); out = cur[0] < 0 || cur[0] >= g.dims[0]; }
+        else if (i == 1) { enter_t = tmax[1]; cur[1] += step[1]; tmax[1] = dadd(tmax[1], tdelta[1]); out = cur[1] < 0 || cur[1] >= g.dims[1]; }
+        else             { enter_t = tmax[2]; cur[2] += step[2]; tmax[2] = dadd(tmax[2], tdelta[2]); out = cur[2] < 0 || cur[2] >= g.dims[2]; }
+        if (out || enter_t >= max_t) return hit;
     }
+    // cells left before the walk leaves the brick along each axis (an axis with step 0 never runs out)
+    int rem0 = step[0] > 0 ? g.dims[0] - 1 - cur[0] : (step[0] < 0 ? cur[0] : 0x7fffffff);
+    int rem1 = step[1] > 0 ? g.dims[1] - 1 - cur[1] : (step[1] < 0 ? cur[1] : 0x7fffffff);
+    int rem2 = step[2] > 0 ? g.dims[2] - 1 - cur[2] : (step[2] < 0 ? cur[2] : 0x7fffffff);
+    double t0 = tmax[0], t1 = tmax[1], t2 = tmax[2];
+    const double d0 = tdelta[0], d1 = tdelta[1], d2 = tdelta[2];
+    smp.template begin<MASKED>(cur, step);
+    bool go;
+    do {
+        hit++;
+        const bool a01 = t0 < t1, a02 = t0 < t2, a12 = t1 < t2;
+        const bool is0 = a01 && a02, is1 = !a01 && a12;
+        const bool is2 = !(is0 || is1);
+        const double tm = is0 ? t0 : (is1 ? t1 : t2);
+        const double exit_t = tm < max_t ? tm : max_t;
+        smp.template cell<MASKED>(enter_t, exit_t);
+        enter_t = tm;
+        if (is0) { t0 = dadd(t0, d0); rem0--; }
+        if (is1) { t1 = dadd(t1, d1); rem1--; }
+        if (is2) { t2 = dadd(t2, d2); rem2--; }
+        smp.template advance<MASKED>(is0, is1, is2);
+        go = (rem0 | rem1 | rem2) >= 0 && !(enter_t >= max_t);
+    } while (go);
     return hit;
 }
 
@@ -304,13 +337,26 @@ __device__ __forceinline__ void eval_transfer32(const DevTF &tf, const float2 *p
 // bins): the (r,g,b,a) row of every bin is replicated NCOPY (8) times, copy k living in 16-byte
 // bank group k, and lane l reads copy l & 7.  The 8 lanes of each LDS.128 quarter-warp then
 // touch 8 distinct bank groups whatever their bins are: 4 wavefronts per load, the minimum.
+// Per-lane state of the colour fast path is just `base`; every other constant is read from the kernel
+// parameters (constant bank operands cost no registers).
 struct ColourTable {
-    unsigned base;     // shared-space byte address of this lane's copy of bin 0
-    float b0_hi, b0_lo, b1, idbin;
-    int nbins_m2;
+    unsigned base;     // shared-space byte address of this lane's copy of row 0, pre-biased (see colour_cell_run)
+    const DevTF *tf;   // kernel-parameter copy of the table description:
+                       //   b0_hi[0]            fp32 head of the lower bound; its tail is folded into colour_c0
+                       //   idbin_f[0], colour_c0   row coordinate of a value: fb = (val - b0_hi) * idbin + c0
+                       //   colour_lo/hi        row coordinates of the bounds: a sample is valid iff lo < fb < hi
+                       //   colour_mid/half     (lo + hi) / 2 and (hi - lo) / 2: valid iff |fb - mid| < half
+                       //   colour_zrow         row coordinate of the value 0 (rejected when 0 lies inside the bounds)
+                       //   colour_band         bound on the fp32 error of a row coordinate near the thresholds
+                       //   colour_clamp_bound  upper bound of any table product that meets dt before a clamp
 };
 constexpr int COLOUR_COPIES = 8;                      // replication factor
-constexpr unsigned COLOUR_ROW_BYTES = COLOUR_COPIES * 16;  // bytes between consecutive bins
+constexpr unsigned COLOUR_ROW_BYTES = COLOUR_COPIES * 16;  // bytes between consecutive rows
+// Row layout (per copy): [0, 0, y_0 ... y_{n-1}, y_{n-1}] -> n + 3 rows.  Row index = bin + 2, so that
+// the two leading zero rows serve every rejected sample without a branch, and bin == n-1 (a value that
+// rounds onto b1) interpolates between two copies of the last entry.
+constexpr int COLOUR_PAD_ROWS = 3;
+constexpr float COLOUR_MAGIC = 8388608.f;             // 2^23: x + 2^23 rounded down == 2^23 + floor(x)
 
 __device__ __forceinline__ float4 lds128(unsigned addr)
 {
@@ -333,15 +379,26 @@ struct CornersP {
     float2 p1, d1;  // (c010, c110) and their z-increments
 };
 
+// Corners converted to table ROW COORDINATES at load time: trilinear interpolation commutes with the
+// affine map val -> (val - b0) * idbin + 2, so the sample loop gets the row coordinate straight out of
+// the interpolation (saves a subtract and an FMA per sample for ~10 packed ops per cell).  The subtract
+// comes first so that |b0| >> (b1 - b0) (log fields) does not cancel catastrophically.
+// Returns whether all 8 corners are exactly (+-)0.
 template <typename T>
-__device__ __forceinline__ void load_corners_p(CornersP &c, const T *d, int sx, int sy)
+__device__ __forceinline__ bool load_corners_rows(CornersP &c, const T *d, int sx, int sy, const ColourTable &ct)
 {
     const float a0 = (float)__ldg(d), a1 = (float)__ldg(d + 1);
     const float b0 = (float)__ldg(d + sy), b1 = (float)__ldg(d + sy + 1);
     const float e0 = (float)__ldg(d + sx), e1 = (float)__ldg(d + sx + 1);
     const float f0 = (float)__ldg(d + sx + sy), f1 = (float)__ldg(d + sx + sy + 1);
-    c.p0 = make_float2(a0, e0); c.d0 = make_float2(a1 - a0, e1 - e0);
-    c.p1 = make_float2(b0, f0); c.d1 = make_float2(b1 - b0, f1 - f0);
+    const float2 nb = bcast2(-ct.tf->b0_hi[0]), sc = bcast2(ct.tf->idbin_f[0]), c0 = bcast2(ct.tf->colour_c0);
+    const float2 lo0 = fma2(add2(make_float2(a0, e0), nb), sc, c0), hi0 = fma2(add2(make_float2(a1, e1), nb), sc, c0);
+    const float2 lo1 = fma2(add2(make_float2(b0, f0), nb), sc, c0), hi1 = fma2(add2(make_float2(b1, f1), nb), sc, c0);
+    c.p0 = lo0; c.d0 = fma2(lo0, make_float2(-1.f, -1.f), hi0);
+    c.p1 = lo1; c.d1 = fma2(lo1, make_float2(-1.f, -1.f), hi1);
+    const unsigned bits = (__float_as_uint(a0) | __float_as_uint(a1) | __float_as_uint(b0)) | (__float_as_uint(b1) | __float_as_uint(e0) | __float_as_uint(e1)) |
+                          (__float_as_uint(f0) | __float_as_uint(f1));
+    return (bits << 1) == 0u;
 }
 
 // Accumulators of one ray on the ColorTransferFunction path: colour C and (PARTIAL) transmittance B.
@@ -352,51 +409,97 @@ struct ColourAcc {
 
 // All n_samples samples of one cell: trilinear value -> 4-table lookup -> composite
 // (image_samplers.pyx:480-487 + field_interpolation_tables.pxd:66-110, fp32).
-template <bool PARTIAL, bool GREY>
-__device__ __forceinline__ void colour_cell_run(const CornersP &c, const ColourTable &ct, int n_samples, float x, float y, float z,
+//
+// Instruction diet (ncu r01a: 56 thread-instructions per sample, XU pipe 20 % busy with F2I/I2F):
+//   * the corners are already in row coordinates, so the interpolated value IS the row coordinate;
+//   * floor() and the row address come from one round-down add of 2^23 (FADD.RM): the integer part
+//     sits in the mantissa bits, so `bits * 128 + base` is the row address (base is pre-biased) and
+//     `(t - 2^23)` is the integer part as a float -- no F2I, no I2F, no clamps;
+//   * rejected samples (out of bounds, NaN, inf) are steered between the two zero rows by ONE select on
+//     the row coordinate instead of selects on fraction and alpha; exact zeros are rejected per cell;
+//   * CLAMP=false drops the max(1 - dt*T, 0) clamps when the caller proved dt*T <= 1 for the cell.
+template <bool PARTIAL, bool GREY, bool CLAMP, bool EDGE>
+__device__ __forceinline__ float colour_cell_run(const CornersP &c, const ColourTable &ct, int n_samples, float x, float y, float z,
                                                 float sx, float sy, float sz, float dt, ColourAcc &A)
 {
+    float closest = 3.0e38f;
     const float2 neg1 = make_float2(-1.f, -1.f), one2 = make_float2(1.f, 1.f);
-    float2 zz = bcast2(z), yy = bcast2(y);
-    const float2 szz = bcast2(sz), syy = bcast2(sy);
-#pragma unroll 2
+    float2 zy = make_float2(z, y);
+    const float2 szy = make_float2(sz, sy);
+#ifndef YTB_SAMPLE_UNROLL
+#define YTB_SAMPLE_UNROLL 2
+#endif
+    constexpr int kUnroll = YTB_SAMPLE_UNROLL;
+#pragma unroll kUnroll
     for (int s = 0; s < n_samples; s++) {
         // trilinear (fixed_interpolator.cpp:34-52): z pairs, y pair, x
+#if defined(YTB_SCALAR_TRILINEAR)
+        const float v00 = fmaf(zy.x, c.d0.x, c.p0.x), v10 = fmaf(zy.x, c.d0.y, c.p0.y);
+        const float v01 = fmaf(zy.x, c.d1.x, c.p1.x), v11 = fmaf(zy.x, c.d1.y, c.p1.y);
+        const float2 v = make_float2(fmaf(zy.y, v01 - v00, v00), fmaf(zy.y, v11 - v10, v10));
+#else
+        const float2 zz = bcast2(zy.x), yy = bcast2(zy.y);
         const float2 va = fma2(zz, c.d0, c.p0);        // (v00, v10)
         const float2 vb = fma2(zz, c.d1, c.p1);        // (v01, v11)
         const float2 v = fma2(yy, fma2(va, neg1, vb), va);  // (v0, v1)
-        const float val = fmaf(x, v.y - v.x, v.x);
-        zz = add2(zz, szz); yy = add2(yy, syy); x += sx;
-        // FIT_get_value for the 4 tables at once; rejects (out of bounds, 0, NaN, inf) zero alpha,
-        // which zeroes the alpha-weighted RGB too -> identity map, no branch.
-        const float u = (val - ct.b0_hi) - ct.b0_lo;
-        const bool valid = (u > 0.f) && (val < ct.b1) && (val != 0.f);
-        const float fb = u * ct.idbin;
-        int bin = (int)fb;  // NaN -> 0
-        bin = max(0, min(bin, ct.nbins_m2));
-        const float fr = valid ? fb - (float)bin : 0.f;
-        const unsigned addr = ct.base + (unsigned)bin * COLOUR_ROW_BYTES;
+#endif
+        const float fb = fmaf(x, v.y - v.x, v.x);      // row coordinate of the sample value
+        zy = add2(zy, szy); x += sx;
+        // FIT_get_value for the 4 tables at once.  margin < 0 <=> b0 < value < b1 (false for NaN).
+        // EDGE: keep the smallest |margin| of the cell; the caller compares it with the fp32 error band.
+        const float margin = fabsf(fb - ct.tf->colour_mid) - ct.tf->colour_half;
+        const bool valid = margin < 0.f;
+        if (EDGE) closest = fminf(closest, fabsf(margin));
+        const float fs = valid ? fb : 0.5f;
+        const float t = __fadd_rd(fs, COLOUR_MAGIC);   // 2^23 + floor(fs)
+        const float fr = fs - (t - COLOUR_MAGIC);
+        const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_ROW_BYTES + ct.base;
         const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
         const float2 fr2 = bcast2(fr);
         const float2 rg = fma2(fr2, fma2(make_float2(t0.x, t0.y), neg1, make_float2(t1.x, t1.y)), make_float2(t0.x, t0.y));
         const float2 ba = fma2(fr2, fma2(make_float2(t0.z, t0.w), neg1, make_float2(t1.z, t1.w)), make_float2(t0.z, t0.w));
-        const float adt = (valid ? ba.y : 0.f) * dt;   // dt * alpha-table value
+        const float adt = ba.y * dt;                   // dt * alpha-table value
         const float2 e01 = mul2(rg, bcast2(adt));      // dt * T_r, dt * T_g (RGB weighted by alpha)
         const float e2 = ba.x * adt;
         if (GREY) {
-            const float ta = fmaxf(1.f - adt, 0.f);
+            float ta = 1.f - adt;
+            if (CLAMP) ta = fmaxf(ta, 0.f);
             A.c01 = fma2(bcast2(ta), A.c01, e01);
             A.c2 = fmaf(ta, A.c2, e2);
             A.c3 = fmaf(ta, A.c3, adt);
             if (PARTIAL) { A.b01 = mul2(A.b01, bcast2(ta)); A.b2 *= ta; A.b3 *= ta; }
         } else {
             float2 a01 = fma2(e01, neg1, one2);
-            a01.x = fmaxf(a01.x, 0.f); a01.y = fmaxf(a01.y, 0.f);
-            const float a2 = fmaxf(1.f - e2, 0.f);
+            float a2 = 1.f - e2;
+            if (CLAMP) { a01.x = fmaxf(a01.x, 0.f); a01.y = fmaxf(a01.y, 0.f); a2 = fmaxf(a2, 0.f); }
             A.c01 = fma2(a01, A.c01, e01);
             A.c2 = fmaf(a2, A.c2, e2);
             if (PARTIAL) { A.b01 = mul2(A.b01, a01); A.b2 *= a2; }
         }
+    }
+    return closest;
+}
+
+// One sample on the careful path: `fs` is the row coordinate (0.5 if the sample was rejected); same table
+// lookup and compositing as colour_cell_run, with the clamps always on.
+template <bool PARTIAL, bool GREY>
+__device__ __forceinline__ void colour_sample(const ColourTable &ct, float fs, float dt, ColourAcc &A)
+{
+    const float t = __fadd_rd(fs, COLOUR_MAGIC);
+    const float fr = fs - (t - COLOUR_MAGIC);
+    const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_ROW_BYTES + ct.base;
+    const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
+    const float r = fmaf(fr, t1.x - t0.x, t0.x), g = fmaf(fr, t1.y - t0.y, t0.y), b = fmaf(fr, t1.z - t0.z, t0.z);
+    const float adt = fmaf(fr, t1.w - t0.w, t0.w) * dt;
+    const float e0 = r * adt, e1 = g * adt, e2 = b * adt;
+    if (GREY) {
+        const float ta = fmaxf(1.f - adt, 0.f);
+        A.c01.x = fmaf(ta, A.c01.x, e0); A.c01.y = fmaf(ta, A.c01.y, e1); A.c2 = fmaf(ta, A.c2, e2); A.c3 = fmaf(ta, A.c3, adt);
+        if (PARTIAL) { A.b01.x *= ta; A.b01.y *= ta; A.b2 *= ta; A.b3 *= ta; }
+    } else {
+        const float a0 = fmaxf(1.f - e0, 0.f), a1 = fmaxf(1.f - e1, 0.f), a2 = fmaxf(1.f - e2, 0.f);
+        A.c01.x = fmaf(a0, A.c01.x, e0); A.c01.y = fmaf(a1, A.c01.y, e1); A.c2 = fmaf(a2, A.c2, e2);
+        if (PARTIAL) { A.b01.x *= a0; A.b01.y *= a1; A.b2 *= a2; }
     }
 }
 

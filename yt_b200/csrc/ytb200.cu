@@ -174,6 +174,11 @@ static int fill_geometry(ytb200_brickset *s, int64_t index, const int64_t dims[3
         b.dds[i] = (b.re[i] - b.le[i]) / (double)dims[i];  // partitioned_grid.pyx:51-52
         b.idds[i] = 1.0 / b.dds[i];
     }
+    // the kernels follow the walk with 32-bit running element offsets
+    const double nelem = ((double)dims[0] + 1.0) * ((double)dims[1] + 1.0) * ((double)dims[2] + 1.0);
+    if (nelem >= 4294967296.0)
+        return fail(E_UNSUPPORTED, "brick %lld has %.3g elements per field; split it on cell boundaries below 2^32 "
+                    "(sub-bricks reproduce the single-brick image, SURVEY.md finding 6)", (long long)index, nelem);
     b.n_fields = s->n_fields;
     s->committed = false;
     return 0;
@@ -342,7 +347,7 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
         const double dbin = (b1 - b0) / (nbins[i] - 1), idbin = 1.0 / dbin;
         d.b0[i] = b0; d.b1[i] = b1; d.idbin[i] = idbin;
         d.b0_hi[i] = (float)b0; d.b0_lo[i] = (float)(b0 - (double)d.b0_hi[i]);
-        d.b1_f[i] = (float)b1; d.idbin_f[i] = (float)idbin;
+        d.b0_f[i] = (float)b0; d.b1_f[i] = (float)b1; d.idbin_f[i] = (float)idbin;
         for (int j = 0; j < nbins[i]; j++) {
             const int o = d.offset[i] + j;
             values[o] = y[i][j];
@@ -369,13 +374,36 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
     rc |= to_device(t, dy, &d.dy);
     rc |= to_device(t, pairs, &d.pairs);
     if (colour) {
-        std::vector<float4> col((size_t)nbins[0]);
-        for (int j = 0; j < nbins[0]; j++)
-            col[j] = make_float4((float)y[0][j], (float)y[1][j], (float)y[2][j], (float)y[3][j]);
+        // rows [0, 0, y_0 .. y_{n-1}, y_{n-1}] (raycast.cuh, COLOUR_PAD_ROWS): row = bin + 2
+        const int nb = nbins[0];
+        std::vector<float4> col((size_t)nb + COLOUR_PAD_ROWS, make_float4(0.f, 0.f, 0.f, 0.f));
+        double rgb_max = 0.0, a_max = 0.0;
+        for (int j = 0; j < nb; j++) {
+            col[(size_t)j + 2] = make_float4((float)y[0][j], (float)y[1][j], (float)y[2][j], (float)y[3][j]);
+            rgb_max = fmax(rgb_max, fmax(fabs(y[0][j]), fmax(fabs(y[1][j]), fabs(y[2][j]))));
+            a_max = fmax(a_max, fabs(y[3][j]));
+        }
+        col[(size_t)nb + 2] = col[(size_t)nb + 1];
         rc |= to_device(t, col, &d.colour);
-        // the fast path replicates every row 8x in shared memory (bank-conflict-free): <= 64 KiB
+        // the fast path replicates every row 8x in shared memory (bank-conflict-free): <= 64.4 KiB at 512 bins
         d.colour_copy_shift = 3;
-        if (nbins[0] > 512) d.colour_fast = 0;
+        const double b0 = bounds[0], b1 = bounds[1];
+        const double idbin = d.idbin[0];
+        // fb = (val - b0_hi) * idbin + c0 with c0 = 2 - b0_lo * idbin  (== (val - b0) * idbin + 2)
+        d.colour_c0 = (float)(2.0 - (b0 - (double)d.b0_hi[0]) * idbin);
+        // every product that meets dt before a clamp: alpha (grey) or alpha * colour (RGB weighted by alpha)
+        d.colour_clamp_bound = (float)(1.0000002 * a_max * fmax(1.0, rgb_max));
+        d.colour_zero_inside = (b0 < 0.0 && b1 > 0.0) ? 1 : 0;
+        // does a sample flipping across a bound change the result?  Only if the alpha table (which also
+        // weights R, G, B) does not vanish there.
+        const double edge = fmax(fabs(y[3][0]), fabs(y[3][nb - 1])) * fmax(1.0, rgb_max);
+        d.colour_edge = edge > 1e-30 ? 1 : 0;
+        d.colour_lo = 2.f; d.colour_hi = (float)(nb + 1);
+        d.colour_mid = 0.5f * (float)(nb + 3); d.colour_half = 0.5f * (float)(nb - 1);
+        d.colour_band = 4e-6f * (float)(nb + 512);
+        // row coordinate of the value 0, with the very operations load_corners_rows applies to a corner
+        d.colour_zrow = fmaf(0.f - d.b0_hi[0], d.idbin_f[0], d.colour_c0);
+        if (nb > 512 || !std::isfinite(d.colour_clamp_bound) || !std::isfinite(d.colour_c0)) d.colour_fast = 0;
     }
     if (rc) { ytb200_tf_destroy(t); return rc; }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -554,7 +582,7 @@ template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T>
 static cudaError_t launch_one(const CastParams &p, unsigned grid, size_t smem, cudaStream_t st)
 {
     auto k = cast_kernel<KIND, EXACT, TFM, PARTIAL, NF1, T>;
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {  // static shared memory counts against the 48 KiB default too
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
@@ -574,12 +602,13 @@ template <int KIND, int TFM>
 static cudaError_t launch_kind(const CastParams &p, unsigned grid, size_t smem, cudaStream_t st, bool exact, bool f64,
                                bool partial, bool nf1)
 {
+    constexpr int TFM_MULTI = tfm_is_colour(TFM) ? TFM_GENERAL : TFM;  // the colour fast path is single-field
     if (partial) {
         if (nf1) return launch_prec<KIND, TFM, true, true>(p, grid, smem, st, exact, f64);
-        return launch_prec<KIND, (TFM == TFM_COLOUR ? TFM_GENERAL : TFM), true, false>(p, grid, smem, st, exact, f64);
+        return launch_prec<KIND, TFM_MULTI, true, false>(p, grid, smem, st, exact, f64);
     }
     if (nf1) return launch_prec<KIND, TFM, false, true>(p, grid, smem, st, exact, f64);
-    return launch_prec<KIND, (TFM == TFM_COLOUR ? TFM_GENERAL : TFM), false, false>(p, grid, smem, st, exact, f64);
+    return launch_prec<KIND, TFM_MULTI, false, false>(p, grid, smem, st, exact, f64);
 }
 
 static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order, int64_t n_order,
@@ -612,6 +641,7 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
         p.cam = f->cam;
         p.bricks = set->dev; p.order = f->order_dev; p.extent = f->extent_dev; p.n_order = (int)n_order;
         p.n_samples = n_samples < 1 ? 1 : n_samples;
+        p.inv_ns = 1.0 / (double)p.n_samples;
         p.image = f->image; p.zbuffer = f->zbuffer; p.partial = partial;
         if (tf) p.tf = tf->d;
         p.counters = f->ctx->counters;
@@ -623,11 +653,23 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
         if (kind == YTB200_VOLUME_RENDER) {
             const bool colour = !exact && nf1 && tf->d.colour_fast;
             if (exact) smem = (size_t)tf->d.total_bins * 3 * sizeof(double);
-            else if (colour) smem = ((size_t)tf->d.nbins[0] << tf->d.colour_copy_shift) * sizeof(float4);
+            else if (colour) smem = ((size_t)(tf->d.nbins[0] + COLOUR_PAD_ROWS) << tf->d.colour_copy_shift) * sizeof(float4);
             else smem = (size_t)tf->d.total_bins * sizeof(float2);
             if (smem > 200 * 1024) return fail(E_UNSUPPORTED, "transfer function tables (%zu B) exceed shared memory", smem);
-            if (colour) e = launch_kind<KIND_VR, TFM_COLOUR>(p, grid, smem, st, exact, f64, partial != nullptr, nf1);
-            else e = launch_kind<KIND_VR, TFM_GENERAL>(p, grid, smem, st, exact, f64, partial != nullptr, nf1);
+            if (colour) {
+                const int mode = (tf->d.grey ? TFM_GREY : 0) | (tf->d.colour_zero_inside ? TFM_ZERO_INSIDE : 0) | (tf->d.colour_edge ? TFM_EDGE : 0);
+                const bool pt = partial != nullptr;
+                switch (mode) {
+                case 0: e = launch_kind<KIND_VR, TFM_COLOUR + 0>(p, grid, smem, st, exact, f64, pt, nf1); break;
+                case 1: e = launch_kind<KIND_VR, TFM_COLOUR + 1>(p, grid, smem, st, exact, f64, pt, nf1); break;
+                case 2: e = launch_kind<KIND_VR, TFM_COLOUR + 2>(p, grid, smem, st, exact, f64, pt, nf1); break;
+                case 3: e = launch_kind<KIND_VR, TFM_COLOUR + 3>(p, grid, smem, st, exact, f64, pt, nf1); break;
+                case 4: e = launch_kind<KIND_VR, TFM_COLOUR + 4>(p, grid, smem, st, exact, f64, pt, nf1); break;
+                case 5: e = launch_kind<KIND_VR, TFM_COLOUR + 5>(p, grid, smem, st, exact, f64, pt, nf1); break;
+                case 6: e = launch_kind<KIND_VR, TFM_COLOUR + 6>(p, grid, smem, st, exact, f64, pt, nf1); break;
+                default: e = launch_kind<KIND_VR, TFM_COLOUR + 7>(p, grid, smem, st, exact, f64, pt, nf1); break;
+                }
+            } else e = launch_kind<KIND_VR, TFM_GENERAL>(p, grid, smem, st, exact, f64, partial != nullptr, nf1);
         } else if (kind == YTB200_INTERPOLATED_PROJECTION) {
             e = launch_kind<KIND_IPROJ, TFM_NONE>(p, grid, 0, st, exact, f64, partial != nullptr, nf1);
         } else {
