@@ -117,3 +117,35 @@ def test_leaves_tile_the_domain_and_bricks_slice_the_grids():
         for c in g.Children:
             overlap = np.minimum(b.RightEdge, c.RightEdge) - np.maximum(b.LeftEdge, c.LeftEdge)
             assert not np.all(overlap > 1e-12)
+
+
+@pytest.mark.parametrize("size", [2, 4, 8])
+def test_rank_subtrees_partition_the_leaves_and_paths_follow_rank_bits(size):
+    """Each rank builds only its own subtree (should_i_build); together they hold every serial leaf, and the
+    kd path handed to the binary swap is the chain of splits above heap node size + rank."""
+    from yt_b200 import parallel
+    ds = cases()["nested3"]
+    serial = Tree(ds)
+    sn = serial.nodes
+    serial_leaves = sorted((tuple(sn["left_edge"][i]), tuple(sn["right_edge"][i]), int(sn["grid"][i])) for i in serial.traverse())
+    mine = []
+    k = int(np.log2(size))
+    for rank in range(size):
+        t = Tree(ds, comm_rank=rank, comm_size=size)
+        nd = t.nodes
+        mine += [(tuple(nd["left_edge"][i]), tuple(nd["right_edge"][i]), int(nd["grid"][i])) for i in t.traverse()]
+        path = parallel.kd_path_of_rank(nd, rank, size)
+        assert len(path) == k
+        for level, (ax, pos, upper) in enumerate(path):
+            assert upper == bool((rank >> (k - 1 - level)) & 1)
+        # the subtree root's box is the intersection of the half-spaces along the path
+        by_id = {int(i): n for n, i in enumerate(nd["node_id"])}
+        root = by_id[size + rank]
+        for ax, pos, upper in path:
+            if upper:
+                assert nd["left_edge"][root][ax] >= pos
+            else:
+                assert nd["right_edge"][root][ax] <= pos
+        rounds, strip = parallel.plan_binary_swap(rank, size, 1000, path, np.array([2.0, -1.0, 0.3]))
+        assert len(rounds) == k
+    assert sorted(mine) == serial_leaves

@@ -105,7 +105,11 @@ class AMRKDTree:
     log_fields = None
     no_ghost = True
 
-    def __init__(self, ds, min_level=None, max_level=None, data_source=None, comm_rank=0, comm_size=1):
+    def __init__(self, ds, min_level=None, max_level=None, data_source=None, comm_rank=None, comm_size=None):
+        from . import parallel
+        if comm_rank is None:
+            comm_rank, comm_size = parallel.comm_rank(), parallel.comm_size()
+        self.comm_rank, self.comm_size = comm_rank, comm_size
         if not hasattr(ds.index, "grids"):
             raise RuntimeError("AMRKDTree does not support particle or octree-based data.")
         self.ds = ds
@@ -202,9 +206,17 @@ class AMRKDTree:
             raise RuntimeError("device_bricks() must be called first")
         return self._leaf_slot[self.tree.traverse(viewpoint)]
 
-    # -- parallel reduction: single process here; multi-GPU compositing is yt_b200.parallel ----------------
+    # -- parallel reduction -------------------------------------------------------------------------------
     def reduce_tree_images(self, image, viewpoint, *, use_opacity=True):
+        """Single process: nothing to do.  With several ranks the compositing happens on the devices, inside
+        ``ImageSampler.flush_parallel`` (binary swap of affine partial images), before the image reaches the
+        host -- so by the time the reference would call this, `image` is already the reduced one."""
         return image
+
+    def kd_path(self):
+        """Splits from the root down to this rank's subtree (see parallel.kd_path_of_rank)."""
+        from . import parallel
+        return parallel.kd_path_of_rank(self.tree.nodes, self.comm_rank, self.comm_size)
 
     def locate_node(self, pos):
         nd = self.tree.nodes

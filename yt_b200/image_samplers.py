@@ -181,6 +181,47 @@ class ImageSampler:
         fr.download(self.aimage_host)
         self._pending, self._batches, self._dirty = [], [], False
 
+    def flush_parallel(self, swap, broadcast=True):
+        """Multi-GPU flush: cast this rank's bricks into an affine partial image, composite the partials
+        of all ranks in view order (binary swap), leave the result in the host image of rank 0 (of every
+        rank with ``broadcast``).  Replaces reduce_tree_images (amr_kdtree.py:297-323)."""
+        import torch
+        fr = self._frame
+        fr.upload(self.aimage_host, self.azbuffer)
+        work = list(self._batches)
+        if self._pending:
+            bs = build_brickset(self._pending, self._ctx, self._storage)
+            work.append((bs, np.arange(len(self._pending), dtype=np.int64)))
+        nx, ny = self.aimage_host.shape[:2]
+        dev = torch.device("cuda", self._ctx.device)
+        stream = torch.cuda.ExternalStream(self._ctx.stream, device=dev)
+        with torch.cuda.stream(stream):
+            partial = torch.empty((nx * ny, 8), dtype=torch.float64, device=dev)
+            if len(work) > 1:
+                raise NotImplementedError("one brick set per parallel flush")
+            if work:
+                bs, order = work[0]
+            else:
+                bs, order = self._empty_set(), np.zeros(0, dtype=np.int64)
+            fr.cast_partial(self.kind, bs, order, partial.data_ptr(), tf=self._tables, n_samples=self.n_samples,
+                            precision=self._precision)
+            swap.composite(partial, fr, broadcast=broadcast)
+            stream.synchronize()
+        if broadcast or swap.rank == 0:
+            fr.download(self.aimage_host)
+        self._pending, self._batches, self._dirty = [], [], False
+
+    def _empty_set(self):
+        """A committed one-brick set far outside any view box, for ranks that own no brick."""
+        cen = L.CELL_CENTRED if self.kind == L.PROJECTION else L.VERTEX_CENTRED
+        n = 1 if cen == L.CELL_CENTRED else 2
+        nf = 1
+        if self._tables is not None:
+            nf = 1 + max(int(f) for f in list(self.tf_obj.field_ids)[: self.tf_obj.n_field_tables])
+        pg = PartitionedGrid(-1, [np.zeros((n, n, n))] * nf, np.ones((1, 1, 1), "uint8"), np.full(3, 1e30), np.full(3, 2e30),
+                             np.ones(3, "int64"))
+        return build_brickset([pg], self._ctx, self._storage)
+
     @property
     def aimage(self):
         self.flush()

@@ -11,7 +11,62 @@ Order: the partner pair of round j are the two children of the kd split at depth
 child is applied first follows the reference's traversal rule (amr_kdtools.pyx:708-755):
 ``viewpoint[dim] <= pos`` -> the upper child is farther and therefore composited first.
 """
+import os
+
 import numpy as np
+
+# ---- communicator: one process per GPU (torchrun), torch.distributed for the plumbing -------------------
+_comm = {"rank": 0, "size": 1, "group": None, "backend": None}
+
+
+def enable_parallelism(backend=None):
+    """``yt.enable_parallelism()`` for the ray caster: join the torchrun process group (NCCL when CUDA is
+    visible, gloo otherwise) and bind this process to GPU ``LOCAL_RANK``.  Returns (rank, size)."""
+    size = int(os.environ.get("WORLD_SIZE", "1"))
+    if size == 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend, **kw)
+    _comm.update(rank=dist.get_rank(), size=dist.get_world_size(), backend=dist.get_backend())
+    if _comm["size"] & (_comm["size"] - 1):
+        raise RuntimeError("the kd-tree partition needs a power-of-two number of ranks (got %d)" % _comm["size"])
+    return _comm["rank"], _comm["size"]
+
+
+def comm_rank():
+    return _comm["rank"]
+
+
+def comm_size():
+    return _comm["size"]
+
+
+def kd_path_of_rank(nodes, rank, size):
+    """[(axis, split_pos, is_upper)] from the root split down to the subtree owned by `rank`: heap node
+    ``size + rank`` (amr_kdtools.pyx:670-676, amr_kdtree.py:283-295).  `nodes` is Tree.nodes.  Levels that
+    do not exist (an empty region was never split) get a dummy split: both sides are empty there."""
+    k = int(round(np.log2(size))) if size > 1 else 0
+    by_id = {int(i): n for n, i in enumerate(nodes["node_id"])}
+    path = []
+    target = size + rank
+    for level in range(k):
+        anc = target >> (k - level)          # ancestor at this depth
+        upper = (target >> (k - level - 1)) & 1
+        n = by_id.get(anc)
+        if n is None or nodes["split_dim"][n] < 0:
+            path.append((0, 0.0, bool(upper)))
+        else:
+            path.append((int(nodes["split_dim"][n]), float(nodes["split_pos"][n]), bool(upper)))
+    return path
 
 
 def bit_reverse(x, bits):
@@ -141,10 +196,21 @@ class BinarySwap:
                 w.wait()
 
     # -- frame-level convenience used by the bench and the scene mirror -----------------------------------
-    def composite(self, partial, frame):
-        """Compose this rank's partial with all others and leave the final image in rank 0's frame.
+    def composite(self, partial, frame, broadcast=False):
+        """Compose this rank's partial with all others and leave the final image in rank 0's frame (in
+        every rank's frame with ``broadcast``, like scatter_image of amr_kdtools.py:43-50).
         The frame's device image must already hold the initial colours C_0 (``frame.clear()`` or
         ``frame.upload()``), exactly what it held when the partial was cast."""
         image = self.torch.as_tensor(_DevArray(frame.device_image, (self.npx, 4)), device=partial.device)
         self.composite_tensors(partial, image)
-        self.gather_strips(image, 0)
+        if broadcast and self.world > 1:
+            self.allgather_strips(image)
+        else:
+            self.gather_strips(image, 0)
+
+    def allgather_strips(self, image):
+        """Every rank ends up with every strip (strips have equal length up to the halving remainders)."""
+        dist = self.torch.distributed
+        for r, (p0, p1) in enumerate(self.strips):
+            if p1 > p0:
+                dist.broadcast(image[p0:p1], src=r, group=self.group)

@@ -270,7 +270,18 @@ class KDTreeVolumeSource(VolumeSource):
                 for data in brick.my_data:
                     if np.any(np.isnan(data)):
                         raise RuntimeError
-        if self.batched:
+        if self.volume.comm_size > 1:
+            # one process per GPU: this rank casts the leaves of its kd subtree; the partial images are
+            # composited in view order on the devices (replaces reduce_tree_images)
+            from ..parallel import BinarySwap
+            nx, ny = camera.resolution
+            if len(self.volume.tree.traverse()) > 0:
+                bricks = self.volume.device_bricks(self.sampler._ctx, self.sampler._storage)
+                self.sampler.cast_bricks(bricks, self.volume.view_order(camera.lens.viewpoint))
+            swap = BinarySwap(self.sampler._ctx, nx, ny, self.volume.kd_path(), camera.lens.viewpoint,
+                              self.volume.comm_rank, self.volume.comm_size)
+            self.sampler.flush_parallel(swap, broadcast=True)
+        elif self.batched:
             bricks = self.volume.device_bricks(self.sampler._ctx, self.sampler._storage)
             self.sampler.cast_bricks(bricks, self.volume.view_order(camera.lens.viewpoint))
         else:
