@@ -273,6 +273,137 @@ struct FastSampler {
         }
     }
 
+    // ------------------------------------------------------------------------------------------------
+    // The fused walk of the ColorTransferFunction path (the north-star hot loop).  Same cells, same
+    // (enter_t, exit_t) as walk_brick; what differs is the bookkeeping around them (ncu r01c: 133 of the
+    // 445 instructions per cell were not samples, and 20 % of the stall cycles waited for corner loads):
+    //   * one PTX block per cell does the axis choice, exit_t, the sample spacing and the step with
+    //     PREDICATED adds (nvcc turns `if (is0) t0 += d0` into an add plus two selects);
+    //   * the cell-local coordinate of the first sample needs no running origin: along a stepping axis
+    //     it is base + (t_mid - tmax_axis) * dc with base = 1 (stepping up) or 0 (stepping down), because
+    //     the ray leaves the cell at t = tmax_axis through that face; the cancellation t_mid - tmax is
+    //     done in fp64 (H13), the rest in fp32;
+    //   * the 8 corners of the NEXT cell are requested before the current cell is sampled, so their
+    //     latency hides behind ~300 sample instructions.
+    // ------------------------------------------------------------------------------------------------
+    template <bool MASKED>
+    __device__ __forceinline__ void walk_colour(const WalkState &w)
+    {
+        const int ny = br->dims[1], nz = br->dims[2];
+        const int vsx = (ny + 1) * (nz + 1), vsy = nz + 1;
+        float dcx[3], bse[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const double idds = br->idds[i];
+            const double vdi = ray[(3 + i) * CTA_THREADS + threadIdx.x];
+            dcx[i] = (float)(vdi * idds);
+            if (w.step[i] > 0) bse[i] = 1.f;
+            else if (w.step[i] < 0) bse[i] = 0.f;
+            else bse[i] = (float)((ray[i * CTA_THREADS + threadIdx.x] - br->le[i]) * idds - (double)w.cur[i]);
+        }
+        unsigned o = (unsigned)w.cur[0] * (unsigned)vsx + (unsigned)w.cur[1] * (unsigned)vsy + (unsigned)w.cur[2];
+        const int st0 = w.step[0] * vsx, st1 = w.step[1] * vsy, st2 = w.step[2];
+        unsigned mo = 0;
+        int ms0 = 0, ms1 = 0;
+        if (MASKED) {
+            mo = ((unsigned)w.cur[0] * (unsigned)ny + (unsigned)w.cur[1]) * (unsigned)nz + (unsigned)w.cur[2];
+            ms0 = w.step[0] * ny * nz; ms1 = w.step[1] * nz;
+        }
+        // an axis the ray does not move along keeps tmax = 1e60 in the reference; 1e30 is as unreachable and
+        // keeps (float)(t_mid - tmax) finite (times dc = 0 it contributes nothing)
+        double t0 = w.step[0] == 0 ? 1e30 : w.t0, t1 = w.step[1] == 0 ? 1e30 : w.t1, t2 = w.step[2] == 0 ? 1e30 : w.t2;
+        const double d0 = w.d0, d1 = w.d1, d2 = w.d2, max_t = w.max_t, inv_ns = prm->inv_ns;
+        int rem0 = w.rem0, rem1 = w.rem1, rem2 = w.rem2;
+        double enter_t = w.enter_t;
+        const T *data = (const T *)br->data[0];
+        RawCorners cur_c;
+        load_raw_corners(cur_c, data + o, vsx, vsy);
+        unsigned cont;
+        do {
+            const unsigned mo_cur = mo;
+            float dt, q0, q1, q2;
+            unsigned axis;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred a01, a02, a12, n01, p0, p1, p2, pc, pm;\n\t"
+                ".reg .f64 tm, ex, dl, dt, tmid, q;\n\t"
+                ".reg .s32 ds, rr;\n\t"
+                // axis of the smallest tmax, reference tie rule (grid_traversal.pyx:122-131)
+                "setp.lt.f64 a01, %0, %1;\n\t"
+                "setp.lt.f64 a02, %0, %2;\n\t"
+                "setp.lt.f64 a12, %1, %2;\n\t"
+                "and.pred p0, a01, a02;\n\t"
+                "not.pred n01, a01;\n\t"
+                "and.pred p1, n01, a12;\n\t"
+                "or.pred p2, p0, p1;\n\t"            // p2 == NOT (axis 2)
+                "selp.f64 tm, %1, %2, p1;\n\t"
+                "selp.f64 tm, %0, tm, p0;\n\t"
+                "setp.lt.f64 pm, tm, %17;\n\t"
+                "selp.f64 ex, tm, %17, pm;\n\t"       // exit_t = tm < max_t ? tm : max_t
+                // sample spacing and the first sample's distance to each exit face (fp64 cancellation)
+                "sub.rn.f64 dl, ex, %7;\n\t"
+                "mul.rn.f64 dt, dl, %18;\n\t"
+                "fma.rn.f64 tmid, dt, 0d3FE0000000000000, %7;\n\t"
+                "cvt.rn.f32.f64 %8, dt;\n\t"
+                "sub.rn.f64 q, tmid, %0;\n\t"
+                "cvt.rn.f32.f64 %9, q;\n\t"
+                "sub.rn.f64 q, tmid, %1;\n\t"
+                "cvt.rn.f32.f64 %10, q;\n\t"
+                "sub.rn.f64 q, tmid, %2;\n\t"
+                "cvt.rn.f32.f64 %11, q;\n\t"
+                // the step: cur[i] += step[i]; enter_t = tmax[i]; tmax[i] += tdelta[i]
+                "@p0 add.rn.f64 %0, %0, %14;\n\t"
+                "@p1 add.rn.f64 %1, %1, %15;\n\t"
+                "@!p2 add.rn.f64 %2, %2, %16;\n\t"
+                "@p0 add.s32 %3, %3, -1;\n\t"
+                "@p1 add.s32 %4, %4, -1;\n\t"
+                "@!p2 add.s32 %5, %5, -1;\n\t"
+                "selp.b32 ds, %20, %21, p1;\n\t"
+                "selp.b32 ds, %19, ds, p0;\n\t"
+                "add.s32 %6, %6, ds;\n\t"
+                "selp.u32 %13, 1, 2, p1;\n\t"
+                "selp.u32 %13, 0, %13, p0;\n\t"
+                // go on while the stepped index is inside the brick and enter_t < max_t (NaN goes on, like the reference)
+                "or.b32 rr, %3, %4;\n\t"
+                "or.b32 rr, rr, %5;\n\t"
+                "setp.ge.s32 pc, rr, 0;\n\t"
+                "setp.ge.f64 pm, tm, %17;\n\t"
+                "not.pred pm, pm;\n\t"
+                "and.pred pc, pc, pm;\n\t"
+                "selp.u32 %12, 1, 0, pc;\n\t"
+                "mov.f64 %7, tm;\n\t"
+                "}"
+                : "+d"(t0), "+d"(t1), "+d"(t2), "+r"(rem0), "+r"(rem1), "+r"(rem2), "+r"(o), "+d"(enter_t),
+                  "=f"(dt), "=f"(q0), "=f"(q1), "=f"(q2), "=r"(cont), "=r"(axis)
+                : "d"(d0), "d"(d1), "d"(d2), "d"(max_t), "d"(inv_ns), "r"(st0), "r"(st1), "r"(st2));
+            if (MASKED) mo += (unsigned)(axis == 0 ? ms0 : (axis == 1 ? ms1 : st2));
+            // request the next cell's corners now; they are consumed one iteration later
+            RawCorners nxt_c;
+            if (cont) load_raw_corners(nxt_c, data + o, vsx, vsy);
+            bool sample = true;
+            if (MASKED) sample = mask[mo_cur] == 1;
+            if (sample) {
+                CornersP cp;
+                const bool all_zero = rows_from_raw(cp, cur_c, ct);
+                // exact zeros are rejected by FIT_get_value (isnormal); a sample is exactly 0 essentially only
+                // where the data are (zero padding), i.e. where all 8 corners are: test the cell, not every sample
+                if (!(tfm_zero_inside(TFM) && all_zero)) {
+                    const float x = fmaf(q0, dcx[0], bse[0]), y = fmaf(q1, dcx[1], bse[1]), z = fmaf(q2, dcx[2], bse[2]);
+                    const float sxs = dcx[0] * dt, sys = dcx[1] * dt, szs = dcx[2] * dt;
+                    float m;
+                    // dt * (largest table product) <= 1: the max(1 - dt*T, 0) clamps cannot fire in this cell
+                    if (dt * tf->colour_clamp_bound <= 1.f)
+                        m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM)>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+                    else
+                        m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM)>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+                    // some sample sat within fp32 rounding of a table bound (see CarefulSampler)
+                    if (tfm_edge(TFM)) doubt = doubt || (m < tf->colour_band);
+                }
+            }
+            cur_c = nxt_c;
+        } while (cont);
+    }
+
     template <bool MASKED>
     __device__ __forceinline__ void cell(double enter_t, double exit_t)
     {
@@ -317,19 +448,7 @@ struct FastSampler {
         const float dt = (float)dt64;
         const float sxs = dcf[0] * dt, sys = dcf[1] * dt, szs = dcf[2] * dt;
         if (tfm_is_colour(TFM)) {
-            CornersP cp;
-            const bool all_zero = load_corners_rows(cp, (const T *)br->data[0] + off, sx, sy, ct);
-            // exact zeros are rejected by FIT_get_value (isnormal); a sample is exactly 0 essentially only where
-            // the data are (zero padding), i.e. where all 8 corners are: test the cell, not every sample
-            if (tfm_zero_inside(TFM) && all_zero) return;
-            // dt * (largest table product) <= 1: the max(1 - dt*T, 0) clamps cannot fire in this cell
-            float m;
-            if (dt * tf->colour_clamp_bound <= 1.f)
-                m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM)>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
-            else
-                m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM)>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
-            // some sample sat within fp32 rounding of a table bound (see CarefulSampler)
-            if (tfm_edge(TFM)) doubt = doubt || (m < tf->colour_band);
+            // the ColorTransferFunction path has its own fused walk (walk_colour)
         } else if (NF1) {
             Corners c;
             load_corners(c, (const T *)br->data[0] + off, sx, sy);
@@ -375,6 +494,16 @@ __device__ __forceinline__ void make_ray(const DevCamera &cam, int vi, int vj, d
 #pragma unroll
         for (int i = 0; i < 3; i++) { vp[i] = cam.pos_px[o + i]; vd[i] = cam.dir_px[o + i]; }
     }
+}
+
+// walk_volume for the ColorTransferFunction fast path: reference entry logic, then the fused walk
+template <class S>
+__device__ __forceinline__ void cast_colour(const BrickGeom &g, const double (&vp)[3], const double (&vd)[3], double max_t, S &smp, bool masked)
+{
+    WalkState w;
+    if (!walk_setup(g, vp, vd, max_t, smp, w)) return;
+    if (masked) smp.template walk_colour<true>(w);
+    else smp.template walk_colour<false>(w);
 }
 
 template <bool EXACT, class A, class B> struct pick_sampler { using type = A; };
@@ -504,8 +633,7 @@ cast_kernel(const __grid_constant__ CastParams p)
                     entry[0] = smp.ca.c01.x; entry[1] = smp.ca.c01.y; entry[2] = smp.ca.c2; entry[3] = smp.ca.c3;
                     if (PARTIAL) { entry[4] = smp.ca.b01.x; entry[5] = smp.ca.b01.y; entry[6] = smp.ca.b2; entry[7] = smp.ca.b3; }
                     smp.doubt = false;
-                    if (masked) walk_brick<true>(g, vp, vd, max_t, smp);
-                    else walk_brick<false>(g, vp, vd, max_t, smp);
+                    cast_colour(g, vp, vd, max_t, smp, masked);
                     if (smp.doubt) {
                         CarefulSampler<PARTIAL, tfm_grey(TFM), T> cs;
                         cs.ray = s_ray; cs.br = br; cs.tf = &p.tf; cs.base = smp.ct.base; cs.n_samples = p.n_samples;
@@ -522,6 +650,8 @@ cast_kernel(const __grid_constant__ CastParams p)
                         else walk_brick<false>(g2, vp2, vd2, max_t, cs);
                         smp.ca = cs.ca;
                     }
+                } else if constexpr (!EXACT && KIND == KIND_VR && tfm_is_colour(TFM)) {
+                    cast_colour(g, vp, vd, max_t, smp, masked);
                 } else {
                     if (masked) walk_brick<true>(g, vp, vd, max_t, smp);
                     else walk_brick<false>(g, vp, vd, max_t, smp);

@@ -58,10 +58,22 @@ __device__ __forceinline__ double snap_edge(double v, double le, double re, doub
 // would serialise three copies of the step (ncu r01a: BSSY/BSYNC around every step).  The axis choice
 // keeps the reference's tie rule: `tmax0<tmax1 ? (tmax0<tmax2 ? 0 : 2) : (tmax1<tmax2 ? 1 : 2)`.
 // Returns the number of cells visited ("hit").
-template <bool MASKED, class S>
-__device__ __forceinline__ int walk_brick(const BrickGeom &g, const double (&vp)[3], const double (&vd)[3],
-                                          double max_t, S &smp)
+struct WalkState {
+    double t0, t1, t2;      // tmax per axis
+    double d0, d1, d2;      // tdelta per axis
+    double enter_t, max_t;
+    int rem0, rem1, rem2;   // cells left before the walk leaves the brick along each axis
+    int cur[3], step[3];    // start cell and step signs
+    int hit;
+};
+
+// Everything of walk_volume up to the first sampled cell (grid_traversal.pyx:40-117).  Returns false when
+// the ray does not sample the brick at all; w.hit then holds the return value of walk_volume.
+template <class S>
+__device__ __forceinline__ bool walk_setup(const BrickGeom &g, const double (&vp)[3], const double (&vd)[3],
+                                           double max_t, S &smp, WalkState &w)
 {
+    w.hit = 0;
     if (max_t > 1.0) max_t = 1.0;
     double intersect_t = 1.1;
     int direction = -1;
@@ -92,7 +104,7 @@ __device__ __forceinline__ int walk_brick(const BrickGeom &g, const double (&vp)
             intersect_t = tl;
         }
     }
-    if (!((0.0 <= intersect_t) && (intersect_t < max_t))) return 0;
+    if (!((0.0 <= intersect_t) && (intersect_t < max_t))) return false;
     int cur[3];
     double tmax[3], tdelta[3];
 #pragma unroll
@@ -115,8 +127,8 @@ __device__ __forceinline__ int walk_brick(const BrickGeom &g, const double (&vp)
     }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        if (cur[i] == g.dims[i] && step[i] >= 0) return 0;
-        if (cur[i] == -1 && step[i] <= -1) return 0;
+        if (cur[i] == g.dims[i] && step[i] >= 0) return false;
+        if (cur[i] == -1 && step[i] <= -1) return false;
     }
     double enter_t = intersect_t;
     int hit = 0;
@@ -133,15 +145,33 @@ __device__ __forceinline__ int walk_brick(const BrickGeom &g, const double (&vp)
         if (i == 0)      { enter_t = tmax[0]; cur[0] += step[0]; tmax[0] = dadd(tmax[0], tdelta[0]); out = cur[0] < 0 || cur[0] >= g.dims[0]; }
         else if (i == 1) { enter_t = tmax[1]; cur[1] += step[1]; tmax[1] = dadd(tmax[1], tdelta[1]); out = cur[1] < 0 || cur[1] >= g.dims[1]; }
         else             { enter_t = tmax[2]; cur[2] += step[2]; tmax[2] = dadd(tmax[2], tdelta[2]); out = cur[2] < 0 || cur[2] >= g.dims[2]; }
-        if (out || enter_t >= max_t) return hit;
+        if (out || enter_t >= max_t) { w.hit = hit; return false; }
     }
     // cells left before the walk leaves the brick along each axis (an axis with step 0 never runs out)
-    int rem0 = step[0] > 0 ? g.dims[0] - 1 - cur[0] : (step[0] < 0 ? cur[0] : 0x7fffffff);
-    int rem1 = step[1] > 0 ? g.dims[1] - 1 - cur[1] : (step[1] < 0 ? cur[1] : 0x7fffffff);
-    int rem2 = step[2] > 0 ? g.dims[2] - 1 - cur[2] : (step[2] < 0 ? cur[2] : 0x7fffffff);
-    double t0 = tmax[0], t1 = tmax[1], t2 = tmax[2];
-    const double d0 = tdelta[0], d1 = tdelta[1], d2 = tdelta[2];
-    smp.template begin<MASKED>(cur, step);
+    w.rem0 = step[0] > 0 ? g.dims[0] - 1 - cur[0] : (step[0] < 0 ? cur[0] : 0x7fffffff);
+    w.rem1 = step[1] > 0 ? g.dims[1] - 1 - cur[1] : (step[1] < 0 ? cur[1] : 0x7fffffff);
+    w.rem2 = step[2] > 0 ? g.dims[2] - 1 - cur[2] : (step[2] < 0 ? cur[2] : 0x7fffffff);
+    w.t0 = tmax[0]; w.t1 = tmax[1]; w.t2 = tmax[2];
+    w.d0 = tdelta[0]; w.d1 = tdelta[1]; w.d2 = tdelta[2];
+    w.enter_t = enter_t; w.max_t = max_t; w.hit = hit;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { w.cur[i] = cur[i]; w.step[i] = step[i]; }
+    return true;
+}
+
+template <bool MASKED, class S>
+__device__ __forceinline__ int walk_brick(const BrickGeom &g, const double (&vp)[3], const double (&vd)[3],
+                                          double max_t_in, S &smp)
+{
+    WalkState w;
+    if (!walk_setup(g, vp, vd, max_t_in, smp, w)) return w.hit;
+    int rem0 = w.rem0, rem1 = w.rem1, rem2 = w.rem2;
+    double t0 = w.t0, t1 = w.t1, t2 = w.t2;
+    const double d0 = w.d0, d1 = w.d1, d2 = w.d2;
+    double enter_t = w.enter_t;
+    const double max_t = w.max_t;
+    int hit = w.hit;
+    smp.template begin<MASKED>(w.cur, w.step);
     bool go;
     do {
         hit++;
@@ -383,21 +413,31 @@ struct CornersP {
 // affine map val -> (val - b0) * idbin + 2, so the sample loop gets the row coordinate straight out of
 // the interpolation (saves a subtract and an FMA per sample for ~10 packed ops per cell).  The subtract
 // comes first so that |b0| >> (b1 - b0) (log fields) does not cancel catastrophically.
-// Returns whether all 8 corners are exactly (+-)0.
+// The 8 raw corner values of a cell: v[0..3] = (c000, c100, c001, c101), v[4..7] = (c010, c110, c011, c111).
+struct RawCorners {
+    float a0, e0, a1, e1, b0, f0, b1, f1;
+};
+
 template <typename T>
-__device__ __forceinline__ bool load_corners_rows(CornersP &c, const T *d, int sx, int sy, const ColourTable &ct)
+__device__ __forceinline__ void load_raw_corners(RawCorners &r, const T *d, int sx, int sy)
 {
-    const float a0 = (float)__ldg(d), a1 = (float)__ldg(d + 1);
-    const float b0 = (float)__ldg(d + sy), b1 = (float)__ldg(d + sy + 1);
-    const float e0 = (float)__ldg(d + sx), e1 = (float)__ldg(d + sx + 1);
-    const float f0 = (float)__ldg(d + sx + sy), f1 = (float)__ldg(d + sx + sy + 1);
+    r.a0 = (float)__ldg(d); r.a1 = (float)__ldg(d + 1);
+    r.b0 = (float)__ldg(d + sy); r.b1 = (float)__ldg(d + sy + 1);
+    r.e0 = (float)__ldg(d + sx); r.e1 = (float)__ldg(d + sx + 1);
+    r.f0 = (float)__ldg(d + sx + sy); r.f1 = (float)__ldg(d + sx + sy + 1);
+}
+
+// Returns whether all 8 corners are exactly (+-)0.
+__device__ __forceinline__ bool rows_from_raw(CornersP &c, const RawCorners &r, const ColourTable &ct)
+{
     const float2 nb = bcast2(-ct.tf->b0_hi[0]), sc = bcast2(ct.tf->idbin_f[0]), c0 = bcast2(ct.tf->colour_c0);
-    const float2 lo0 = fma2(add2(make_float2(a0, e0), nb), sc, c0), hi0 = fma2(add2(make_float2(a1, e1), nb), sc, c0);
-    const float2 lo1 = fma2(add2(make_float2(b0, f0), nb), sc, c0), hi1 = fma2(add2(make_float2(b1, f1), nb), sc, c0);
+    const float2 lo0 = fma2(add2(make_float2(r.a0, r.e0), nb), sc, c0), hi0 = fma2(add2(make_float2(r.a1, r.e1), nb), sc, c0);
+    const float2 lo1 = fma2(add2(make_float2(r.b0, r.f0), nb), sc, c0), hi1 = fma2(add2(make_float2(r.b1, r.f1), nb), sc, c0);
     c.p0 = lo0; c.d0 = fma2(lo0, make_float2(-1.f, -1.f), hi0);
     c.p1 = lo1; c.d1 = fma2(lo1, make_float2(-1.f, -1.f), hi1);
-    const unsigned bits = (__float_as_uint(a0) | __float_as_uint(a1) | __float_as_uint(b0)) | (__float_as_uint(b1) | __float_as_uint(e0) | __float_as_uint(e1)) |
-                          (__float_as_uint(f0) | __float_as_uint(f1));
+    const unsigned bits = (__float_as_uint(r.a0) | __float_as_uint(r.a1) | __float_as_uint(r.b0)) |
+                          (__float_as_uint(r.b1) | __float_as_uint(r.e0) | __float_as_uint(r.e1)) |
+                          (__float_as_uint(r.f0) | __float_as_uint(r.f1));
     return (bits << 1) == 0u;
 }
 
