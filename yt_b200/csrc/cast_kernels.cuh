@@ -165,7 +165,8 @@ struct CarefulSampler {
         const double dt = ddiv(dsub(exit_t, enter_t), (double)n_samples);
         const float dtf = (float)((exit_t - enter_t) * (1.0 / (double)n_samples));
         const double b0 = tf->b0[0], b1 = tf->b1[0], idbin = tf->idbin[0];
-        const float hi = tf->colour_hi;
+        // a valid sample must read a data row: clamp its row coordinate into [2, hi) against fp32 rounding
+        const float hi = __int_as_float(__float_as_int(tf->colour_hi) - 1);
         ColourTable ct;
         ct.base = base;
         ct.tf = tf;
@@ -189,7 +190,7 @@ struct CarefulSampler {
             const double xv = dadd(dmul(dv, v0), dmul(dp[0], v1));
             const bool valid = !(xv >= b1 || xv <= b0) && is_normal64(xv);
             float fs = 0.5f;
-            if (valid) fs = fminf(fmaxf((float)fma(xv - b0, idbin, 2.0), 1.5f), hi);
+            if (valid) fs = fminf(fmaxf((float)fma(xv - b0, idbin, 2.0), 2.0f), hi);
             colour_sample<PARTIAL, GREY>(ct, fs, dtf, ca);
 #pragma unroll
             for (int i = 0; i < 3; i++) dp[i] = dadd(dp[i], ds[i]);
@@ -392,10 +393,14 @@ struct FastSampler {
                     const float sxs = dcx[0] * dt, sys = dcx[1] * dt, szs = dcx[2] * dt;
                     float m;
                     // dt * (largest table product) <= 1: the max(1 - dt*T, 0) clamps cannot fire in this cell
-                    if (dt * tf->colour_clamp_bound <= 1.f)
-                        m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM)>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
-                    else
-                        m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM)>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+                    const bool clamp = !(dt * tf->colour_clamp_bound <= 1.f);
+                    if (tf->colour_delta) {
+                        if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM), true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+                        else m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM), true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+                    } else {
+                        if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM), false>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+                        else m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM), false>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+                    }
                     // some sample sat within fp32 rounding of a table bound (see CarefulSampler)
                     if (tfm_edge(TFM)) doubt = doubt || (m < tf->colour_band);
                 }
@@ -542,13 +547,20 @@ cast_kernel(const __grid_constant__ CastParams p)
             // replicate each row COLOUR_COPIES times: copy k sits in 16-byte bank group k (rows are already
             // padded with the zero / duplicate rows by ytb200_tf_create)
             float4 *sc = reinterpret_cast<float4 *>(smem_raw);
-            const int nb = p.tf.nbins[0];
-            const int nrows = nb + COLOUR_PAD_ROWS;
-            for (int i = tid; i < nrows * COLOUR_COPIES; i += CTA_THREADS) sc[i] = p.tf.colour[i / COLOUR_COPIES];
+            const int nrows = p.tf.colour_rows;
+            if (p.tf.colour_delta) {
+                // row = [8 copies of the values | 8 copies of the increments]
+                for (int i = tid; i < nrows * 2 * COLOUR_COPIES; i += CTA_THREADS) {
+                    const int r = i / (2 * COLOUR_COPIES), h = (i / COLOUR_COPIES) & 1;
+                    sc[i] = p.tf.colour[2 * r + h];
+                }
+            } else {
+                for (int i = tid; i < nrows * COLOUR_COPIES; i += CTA_THREADS) sc[i] = p.tf.colour[i / COLOUR_COPIES];
+            }
             // colour_cell_run forms the address as float_as_int(2^23 + row) * ROW_BYTES + base: fold the
             // (wrapping) bias of the exponent bits into base
             smp.ct.base = (unsigned)__cvta_generic_to_shared(sc) + (unsigned)(lane & (COLOUR_COPIES - 1)) * 16u
-                          - 0x4B000000u * COLOUR_ROW_BYTES;
+                          - 0x4B000000u * (p.tf.colour_delta ? COLOUR_DELTA_ROW_BYTES : COLOUR_ROW_BYTES);
             smp.ct.tf = &p.tf;
         } else if (KIND == KIND_VR) {
             float2 *sp = reinterpret_cast<float2 *>(smem_raw);

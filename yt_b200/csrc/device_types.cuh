@@ -60,7 +60,8 @@ struct DevTF {
     // row-coordinate constants of the colour fast path (see ColourTable in raycast.cuh); they stay in the
     // kernel-parameter constant bank instead of in registers
     float colour_c0, colour_clamp_bound, colour_lo, colour_hi, colour_mid, colour_half, colour_band, colour_zrow;
-    int colour_zero_inside, colour_edge;
+    float colour_clamp_hi;   // delta layout: row coordinates are clamped to [0.5, nbins + 1.5]
+    int colour_zero_inside, colour_edge, colour_delta, colour_rows;
 };
 
 struct CastParams {

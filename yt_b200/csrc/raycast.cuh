@@ -386,6 +386,12 @@ constexpr unsigned COLOUR_ROW_BYTES = COLOUR_COPIES * 16;  // bytes between cons
 // the two leading zero rows serve every rejected sample without a branch, and bin == n-1 (a value that
 // rounds onto b1) interpolates between two copies of the last entry.
 constexpr int COLOUR_PAD_ROWS = 3;
+// Delta layout (tables of at most COLOUR_DELTA_MAX_BINS bins): a row is 256 bytes = the 8 copies of
+// (r,g,b,a) followed by the 8 copies of the increments to the next bin, so the lerp is ONE packed FMA per
+// pair and every LDS.128 quarter-warp still touches 8 distinct bank groups.  Rows 0, 1 and >= nbins + 1
+// are zero: clamping the row coordinate to [0.5, nbins + 1.5] (two FMNMX, NaN -> 0.5) rejects samples.
+constexpr int COLOUR_DELTA_MAX_BINS = 256;
+constexpr unsigned COLOUR_DELTA_ROW_BYTES = 2 * COLOUR_ROW_BYTES;
 constexpr float COLOUR_MAGIC = 8388608.f;             // 2^23: x + 2^23 rounded down == 2^23 + floor(x)
 
 __device__ __forceinline__ float4 lds128(unsigned addr)
@@ -458,7 +464,7 @@ struct ColourAcc {
 //   * rejected samples (out of bounds, NaN, inf) are steered between the two zero rows by ONE select on
 //     the row coordinate instead of selects on fraction and alpha; exact zeros are rejected per cell;
 //   * CLAMP=false drops the max(1 - dt*T, 0) clamps when the caller proved dt*T <= 1 for the cell.
-template <bool PARTIAL, bool GREY, bool CLAMP, bool EDGE>
+template <bool PARTIAL, bool GREY, bool CLAMP, bool EDGE, bool DELTA>
 __device__ __forceinline__ float colour_cell_run(const CornersP &c, const ColourTable &ct, int n_samples, float x, float y, float z,
                                                 float sx, float sy, float sz, float dt, ColourAcc &A)
 {
@@ -485,19 +491,31 @@ __device__ __forceinline__ float colour_cell_run(const CornersP &c, const Colour
 #endif
         const float fb = fmaf(x, v.y - v.x, v.x);      // row coordinate of the sample value
         zy = add2(zy, szy); x += sx;
-        // FIT_get_value for the 4 tables at once.  margin < 0 <=> b0 < value < b1 (false for NaN).
-        // EDGE: keep the smallest |margin| of the cell; the caller compares it with the fp32 error band.
-        const float margin = fabsf(fb - ct.tf->colour_mid) - ct.tf->colour_half;
-        const bool valid = margin < 0.f;
-        if (EDGE) closest = fminf(closest, fabsf(margin));
-        const float fs = valid ? fb : 0.5f;
-        const float t = __fadd_rd(fs, COLOUR_MAGIC);   // 2^23 + floor(fs)
-        const float fr = fs - (t - COLOUR_MAGIC);
-        const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_ROW_BYTES + ct.base;
-        const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
-        const float2 fr2 = bcast2(fr);
-        const float2 rg = fma2(fr2, fma2(make_float2(t0.x, t0.y), neg1, make_float2(t1.x, t1.y)), make_float2(t0.x, t0.y));
-        const float2 ba = fma2(fr2, fma2(make_float2(t0.z, t0.w), neg1, make_float2(t1.z, t1.w)), make_float2(t0.z, t0.w));
+        // FIT_get_value for the 4 tables at once.
+        // EDGE: keep the smallest distance to a bound of the cell; the caller compares it with the fp32 error band.
+        if (EDGE) closest = fminf(closest, fabsf(fabsf(fb - ct.tf->colour_mid) - ct.tf->colour_half));
+        float2 rg, ba;
+        if (DELTA) {
+            const float fs = fminf(fmaxf(fb, 0.5f), ct.tf->colour_clamp_hi);   // rejected samples land on zero rows
+            const float t = __fadd_rd(fs, COLOUR_MAGIC);   // 2^23 + floor(fs)
+            const float fr = fs - (t - COLOUR_MAGIC);
+            const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_DELTA_ROW_BYTES + ct.base;
+            const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
+            const float2 fr2 = bcast2(fr);
+            rg = fma2(fr2, make_float2(t1.x, t1.y), make_float2(t0.x, t0.y));
+            ba = fma2(fr2, make_float2(t1.z, t1.w), make_float2(t0.z, t0.w));
+        } else {
+            // margin < 0 <=> b0 < value < b1 (false for NaN)
+            const bool valid = fabsf(fb - ct.tf->colour_mid) - ct.tf->colour_half < 0.f;
+            const float fs = valid ? fb : 0.5f;
+            const float t = __fadd_rd(fs, COLOUR_MAGIC);   // 2^23 + floor(fs)
+            const float fr = fs - (t - COLOUR_MAGIC);
+            const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_ROW_BYTES + ct.base;
+            const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
+            const float2 fr2 = bcast2(fr);
+            rg = fma2(fr2, fma2(make_float2(t0.x, t0.y), neg1, make_float2(t1.x, t1.y)), make_float2(t0.x, t0.y));
+            ba = fma2(fr2, fma2(make_float2(t0.z, t0.w), neg1, make_float2(t1.z, t1.w)), make_float2(t0.z, t0.w));
+        }
         const float adt = ba.y * dt;                   // dt * alpha-table value
         const float2 e01 = mul2(rg, bcast2(adt));      // dt * T_r, dt * T_g (RGB weighted by alpha)
         const float e2 = ba.x * adt;
@@ -527,10 +545,13 @@ __device__ __forceinline__ void colour_sample(const ColourTable &ct, float fs, f
 {
     const float t = __fadd_rd(fs, COLOUR_MAGIC);
     const float fr = fs - (t - COLOUR_MAGIC);
-    const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_ROW_BYTES + ct.base;
-    const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
-    const float r = fmaf(fr, t1.x - t0.x, t0.x), g = fmaf(fr, t1.y - t0.y, t0.y), b = fmaf(fr, t1.z - t0.z, t0.z);
-    const float adt = fmaf(fr, t1.w - t0.w, t0.w) * dt;
+    const bool delta = ct.tf->colour_delta != 0;
+    const unsigned addr = (unsigned)__float_as_int(t) * (delta ? COLOUR_DELTA_ROW_BYTES : COLOUR_ROW_BYTES) + ct.base;
+    const float4 t0 = lds128(addr);
+    float4 t1 = lds128(addr + COLOUR_ROW_BYTES);
+    if (!delta) t1 = make_float4(t1.x - t0.x, t1.y - t0.y, t1.z - t0.z, t1.w - t0.w);
+    const float r = fmaf(fr, t1.x, t0.x), g = fmaf(fr, t1.y, t0.y), b = fmaf(fr, t1.z, t0.z);
+    const float adt = fmaf(fr, t1.w, t0.w) * dt;
     const float e0 = r * adt, e1 = g * adt, e2 = b * adt;
     if (GREY) {
         const float ta = fmaxf(1.f - adt, 0.f);

@@ -374,18 +374,35 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
     rc |= to_device(t, dy, &d.dy);
     rc |= to_device(t, pairs, &d.pairs);
     if (colour) {
-        // rows [0, 0, y_0 .. y_{n-1}, y_{n-1}] (raycast.cuh, COLOUR_PAD_ROWS): row = bin + 2
+        // shared-memory row layouts of the fast path (raycast.cuh); row = bin + 2, rows 0 and 1 are zero:
+        //   delta layout  (nbins <= 256): row r holds (y_{r-2}, y_{r-1} - y_{r-2}); rows >= nbins + 1 are zero
+        //   value layout  (nbins <= 512): rows [0, 0, y_0 .. y_{n-1}, y_{n-1}], the lerp reads rows r and r + 1
         const int nb = nbins[0];
-        std::vector<float4> col((size_t)nb + COLOUR_PAD_ROWS, make_float4(0.f, 0.f, 0.f, 0.f));
+        d.colour_delta = nb <= COLOUR_DELTA_MAX_BINS ? 1 : 0;
+        std::vector<float4> col;
         double rgb_max = 0.0, a_max = 0.0;
+        auto row = [&](int j) { return make_float4((float)y[0][j], (float)y[1][j], (float)y[2][j], (float)y[3][j]); };
         for (int j = 0; j < nb; j++) {
-            col[(size_t)j + 2] = make_float4((float)y[0][j], (float)y[1][j], (float)y[2][j], (float)y[3][j]);
             rgb_max = fmax(rgb_max, fmax(fabs(y[0][j]), fmax(fabs(y[1][j]), fabs(y[2][j]))));
             a_max = fmax(a_max, fabs(y[3][j]));
         }
-        col[(size_t)nb + 2] = col[(size_t)nb + 1];
+        if (d.colour_delta) {
+            col.assign(2 * ((size_t)nb + 2), make_float4(0.f, 0.f, 0.f, 0.f));
+            for (int j = 0; j + 1 < nb; j++) {
+                const float4 a = row(j), b = row(j + 1);
+                col[2 * ((size_t)j + 2)] = a;
+                col[2 * ((size_t)j + 2) + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, b.w - a.w);
+            }
+            d.colour_rows = nb + 2;
+        } else {
+            col.assign((size_t)nb + COLOUR_PAD_ROWS, make_float4(0.f, 0.f, 0.f, 0.f));
+            for (int j = 0; j < nb; j++) col[(size_t)j + 2] = row(j);
+            col[(size_t)nb + 2] = col[(size_t)nb + 1];
+            d.colour_rows = nb + COLOUR_PAD_ROWS;
+        }
         rc |= to_device(t, col, &d.colour);
-        // the fast path replicates every row 8x in shared memory (bank-conflict-free): <= 64.4 KiB at 512 bins
+        // every row is replicated 8x in shared memory (bank-conflict-free): 64.4 KiB (value layout, 512 bins)
+        // or 64.5 KiB (delta layout, 256 bins)
         d.colour_copy_shift = 3;
         const double b0 = bounds[0], b1 = bounds[1];
         const double idbin = d.idbin[0];
@@ -399,6 +416,7 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
         const double edge = fmax(fabs(y[3][0]), fabs(y[3][nb - 1])) * fmax(1.0, rgb_max);
         d.colour_edge = edge > 1e-30 ? 1 : 0;
         d.colour_lo = 2.f; d.colour_hi = (float)(nb + 1);
+        d.colour_clamp_hi = (float)nb + 1.5f;
         d.colour_mid = 0.5f * (float)(nb + 3); d.colour_half = 0.5f * (float)(nb - 1);
         d.colour_band = 4e-6f * (float)(nb + 512);
         // row coordinate of the value 0, with the very operations load_corners_rows applies to a corner
@@ -653,7 +671,7 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
         if (kind == YTB200_VOLUME_RENDER) {
             const bool colour = !exact && nf1 && tf->d.colour_fast;
             if (exact) smem = (size_t)tf->d.total_bins * 3 * sizeof(double);
-            else if (colour) smem = ((size_t)(tf->d.nbins[0] + COLOUR_PAD_ROWS) << tf->d.colour_copy_shift) * sizeof(float4);
+            else if (colour) smem = ((size_t)tf->d.colour_rows << tf->d.colour_copy_shift) * sizeof(float4) * (tf->d.colour_delta ? 2 : 1);
             else smem = (size_t)tf->d.total_bins * sizeof(float2);
             if (smem > 200 * 1024) return fail(E_UNSUPPORTED, "transfer function tables (%zu B) exceed shared memory", smem);
             if (colour) {
