@@ -17,6 +17,10 @@ constexpr int TILE_I = 16, TILE_J = 16, CTA_THREADS = 256;
 #ifndef YTB_MIN_BLOCKS_PROJ
 #define YTB_MIN_BLOCKS_PROJ 3   // the projection cast is load-latency bound: occupancy pays (ncu r01c)
 #endif
+#ifndef YTB_PROJ_DEPTH
+#define YTB_PROJ_DEPTH 8
+#endif
+constexpr int PROJ_DEPTH = YTB_PROJ_DEPTH;   // cells of one ray in flight in the fused projection walk
 enum { KIND_PROJ = 0, KIND_IPROJ = 1, KIND_VR = 2 };
 // transfer-function mode of the FAST path.  The ColorTransferFunction fast path is specialised on
 // grey_opacity and on "0 lies strictly inside the table bounds" (both uniform per launch).
@@ -409,6 +413,95 @@ struct FastSampler {
         } while (cont);
     }
 
+    // ------------------------------------------------------------------------------------------------
+    // The fused walk of the single-field ProjectionSampler (image_samplers.pyx:327-343 inside
+    // grid_traversal.pyx:119-138).  Same cells and the same (enter_t, exit_t) as walk_brick.  ncu r01e on
+    // the generic loop: 75 instructions per cell, the data pointer re-read from the brick table for every
+    // cell and the value consumed right after its load (long_scoreboard 6.2 of 9.7 stall cycles per issue).
+    // Here the pointer lives in a register, the step is one PTX block with predicated adds, and the NEXT
+    // cell's value is requested before the current one is accumulated.
+    // ------------------------------------------------------------------------------------------------
+    __device__ __forceinline__ void walk_proj(const WalkState &w)
+    {
+        const int ny = br->dims[1], nz = br->dims[2];
+        unsigned o = ((unsigned)w.cur[0] * (unsigned)ny + (unsigned)w.cur[1]) * (unsigned)nz + (unsigned)w.cur[2];
+        const int st0 = w.step[0] * ny * nz, st1 = w.step[1] * nz, st2 = w.step[2];
+        double t0 = w.t0, t1 = w.t1, t2 = w.t2;
+        const double d0 = w.d0, d1 = w.d1, d2 = w.d2, max_t = w.max_t;
+        int rem0 = w.rem0, rem1 = w.rem1, rem2 = w.rem2;
+        double enter_t = w.enter_t;
+        const T *data = (const T *)br->data[0];
+        double a = acc[0];
+        // The walk runs PROJ_DEPTH cells AHEAD of the accumulation: a ring of (value, path length) slots keeps
+        // that many loads of one ray in flight (r01g: with one load in flight a warp paid a full L2/DRAM
+        // latency, ~620 cycles, per cell).  `live` goes false when the reference's loop would have ended
+        // (it never comes back: the exit tests are monotone along the walk); dead slots hold 0 * 0.
+        T v[PROJ_DEPTH];
+        double dl[PROJ_DEPTH];
+        unsigned live = 1u;   // walk_setup returned true: the start cell is sampled
+        auto produce = [&](T &vj, double &dlj) {
+            vj = T(0);
+            if (live) vj = __ldg(data + o);
+            double len;
+            unsigned cont;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred a01, a02, a12, n01, p0, p1, p2, pc, pm;\n\t"
+                ".reg .f64 tm, ex;\n\t"
+                ".reg .s32 ds, rr;\n\t"
+                // axis of the smallest tmax, reference tie rule (grid_traversal.pyx:122-131)
+                "setp.lt.f64 a01, %0, %1;\n\t"
+                "setp.lt.f64 a02, %0, %2;\n\t"
+                "setp.lt.f64 a12, %1, %2;\n\t"
+                "and.pred p0, a01, a02;\n\t"
+                "not.pred n01, a01;\n\t"
+                "and.pred p1, n01, a12;\n\t"
+                "or.pred p2, p0, p1;\n\t"            // p2 == NOT (axis 2)
+                "selp.f64 tm, %1, %2, p1;\n\t"
+                "selp.f64 tm, %0, tm, p0;\n\t"
+                "setp.lt.f64 pm, tm, %13;\n\t"
+                "selp.f64 ex, tm, %13, pm;\n\t"       // exit_t = tm < max_t ? tm : max_t
+                "sub.rn.f64 %8, ex, %7;\n\t"          // path length in t through this cell
+                // the step: cur[i] += step[i]; enter_t = tmax[i]; tmax[i] += tdelta[i]
+                "@p0 add.rn.f64 %0, %0, %10;\n\t"
+                "@p1 add.rn.f64 %1, %1, %11;\n\t"
+                "@!p2 add.rn.f64 %2, %2, %12;\n\t"
+                "@p0 add.s32 %3, %3, -1;\n\t"
+                "@p1 add.s32 %4, %4, -1;\n\t"
+                "@!p2 add.s32 %5, %5, -1;\n\t"
+                "selp.b32 ds, %15, %16, p1;\n\t"
+                "selp.b32 ds, %14, ds, p0;\n\t"
+                "add.s32 %6, %6, ds;\n\t"
+                // go on while the stepped index is inside the brick and enter_t < max_t (NaN goes on, like the reference)
+                "or.b32 rr, %3, %4;\n\t"
+                "or.b32 rr, rr, %5;\n\t"
+                "setp.ge.s32 pc, rr, 0;\n\t"
+                "setp.ge.f64 pm, tm, %13;\n\t"
+                "not.pred pm, pm;\n\t"
+                "and.pred pc, pc, pm;\n\t"
+                "selp.u32 %9, 1, 0, pc;\n\t"
+                "mov.f64 %7, tm;\n\t"
+                "}"
+                : "+d"(t0), "+d"(t1), "+d"(t2), "+r"(rem0), "+r"(rem1), "+r"(rem2), "+r"(o), "+d"(enter_t),
+                  "=d"(len), "=r"(cont)
+                : "d"(d0), "d"(d1), "d"(d2), "d"(max_t), "r"(st0), "r"(st1), "r"(st2));
+            dlj = live ? len : 0.0;
+            live &= cont;
+        };
+#pragma unroll
+        for (int j = 0; j < PROJ_DEPTH; j++) produce(v[j], dl[j]);
+        while (live) {
+#pragma unroll
+            for (int j = 0; j < PROJ_DEPTH; j++) {
+                a = fma((double)v[j], dl[j], a);
+                produce(v[j], dl[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PROJ_DEPTH; j++) a = fma((double)v[j], dl[j], a);
+        acc[0] = a;
+    }
+
     template <bool MASKED>
     __device__ __forceinline__ void cell(double enter_t, double exit_t)
     {
@@ -664,6 +757,9 @@ cast_kernel(const __grid_constant__ CastParams p)
                     }
                 } else if constexpr (!EXACT && KIND == KIND_VR && tfm_is_colour(TFM)) {
                     cast_colour(g, vp, vd, max_t, smp, masked);
+                } else if constexpr (!EXACT && KIND == KIND_PROJ && NF1) {
+                    WalkState w;
+                    if (walk_setup(g, vp, vd, max_t, smp, w)) smp.walk_proj(w);
                 } else {
                     if (masked) walk_brick<true>(g, vp, vd, max_t, smp);
                     else walk_brick<false>(g, vp, vd, max_t, smp);

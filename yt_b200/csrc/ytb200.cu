@@ -691,7 +691,7 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
         } else if (kind == YTB200_INTERPOLATED_PROJECTION) {
             e = launch_kind<KIND_IPROJ, TFM_NONE>(p, grid, 0, st, exact, f64, partial != nullptr, nf1);
         } else {
-            e = launch_kind<KIND_PROJ, TFM_NONE>(p, grid, 0, st, exact, f64, partial != nullptr, false);
+            e = launch_kind<KIND_PROJ, TFM_NONE>(p, grid, 0, st, exact, f64, partial != nullptr, nf1);
         }
         if (e != cudaSuccess) return fail(-100 - (int)e, "cast launch: %s", cudaGetErrorString(e));
         launches++;
