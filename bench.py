@@ -415,7 +415,7 @@ def run_ours(args):
         "ms_per_frame": ms_step,
         "e2e": {"value": gs_e2e, "unit": "Gsamples/s", "ms_per_frame": ms_e2e,
                 "h2d_bytes_per_step": res * res * 40, "d2h_bytes_per_step": res * res * 32,
-                "note": "host image+zbuffer in, host image out through ytb200_render; bricks device-resident across frames"},
+                "note": "host (page-locked) image+zbuffer in, host image out through ytb200_render; at N=1 the cast kernel reads/writes the host arrays in place over PCIe; bricks device-resident across frames"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

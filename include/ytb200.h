@@ -147,7 +147,11 @@ int ytb200_partial_compose(ytb200_ctx *ctx, const double *earlier_dev, const dou
 int ytb200_partial_apply(ytb200_ctx *ctx, const double *partial_dev, double *image_dev, int64_t n_pixels);
 
 /* ---- one-shot convenience: everything above for host buffers --------------------------------
- * upload image+zbuffer -> cast -> download.  This is the call the e2e benchmark times. */
+ * upload image+zbuffer -> cast -> download.  This is the call the e2e benchmark times.
+ * When `image_host_inout` (and `zbuffer_host`, if given) are page-locked (ytb200_host_alloc, cudaHostAlloc,
+ * cudaHostRegister) the cast kernel reads and writes them in place over PCIe -- no staging copies, and the
+ * frame's device image is left untouched; pageable arrays are staged through the frame's device buffers.
+ * Either way the result is in `image_host_inout` when the call returns (image_samplers.pyx:111,192). */
 int ytb200_render(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order, int64_t n_order,
                   const ytb200_tf *tf, int n_samples, int precision, const double *zbuffer_host,
                   double *image_host_inout, ytb200_stats *stats);

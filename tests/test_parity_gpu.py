@@ -139,3 +139,42 @@ def test_reference_error_behaviour(gpu):
     pargs, pkw = T.sampler_args(persp.cam)
     with pytest.raises(RuntimeError, match="Bad lens shape"):
         S.ProjectionSampler(pargs[0][:-1], *pargs[1:], 10, **pkw)
+
+
+@pytest.mark.parametrize("name", ["vr_colour_grey_zbuf", "proj_offaxis_zbuf", "vr_8bricks_perspective_grey", "vr_colour"])
+def test_render_in_place_on_pinned_host_arrays(gpu, name, monkeypatch):
+    """ytb200_render with page-locked host arrays (the kernel reads/writes them over PCIe) gives the same
+    image as the staged route (copy in, cast, copy out) and matches the oracle."""
+    from yt_b200 import _lib as L
+    from yt_b200 import device as D
+    from yt_b200.partitioned_grid import build_brickset
+    S, G = _gpu_mods()
+    sc = [s for s in T.scenarios() if s.name == name][0]
+    want = T.run_scenario(sc, O, O, num_threads=0)
+    nx, ny = sc.cam.resolution
+    outs = []
+    for zero_copy in (True, False):
+        if zero_copy:
+            monkeypatch.delenv("YTB200_NO_ZEROCOPY", raising=False)
+        else:
+            monkeypatch.setenv("YTB200_NO_ZEROCOPY", "1")
+        img = D.pinned_empty((nx, ny, 4))
+        img[:] = 0.0 if sc.image0 is None else sc.image0
+        zb = None
+        if sc.zbuffer is not None:
+            zb = D.pinned_empty((nx, ny))
+            zb[:] = sc.zbuffer
+        args, kwargs = T.sampler_args(sc.cam, zbuffer=zb, image=img)
+        if sc.cam.lens.lens_type != "perspective" or sc.kind != "vr":
+            kwargs.pop("camera_data")
+        if sc.kind == "vr":
+            s = S.VolumeRenderSampler(*args, sc.tf, sc.n_samples, **kwargs)
+        else:
+            s = S.ProjectionSampler(*args, sc.n_samples, **kwargs)
+        grids = [G.PartitionedGrid(i, list(b[0]), b[1], np.array(b[2], "float64"), np.array(b[3], "float64"), np.array(b[4], "int64"))
+                 for i, b in enumerate(sc.bricks)]
+        bs = build_brickset(grids, s._ctx, s._storage)
+        s._frame.render(s.kind, bs, np.array(sc.order), img, zbuffer=zb, tf=s._tables, n_samples=sc.n_samples)
+        outs.append(np.array(img, copy=True))
+    assert np.array_equal(outs[0], outs[1])
+    _check(sc, outs[0], want, exact=False)
