@@ -96,6 +96,24 @@ int ytb200_brick_upload(ytb200_brickset *set, int64_t index, const int64_t dims[
 /* Same, but data[f] / mask are DEVICE pointers already in the set's storage type; not copied, not owned. */
 int ytb200_brick_attach(ytb200_brickset *set, int64_t index, const int64_t dims[3], const double left_edge[3],
                         const double right_edge[3], const void *const *dev_data, const uint8_t *dev_mask);
+/* ---- vertex centring on the device (replaces the host passes that feed PartitionedGrid) -------
+ * grid.get_vertex_centered_data(fields, no_ghost=True)  grid_patch.py:270-296 -> ghost_zone_interpolate,
+ *                                                       interpolators.pyx:177-227 (rf=1, input_left=0.5)
+ * log10 with values <= 0 -> NaN                         amr_kdtree.py:346-352
+ * data[li:ri+1] slices of the kd leaf                   amr_kdtree.py:333-335,362-365
+ * Cell data of a grid go to the device once (fp64, C-order (nx,ny,nz)) ... */
+int ytb200_cells_upload(ytb200_ctx *ctx, const double *cells_host, const int64_t dims[3], void **cells_dev_out);
+int ytb200_cells_free(ytb200_ctx *ctx, void *cells_dev);
+/* ... and every kd leaf of that grid becomes brick `index`: vertices lo..hi (inclusive, hi - lo = the leaf's
+ * cell dims) of the grid's vertex-centred field, in the set's storage type, log10'd where log_fields[f] != 0
+ * (NULL = none).  cells_dev[f] are DEVICE pointers to the grid's cell-centred fields (fp64, or fp32 when
+ * cells_are_f32); mask_host as in ytb200_brick_upload.  fp64 storage is bit-identical to the reference for
+ * linear fields; log10 is CUDA's (<= 2 ulp from libm).  Needs >= 2 cells per grid axis (the reference yields NaN
+ * below that).  `stats` (optional) returns the CUDA-event time of the centring kernels. */
+int ytb200_brick_from_cells(ytb200_brickset *set, int64_t index, const int64_t grid_dims[3], const int64_t lo[3],
+                            const int64_t hi[3], const double left_edge[3], const double right_edge[3],
+                            const void *const *cells_dev, int cells_are_f32, const int32_t *log_fields,
+                            const uint8_t *mask_host, ytb200_stats *stats);
 /* Must be called after the last upload/attach and before the first cast (uploads the brick table). */
 int ytb200_bricks_commit(ytb200_brickset *set);
 int ytb200_bricks_destroy(ytb200_brickset *set);

@@ -59,6 +59,9 @@ def lib():
             C.c_int, C.POINTER(dp), C.POINTER(C.c_uint8), dp, dp, C.POINTER(C.c_int64),
             C.POINTER(_TFDesc), C.c_int, C.c_int]
         _lib.orc_max_threads.restype = C.c_int
+        i64p = C.POINTER(C.c_int64)
+        _lib.orc_ghost_zone_interpolate.restype = None
+        _lib.orc_ghost_zone_interpolate.argtypes = [C.c_int, dp, i64p, dp, dp, i64p, dp]
     return _lib
 
 
@@ -174,6 +177,31 @@ class VolumeRenderSampler(ImageSampler):
             d.field_table_ids[i] = tf_obj.field_table_ids[i]
         d.grey_opacity = int(getattr(tf_obj, "grey_opacity", 0))
         self._tf = d
+
+
+def vertex_centre(cells):
+    """grid.get_vertex_centered_data(no_ghost=True) of one field: grid_patch.py:284-296 ->
+    ghost_zone_interpolate(1, cells, [0.5]*3, out, [0]*3) (interpolators.pyx:177-227)."""
+    cells = np.ascontiguousarray(cells, dtype="float64")
+    out = np.zeros(tuple(s + 1 for s in cells.shape), dtype="float64")
+    ish = np.array(cells.shape, dtype="int64")
+    osh = np.array(out.shape, dtype="int64")
+    il, ol = np.full(3, 0.5), np.zeros(3)
+    i64p = C.POINTER(C.c_int64)
+    lib().orc_ghost_zone_interpolate(1, _dptr(cells), ish.ctypes.data_as(i64p), _dptr(il), _dptr(out),
+                                     osh.ctypes.data_as(i64p), _dptr(ol))
+    return out
+
+
+def brick_data_from_cells(cells, li, ri, take_log):
+    """The data array of one kd leaf as AMRKDTree.get_brick_data builds it (amr_kdtree.py:343-365):
+    vertex-centre the whole grid, log10 with values <= 0 -> NaN, slice [li:ri+1]."""
+    v = vertex_centre(cells)
+    if take_log:
+        v[v <= 0] = np.nan
+        with np.errstate(invalid="ignore"):
+            v = np.log10(v)
+    return v[li[0]:ri[0] + 1, li[1]:ri[1] + 1, li[2]:ri[2] + 1].copy()
 
 
 def ref_available():

@@ -55,6 +55,10 @@ SIGNATURES = {
     "ytb200_bricks_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ytb200_brick_upload": (C.c_int, [C.c_void_p, C.c_int64, i64p, dp, dp, C.POINTER(dp), u8p]),
     "ytb200_brick_attach": (C.c_int, [C.c_void_p, C.c_int64, i64p, dp, dp, C.POINTER(C.c_void_p), C.c_void_p]),
+    "ytb200_cells_upload": (C.c_int, [C.c_void_p, dp, i64p, C.POINTER(C.c_void_p)]),
+    "ytb200_cells_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ytb200_brick_from_cells": (C.c_int, [C.c_void_p, C.c_int64, i64p, i64p, i64p, dp, dp, C.POINTER(C.c_void_p), C.c_int,
+                                          i32p, u8p, C.POINTER(Stats)]),
     "ytb200_bricks_commit": (C.c_int, [C.c_void_p]),
     "ytb200_bricks_destroy": (C.c_int, [C.c_void_p]),
     "ytb200_brick_device_ptrs": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),

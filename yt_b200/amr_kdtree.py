@@ -190,15 +190,52 @@ class AMRKDTree:
         return brick
 
     # -- device residency (ours) ---------------------------------------------------------------------------
-    def device_bricks(self, ctx, storage):
-        """One device brick table over every leaf (depth-first order); built once, reused every frame."""
-        key = (ctx.device, storage)
+    def device_bricks(self, ctx, storage, centre_on_device=None):
+        """One device brick table over every leaf (depth-first order); built once, reused every frame.
+
+        With ``centre_on_device`` (default: whenever ``no_ghost``) the host never builds a vertex array:
+        each grid's cell-centred fields go to the device once and every leaf is vertex-centred, log10'd,
+        sliced and converted by ``ytb200_brick_from_cells`` (get_brick_data's arithmetic, amr_kdtree.py:343-365)."""
+        if centre_on_device is None:
+            centre_on_device = bool(self.no_ghost)
+        key = (ctx.device, storage, bool(centre_on_device))
         if key not in self._device_sets:
             leaves = [int(i) for i in self.tree.traverse()]
             self._leaf_slot = np.full(len(self.tree.nodes["grid"]), -1, dtype="int64")
             self._leaf_slot[leaves] = np.arange(len(leaves))
-            self._device_sets[key] = build_brickset([self.get_brick_data(i) for i in leaves], ctx, storage)
+            if centre_on_device and leaves:
+                self._device_sets[key] = self._device_bricks_from_cells(leaves, ctx, storage)
+            else:
+                self._device_sets[key] = build_brickset([self.get_brick_data(i) for i in leaves], ctx, storage)
         return self._device_sets[key]
+
+    def _device_bricks_from_cells(self, leaves, ctx, storage):
+        from . import _lib as L
+        from . import device as D
+        if not self.no_ghost:
+            raise NotImplementedError("ghost-zone vertex centring is not on the device path")
+        nd = self.tree.nodes
+        out = D.BrickSet(ctx, len(leaves), len(self.fields), L.VERTEX_CENTRED, storage)
+        cells_of_grid = {}
+        for slot, node in enumerate(leaves):
+            grid = self.ds.index.grids[nd["grid"][node] - self._id_offset]
+            if grid.id not in cells_of_grid:
+                if np.any(np.asarray(grid.ActiveDimensions) < 2):
+                    raise NotImplementedError("no-ghost vertex centring needs >= 2 cells per grid axis")
+                cells_of_grid[grid.id] = [D.DeviceCells(ctx, grid[f]) for f in self.fields]
+            cells = cells_of_grid[grid.id]
+            dds, gle = grid.dds, grid.LeftEdge
+            nle, nre = nd["left_edge"][node].copy(), nd["right_edge"][node].copy()
+            li = np.rint((nle - gle) / dds).astype("int64")   # amr_kdtree.py:333-335
+            ri = np.rint((nre - gle) / dds).astype("int64")
+            mask = None
+            if self.data_source.selector is not None:
+                mask, _ = self.data_source.selector.fill_mask_regular_grid(grid)
+                mask = mask[li[0]:ri[0], li[1]:ri[1], li[2]:ri[2]].astype("uint8")
+            out.from_cells(slot, [c.ptr for c in cells], grid.ActiveDimensions, li, ri, nle, nre,
+                           log_fields=self.log_fields, mask=mask)
+        ctx.synchronize()   # the cell arrays may be released once every leaf has been centred
+        return out.commit()
 
     def view_order(self, viewpoint):
         """Positions in the device brick table, back to front w.r.t. ``viewpoint``."""

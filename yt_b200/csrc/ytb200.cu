@@ -3,6 +3,7 @@
 // No CPU compute path exists: every call needs a CUDA device and fails loudly otherwise.
 #include "../../include/ytb200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -236,6 +237,100 @@ extern "C" int ytb200_brick_upload(ytb200_brickset *s, int64_t index, const int6
     }
     CK(cudaStreamSynchronize(st));
     if (stage) CK(cudaFree(stage));
+    return 0;
+}
+
+// ---- vertex centring on the device -------------------------------------------------------------------
+extern "C" int ytb200_cells_upload(ytb200_ctx *ctx, const double *cells_host, const int64_t dims[3], void **cells_dev_out)
+{
+    if (!ctx || !cells_host || !dims || !cells_dev_out) return fail(E_ARG, "NULL argument");
+    for (int i = 0; i < 3; i++) if (dims[i] < 1) return fail(E_ARG, "bad dims[%d]=%lld", i, (long long)dims[i]);
+    DeviceGuard g(ctx->device);
+    const size_t n = (size_t)dims[0] * (size_t)dims[1] * (size_t)dims[2];
+    void *d = nullptr;
+    CK(cudaMalloc(&d, n * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d, cells_host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFree(d); return fail(-100 - (int)e, "cells upload: %s", cudaGetErrorString(e)); }
+    *cells_dev_out = d;
+    return 0;
+}
+
+extern "C" int ytb200_cells_free(ytb200_ctx *ctx, void *cells_dev)
+{
+    if (!ctx) return fail(E_ARG, "ctx is NULL");
+    DeviceGuard g(ctx->device);
+    if (cells_dev) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(cells_dev)); }
+    return 0;
+}
+
+extern "C" int ytb200_brick_from_cells(ytb200_brickset *s, int64_t index, const int64_t grid_dims[3], const int64_t lo[3],
+                                       const int64_t hi[3], const double le[3], const double re[3],
+                                       const void *const *cells_dev, int cells_are_f32, const int32_t *log_fields,
+                                       const uint8_t *mask_host, ytb200_stats *stats)
+{
+    if (!s || !grid_dims || !lo || !hi || !le || !re || !cells_dev) return fail(E_ARG, "NULL argument");
+    if (s->centring != YTB200_VERTEX_CENTRED) return fail(E_ARG, "vertex centring needs a VERTEX_CENTRED brick set");
+    int64_t dims[3];
+    for (int i = 0; i < 3; i++) {
+        // ghost_zone_interpolate divides by (shape - 1): a one-cell axis is NaN in the reference
+        if (grid_dims[i] < 2 || grid_dims[i] > 0x7ffffff0) return fail(E_UNSUPPORTED, "grid_dims[%d]=%lld: no-ghost vertex centring needs >= 2 cells per axis", i, (long long)grid_dims[i]);
+        if (lo[i] < 0 || hi[i] <= lo[i] || hi[i] > grid_dims[i]) return fail(E_ARG, "bad vertex range [%lld, %lld] on axis %d", (long long)lo[i], (long long)hi[i], i);
+        dims[i] = hi[i] - lo[i];
+    }
+    int rc = fill_geometry(s, index, dims, le, re);
+    if (rc) return rc;
+    DeviceGuard g(s->ctx->device);
+    cudaStream_t st = s->ctx->stream;
+    DevBrick &b = s->host[(size_t)index];
+    const int m0 = (int)dims[0] + 1, m1 = (int)dims[1] + 1, m2 = (int)dims[2] + 1;
+    const size_t nelem = (size_t)m0 * (size_t)m1 * (size_t)m2;
+    const size_t ncell = (size_t)dims[0] * (size_t)dims[1] * (size_t)dims[2];
+    if (m1 > 65535 || (m0 + VC_XCHUNK - 1) / VC_XCHUNK > 65535) return fail(E_UNSUPPORTED, "brick too large for one centring launch");
+    const dim3 grid((unsigned)((m2 + VC_ZSPAN - 1) / VC_ZSPAN), (unsigned)m1, (unsigned)((m0 + VC_XCHUNK - 1) / VC_XCHUNK));
+    if (stats) CK(cudaEventRecord(s->ctx->ev0, st));
+    for (int f = 0; f < s->n_fields; f++) {
+        if (!cells_dev[f]) return fail(E_ARG, "cells_dev[%d] is NULL", f);
+        const int lg = log_fields ? log_fields[f] : 0;
+        const bool f64 = s->storage == YTB200_STORE_F64;
+        void *dst = nullptr;
+        CK(cudaMalloc(&dst, nelem * (f64 ? sizeof(double) : sizeof(float))));
+        s->owned.push_back(dst);
+        s->bytes += (int64_t)(nelem * (f64 ? 8 : 4));
+        const int nx = (int)grid_dims[0], ny = (int)grid_dims[1], nz = (int)grid_dims[2];
+        const int l0 = (int)lo[0], l1 = (int)lo[1], l2 = (int)lo[2];
+        if (cells_are_f32) {
+            if (f64) vertex_centre_kernel<float, double><<<grid, VC_THREADS, 0, st>>>((const float *)cells_dev[f], (double *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg);
+            else vertex_centre_kernel<float, float><<<grid, VC_THREADS, 0, st>>>((const float *)cells_dev[f], (float *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg);
+        } else {
+            if (f64) vertex_centre_kernel<double, double><<<grid, VC_THREADS, 0, st>>>((const double *)cells_dev[f], (double *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg);
+            else vertex_centre_kernel<double, float><<<grid, VC_THREADS, 0, st>>>((const double *)cells_dev[f], (float *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg);
+        }
+        CK(cudaGetLastError());
+        b.data[f] = dst;
+    }
+    if (stats) {
+        CK(cudaEventRecord(s->ctx->ev1, st));
+        CK(cudaEventSynchronize(s->ctx->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s->ctx->ev0, s->ctx->ev1));
+        stats->kernel_ms = ms; stats->n_launches = s->n_fields; stats->n_cells = 0; stats->n_samples = 0;
+    }
+    b.mask = nullptr;
+    if (mask_host) {
+        bool all_one = true;
+        for (size_t i = 0; i < ncell; i++) if (mask_host[i] != 1) { all_one = false; break; }
+        if (!all_one) {
+            void *dm = nullptr;
+            CK(cudaMalloc(&dm, ncell));
+            CK(cudaMemcpyAsync(dm, mask_host, ncell, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            s->owned.push_back(dm);
+            b.mask = (const unsigned char *)dm;
+            s->any_mask = true;
+            s->bytes += (int64_t)ncell;
+        }
+    }
     return 0;
 }
 

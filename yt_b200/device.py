@@ -62,6 +62,22 @@ def _dptr(a):
     return a.ctypes.data_as(L.dp)
 
 
+class DeviceCells:
+    """One grid's cell-centred fp64 field resident on the device (``ytb200_cells_upload``): the input of
+    the on-device vertex centring.  Uploaded once per (grid, field); every kd leaf of the grid reads it."""
+
+    def __init__(self, ctx, cells):
+        a = _f64(cells)
+        if a.ndim != 3:
+            raise ValueError("cells must be a 3-D array")
+        dims = np.array(a.shape, dtype=np.int64)
+        p = C.c_void_p()
+        lib = L.load()
+        L.check(lib.ytb200_cells_upload(ctx.handle, _dptr(a), dims.ctypes.data_as(L.i64p), C.byref(p)))
+        self.ptr, self.shape, self.ctx = int(p.value), tuple(int(d) for d in a.shape), ctx
+        self._fin = weakref.finalize(self, lib.ytb200_cells_free, ctx.handle, C.c_void_p(self.ptr))
+
+
 class BrickSet:
     """Device-resident list of bricks (``ytb200_brickset``)."""
 
@@ -95,6 +111,33 @@ class BrickSet:
         L.check(L.load().ytb200_brick_upload(
             self.handle, int(index), dims.ctypes.data_as(L.i64p), _dptr(le), _dptr(re), ptrs,
             m.ctypes.data_as(L.u8p) if m is not None else None))
+
+    def from_cells(self, index, cells_ptrs, grid_dims, lo, hi, left_edge, right_edge, log_fields=None, mask=None,
+                   cells_are_f32=False, keep=None, timed=False):
+        """Brick `index` := vertices lo..hi (inclusive) of the grid whose cell-centred fields live at the device
+        pointers `cells_ptrs`: no-ghost vertex centring + log10 + slice + storage conversion in one kernel
+        (grid_patch.py:284-296, amr_kdtree.py:343-365)."""
+        gd = np.ascontiguousarray(grid_dims, dtype=np.int64)
+        lo = np.ascontiguousarray(lo, dtype=np.int64)
+        hi = np.ascontiguousarray(hi, dtype=np.int64)
+        ptrs = (C.c_void_p * self.n_fields)(*[C.c_void_p(int(p)) for p in cells_ptrs])
+        lg = None
+        if log_fields is not None:
+            lg = np.ascontiguousarray([1 if x else 0 for x in log_fields], dtype=np.int32)
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask, dtype=np.uint8)
+            if m.shape != tuple(int(h - l) for l, h in zip(lo, hi)):
+                raise ValueError(f"mask has shape {m.shape}, expected {tuple(int(h - l) for l, h in zip(lo, hi))}")
+        le, re = _f64(left_edge), _f64(right_edge)
+        st = L.Stats() if timed else None
+        L.check(L.load().ytb200_brick_from_cells(
+            self.handle, int(index), gd.ctypes.data_as(L.i64p), lo.ctypes.data_as(L.i64p), hi.ctypes.data_as(L.i64p),
+            _dptr(le), _dptr(re), ptrs, 1 if cells_are_f32 else 0, lg.ctypes.data_as(L.i32p) if lg is not None else None,
+            m.ctypes.data_as(L.u8p) if m is not None else None, C.byref(st) if timed else None))
+        if keep is not None:
+            self._keep.append(keep)
+        return st
 
     def attach(self, index, dev_ptrs, dev_mask, left_edge, right_edge, dims, keep=None):
         """Borrow device arrays (already in this set's storage type); `keep` is kept alive."""
