@@ -165,6 +165,20 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def lsu_pipe_estimate(kind, samples, kernel_ms, sm_mhz, sm_count):
+    """Busy fraction of the L1/shared LSU data pipe (one wavefront per cycle per SM).  Shared-memory wavefronts are
+    exact by construction (two LDS.128 per sample, 4 wavefronts each, zero bank conflicts); wavefronts per global
+    load are the ncu averages of profiles/r01e (VR: 8 corner loads per cell x 4.9) and r01k (PROJ: 14 per load)."""
+    if kind == "vr":
+        cells = samples / N_SAMPLES
+        wf = samples / 32.0 * 8.0 + cells / 32.0 * 8 * 4.9
+    else:
+        wf = samples / 32.0 * 14.0
+    cycles = kernel_ms * 1e-3 * sm_mhz * 1e6
+    return {"wavefronts": wf, "frac": wf / sm_count / cycles,
+            "source": "LDS wavefronts counted, LDG wavefronts per request from ncu (profiles/r01e_vr_*, r01k_proj_*); ncu measured 0.944 (VR) / 0.785 (PROJ)"}
+
+
 def recorded_traffic(workload):
     """DRAM bytes per launch of the cast kernel from the committed ncu --set full capture, if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -312,8 +326,26 @@ def run_ours(args):
             order = np.arange(len(pieces), dtype=np.int64)
             n_bricks = len(pieces)
             cells_desc = [n, n, n]
-        swap = BinarySwap(ctx, res, res, path, cam.lens.viewpoint, rank, world) if world > 1 else None
-        partial = torch.empty((res, res, 8), dtype=torch.float64, device=dev) if world > 1 else None
+        # multi-GPU compositing: binary swap over NVLink peer memory (YTB200_SWAP=nccl: the NCCL send/recv baseline)
+        peer = world > 1 and os.environ.get("YTB200_SWAP", "peer") != "nccl"
+        swap = partial = None
+        if peer:
+            from yt_b200.parallel import PeerSwap
+            swap = PeerSwap(ctx, frame, path, cam.lens.viewpoint, rank, world, f32=(kind == "vr"))
+        elif world > 1:
+            swap = BinarySwap(ctx, res, res, path, cam.lens.viewpoint, rank, world)
+            partial = torch.empty((res, res, 8), dtype=torch.float64, device=dev)
+
+        def cast_partial(timed=False):
+            if peer:
+                return frame.cast_partial(kcode, bricks, order, swap.partial_ptr, tf=tf, n_samples=N_SAMPLES, timed=timed, f32=swap.f32)
+            return frame.cast_partial(kcode, bricks, order, partial.data_ptr(), tf=tf, n_samples=N_SAMPLES, timed=timed)
+
+        def composite():
+            if peer:
+                swap.composite(frame)
+            else:
+                swap.composite(partial, frame)
         stream.synchronize()
 
         # ---- exact work per frame ----------------------------------------------------------------
@@ -333,16 +365,25 @@ def run_ours(args):
                 frame.cast(kcode, bricks, order, tf=tf, n_samples=N_SAMPLES)
             else:
                 frame.clear()
-                frame.cast_partial(kcode, bricks, order, partial.data_ptr(), tf=tf, n_samples=N_SAMPLES)
-                swap.composite(partial, frame)
+                cast_partial()
+                composite()
 
         def frame_e2e():
             if world == 1:
                 frame.render(kcode, bricks, order, img_host, zbuffer=zb_host, tf=tf, n_samples=N_SAMPLES)
+            elif peer:
+                # host arrays are read in place (z-buffer by the cast, the rank's strip of the initial colours by
+                # the swap's last kernel); the composited image lands in rank 0's frame and is copied out
+                cast_partial()
+                composite()
+                if rank == 0:
+                    frame.download(e2e_out)
+                else:
+                    ctx.synchronize()
             else:
                 frame.upload(img_host, zb_host)
-                frame.cast_partial(kcode, bricks, order, partial.data_ptr(), tf=tf, n_samples=N_SAMPLES)
-                swap.composite(partial, frame)
+                cast_partial()
+                composite()
                 if rank == 0:
                     frame.download(img_host)
                 else:
@@ -383,13 +424,26 @@ def run_ours(args):
                 frame.clear()
                 s = frame.cast(kcode, bricks, order, tf=tf, n_samples=N_SAMPLES, timed=True)
             else:
-                s = frame.cast_partial(kcode, bricks, order, partial.data_ptr(), tf=tf, n_samples=N_SAMPLES, timed=True)
+                s = cast_partial(timed=True)
+                composite()   # keeps the ranks' frame counters in step
             kt.append(s.kernel_ms)
         kernel_ms = float(np.mean(kt))
 
+        e2e_out = None
+        if peer:
+            # reference image of the device-timed route, for the check below
+            frame_device()
+            dev_img = frame.download(np.empty((res, res, 4)))
+            e2e_out = D.pinned_empty((res, res, 4))
+            frame.bind_host(img_host, zb_host)
         for _ in range(2):
             frame_e2e()
         ms_e2e = timed(frame_e2e, args.steps) / args.steps
+        if peer:
+            swap.check()   # raises if a device-side wait of the swap timed out
+            frame.bind_host(None)
+            if rank == 0 and not np.array_equal(e2e_out, dev_img):
+                raise SystemExit("e2e image differs from the device-route image")
 
     if rank != 0:
         if world > 1:
@@ -411,17 +465,23 @@ def run_ours(args):
                    "n_samples": N_SAMPLES if kind == "vr" else 1, "lens": "perspective" if amr else "plane-parallel",
                    "view": "camera at (1.6,1.4,1.2) looking at the domain centre" if amr else "default corner camera, width 1.5",
                    "bricks_per_rank": n_bricks, "samples_per_frame": total_samples, "parallelism": "kd%d" % world,
+                   "composite": ("none" if world == 1 else ("binary swap over NVLink peer memory, fp32 (A,B)" if peer and kind == "vr" else
+                                 ("binary swap over NVLink peer memory, fp64 (A,B)" if peer else "binary swap, NCCL send/recv, fp64 (A,B)"))),
                    "l2": "brick (%.2f GB per rank) larger than L2; no flush needed" % (my_elems * elem / 1e9)},
         "ms_per_frame": ms_step,
         "e2e": {"value": gs_e2e, "unit": "Gsamples/s", "ms_per_frame": ms_e2e,
-                "h2d_bytes_per_step": res * res * 40, "d2h_bytes_per_step": res * res * 32,
-                "note": "host (page-locked) image+zbuffer in, host image out through ytb200_render; at N=1 the cast kernel reads/writes the host arrays in place over PCIe; bricks device-resident across frames"},
+                "h2d_bytes_per_step": res * res * 40 if not peer else res * res * 8 * world + res * res * 32,
+                "d2h_bytes_per_step": res * res * 32,
+                "note": ("host (page-locked) image+zbuffer in, host image out through ytb200_render: the cast kernel reads/writes the host arrays in place over PCIe; bricks device-resident across frames" if world == 1 else "host (page-locked) image+zbuffer read in place by every rank (z-buffer by the cast, its strip of the initial colours by the swap), composited image copied out of rank 0's frame; checked equal to the device-route image")},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(args.workload), "peak_source": peak_src, "kernel": "cast_kernel",
                      "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
-                     "note": "volume-render cast is instruction-issue bound (7.7 samples per HBM byte), see `issue`"},
+                     "note": ("volume-render cast: 7.7 samples per HBM byte, so the HBM fraction is structurally ~1-2 %; the unit that is "
+                              "full is the L1/shared LSU data pipe, see `lsu_pipe` and `issue`") if kind == "vr" else
+                             "single-field projection walk: L1 LSU data pipe 78 % busy (ncu r01k), DRAM traffic 2.4x algorithmic"},
+        "lsu_pipe": lsu_pipe_estimate(kind, my_samples, kernel_ms, (clk or {}).get("sm_mhz") or sm_max, ctx.sm_count),
         "issue": {"samples_per_s_per_sm": total_samples / world / (kernel_ms * 1e-3) / ctx.sm_count,
                   "lane_slots_per_sample_at_sm_clock": (ctx.sm_count * 128 * (clk["sm_mhz"] or sm_max) * 1e6) / (my_samples / (kernel_ms * 1e-3))
                   if clk else None},

@@ -164,6 +164,41 @@ int ytb200_partial_compose(ytb200_ctx *ctx, const double *earlier_dev, const dou
 /* image = A + B * image on n_pixels pixels (applies the composed map to the initial colours). */
 int ytb200_partial_apply(ytb200_ctx *ctx, const double *partial_dev, double *image_dev, int64_t n_pixels);
 
+/* Same cast with the partial stored as fp32 (nx,ny,8): half the bytes to exchange; FAST precision only. */
+int ytb200_frame_cast_partial_f32(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
+                                  int64_t n_order, const ytb200_tf *tf, int n_samples, int precision,
+                                  float *partial_dev /* device (nx,ny,8) */, ytb200_stats *stats);
+
+/* ---- binary swap over NVLink peer memory: AMRKDTree.reduce_tree_images (amr_kdtree.py:297-323) -------
+ * One process per GPU.  Every rank creates a swap object (one cudaMalloc'd slab holding the partial-image buffers of
+ * all rounds and the ordering flags), publishes its 64-byte CUDA IPC handle (and that of its frame image, the
+ * destination of the final strips) to the other ranks by any host channel, and opens theirs.  A frame is then
+ *   ytb200_frame_cast_partial[_f32](..., ytb200_swap_partial(swap), ...);  ytb200_swap_composite(swap, frame, broadcast);
+ * Each swap round is ONE kernel that reads the partner's half straight out of its HBM through the peer mapping and
+ * composes it with the local half (A = A2 + B2*A1, B = B2*B1); the final strips are applied to the
+ * initial colours and stored directly into rank 0's (or, with `broadcast`, every rank's) frame image.  No NCCL call,
+ * no receive buffers; cross-GPU ordering is a sequence number per round pushed into the consumer's memory.
+ * `bytes_per_pixel`: 32 (fp32 A,B -- cast with _f32) or 64 (fp64 A,B). */
+/* Multi-GPU frames with host inputs: bind the caller's PAGE-LOCKED image (initial colours) and z-buffer (NULL = ones)
+ * as inputs of the frame; the partial casts then read max_t, and ytb200_swap_composite the initial colours of the
+ * rank's final strip, in place over PCIe instead of from uploaded copies (a rank reads 1/P of the image instead of
+ * uploading all of it).  image_host = NULL unbinds.  The result still lands in the destination frames' device images. */
+int ytb200_frame_bind_host(ytb200_frame *f, const double *image_host, const double *zbuffer_host);
+typedef struct ytb200_swap ytb200_swap;
+int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, int world, int bytes_per_pixel, ytb200_swap **out);
+int ytb200_swap_destroy(ytb200_swap *swap);
+int ytb200_swap_handle(ytb200_swap *swap, void *handle64_out);
+int ytb200_frame_image_handle(ytb200_frame *f, void *handle64_out);
+int ytb200_swap_open(ytb200_swap *swap, int peer_rank, const void *slab_handle64, const void *image_handle64_or_null);
+/* The schedule of this rank (yt_b200.parallel.plan_binary_swap): per round the partner, the pixel region [p0,p1) both
+ * partners hold, the half [k0,k1) this rank keeps, and whether this rank's content is applied first (the far side
+ * of the kd split seen from the viewpoint, amr_kdtools.pyx:708-755). */
+int ytb200_swap_plan(ytb200_swap *swap, int n_rounds, const int32_t *partner, const int64_t *p0, const int64_t *p1,
+                     const int64_t *k0, const int64_t *k1, const int32_t *mine_is_earlier);
+void *ytb200_swap_partial(ytb200_swap *swap);   /* where the NEXT frame's partial cast must write */
+int ytb200_swap_composite(ytb200_swap *swap, ytb200_frame *f, int broadcast);
+int ytb200_swap_error(ytb200_swap *swap, int *error_out);   /* synchronises; 1 = a peer did not arrive within 10 s */
+
 /* ---- one-shot convenience: everything above for host buffers --------------------------------
  * upload image+zbuffer -> cast -> download.  This is the call the e2e benchmark times.
  * When `image_host_inout` (and `zbuffer_host`, if given) are page-locked (ytb200_host_alloc, cudaHostAlloc,

@@ -77,6 +77,18 @@ SIGNATURES = {
     "ytb200_frame_device_image": (C.c_void_p, [C.c_void_p]),
     "ytb200_frame_cast_partial": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, i64p, C.c_int64, C.c_void_p, C.c_int,
                                             C.c_int, C.c_void_p, C.POINTER(Stats)]),
+    "ytb200_frame_cast_partial_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, i64p, C.c_int64, C.c_void_p, C.c_int,
+                                                C.c_int, C.c_void_p, C.POINTER(Stats)]),
+    "ytb200_frame_bind_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ytb200_swap_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "ytb200_swap_destroy": (C.c_int, [C.c_void_p]),
+    "ytb200_swap_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ytb200_frame_image_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ytb200_swap_open": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ytb200_swap_plan": (C.c_int, [C.c_void_p, C.c_int, i32p, i64p, i64p, i64p, i64p, i32p]),
+    "ytb200_swap_partial": (C.c_void_p, [C.c_void_p]),
+    "ytb200_swap_composite": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "ytb200_swap_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "ytb200_partial_compose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "ytb200_partial_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "ytb200_render": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, i64p, C.c_int64, C.c_void_p, C.c_int, C.c_int,

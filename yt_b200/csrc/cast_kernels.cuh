@@ -421,6 +421,7 @@ struct FastSampler {
     // Here the pointer lives in a register, the step is one PTX block with predicated adds, and the NEXT
     // cell's value is requested before the current one is accumulated.
     // ------------------------------------------------------------------------------------------------
+    template <int NF, int DEPTH>
     __device__ __forceinline__ void walk_proj(const WalkState &w)
     {
         const int ny = br->dims[1], nz = br->dims[2];
@@ -430,18 +431,23 @@ struct FastSampler {
         const double d0 = w.d0, d1 = w.d1, d2 = w.d2, max_t = w.max_t;
         int rem0 = w.rem0, rem1 = w.rem1, rem2 = w.rem2;
         double enter_t = w.enter_t;
-        const T *data = (const T *)br->data[0];
-        double a = acc[0];
-        // The walk runs PROJ_DEPTH cells AHEAD of the accumulation: a ring of (value, path length) slots keeps
+        const T *data[NF];
+        double a[NF];
+#pragma unroll
+        for (int f = 0; f < NF; f++) { data[f] = (const T *)br->data[f]; a[f] = acc[f]; }
+        // The walk runs DEPTH cells AHEAD of the accumulation: a ring of (value, path length) slots keeps
         // that many loads of one ray in flight (r01g: with one load in flight a warp paid a full L2/DRAM
         // latency, ~620 cycles, per cell).  `live` goes false when the reference's loop would have ended
         // (it never comes back: the exit tests are monotone along the walk); dead slots hold 0 * 0.
-        T v[PROJ_DEPTH];
-        double dl[PROJ_DEPTH];
+        T v[DEPTH][NF];
+        double dl[DEPTH];
         unsigned live = 1u;   // walk_setup returned true: the start cell is sampled
-        auto produce = [&](T &vj, double &dlj) {
-            vj = T(0);
-            if (live) vj = __ldg(data + o);
+        auto produce = [&](T (&vj)[NF], double &dlj) {
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                vj[f] = T(0);
+                if (live) vj[f] = __ldg(data[f] + o);
+            }
             double len;
             unsigned cont;
             asm volatile(
@@ -488,18 +494,23 @@ struct FastSampler {
             dlj = live ? len : 0.0;
             live &= cont;
         };
+        auto consume = [&](const T (&vj)[NF], double dlj) {
 #pragma unroll
-        for (int j = 0; j < PROJ_DEPTH; j++) produce(v[j], dl[j]);
+            for (int f = 0; f < NF; f++) a[f] = fma((double)vj[f], dlj, a[f]);
+        };
+#pragma unroll
+        for (int j = 0; j < DEPTH; j++) produce(v[j], dl[j]);
         while (live) {
 #pragma unroll
-            for (int j = 0; j < PROJ_DEPTH; j++) {
-                a = fma((double)v[j], dl[j], a);
+            for (int j = 0; j < DEPTH; j++) {
+                consume(v[j], dl[j]);
                 produce(v[j], dl[j]);
             }
         }
 #pragma unroll
-        for (int j = 0; j < PROJ_DEPTH; j++) a = fma((double)v[j], dl[j], a);
-        acc[0] = a;
+        for (int j = 0; j < DEPTH; j++) consume(v[j], dl[j]);
+#pragma unroll
+        for (int f = 0; f < NF; f++) acc[f] = a[f];
     }
 
     template <bool MASKED>
@@ -757,9 +768,18 @@ cast_kernel(const __grid_constant__ CastParams p)
                     }
                 } else if constexpr (!EXACT && KIND == KIND_VR && tfm_is_colour(TFM)) {
                     cast_colour(g, vp, vd, max_t, smp, masked);
-                } else if constexpr (!EXACT && KIND == KIND_PROJ && NF1) {
+                } else if constexpr (!EXACT && KIND == KIND_PROJ) {
+                    // image_samplers.pyx:337-343 sums the first min(4, n_fields) fields
                     WalkState w;
-                    if (walk_setup(g, vp, vd, max_t, smp, w)) smp.walk_proj(w);
+                    if (walk_setup(g, vp, vd, max_t, smp, w)) {
+                        if constexpr (NF1) smp.template walk_proj<1, PROJ_DEPTH>(w);
+                        else {
+                            const int nf = br->n_fields;
+                            if (nf == 2) smp.template walk_proj<2, 4>(w);
+                            else if (nf == 3) smp.template walk_proj<3, 3>(w);
+                            else smp.template walk_proj<4, 3>(w);
+                        }
+                    }
                 } else {
                     if (masked) walk_brick<true>(g, vp, vd, max_t, smp);
                     else walk_brick<false>(g, vp, vd, max_t, smp);
@@ -789,9 +809,15 @@ cast_kernel(const __grid_constant__ CastParams p)
     }
     if (PARTIAL) {
         if (KIND == KIND_VR && !p.tf.grey) { out[3] = 0.0; Bout[3] = 1.0; }
-        double4 *dst = reinterpret_cast<double4 *>(p.partial + pix * 8);
-        dst[0] = make_double4(out[0], out[1], out[2], out[3]);
-        dst[1] = make_double4(Bout[0], Bout[1], Bout[2], Bout[3]);
+        if (p.partial_f32) {
+            float4 *dst = reinterpret_cast<float4 *>(p.partial) + pix * 2;
+            dst[0] = make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
+            dst[1] = make_float4((float)Bout[0], (float)Bout[1], (float)Bout[2], (float)Bout[3]);
+        } else {
+            double4 *dst = reinterpret_cast<double4 *>(p.partial + pix * 8);
+            dst[0] = make_double4(out[0], out[1], out[2], out[3]);
+            dst[1] = make_double4(Bout[0], Bout[1], Bout[2], Bout[3]);
+        }
     } else {
         *reinterpret_cast<double4 *>(p.image + pix * 4) = make_double4(out[0], out[1], out[2], out[3]);
     }
@@ -1015,6 +1041,70 @@ __global__ void __launch_bounds__(VC_THREADS) vertex_centre_kernel(const TIN *__
         if (take_log) v = (v <= 0.0) ? qnan : log10(v);
         *dst = (TOUT)v;
     }
+}
+
+// ---- binary-swap compositing over NVLink peer memory -----------------------------------
+// One swap round = ONE kernel: it composes this rank's kept half with the partner's copy of the same pixels, read
+// straight out of the partner's HBM through its NVLink peer mapping -- no send/recv, no receive buffer.
+// Ordering between GPUs is a sequence number per (rank, round) pushed into the CONSUMER's memory by a
+// stream-ordered `swap_signal_kernel` after the producer kernel, and awaited by `swap_wait_kernel` (local spin).
+template <typename V4>
+__global__ void compose_peer_kernel(const V4 *__restrict__ mine, const V4 *__restrict__ theirs, V4 *__restrict__ out,
+                                    long long n, int mine_is_earlier)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V4 Am = mine[2 * i], Bm = mine[2 * i + 1];
+    const V4 At = theirs[2 * i], Bt = theirs[2 * i + 1];
+    const V4 A1 = mine_is_earlier ? Am : At, B1 = mine_is_earlier ? Bm : Bt;   // applied first
+    const V4 A2 = mine_is_earlier ? At : Am, B2 = mine_is_earlier ? Bt : Bm;   // applied second
+    V4 A, B;
+    A.x = B2.x * A1.x + A2.x; A.y = B2.y * A1.y + A2.y; A.z = B2.z * A1.z + A2.z; A.w = B2.w * A1.w + A2.w;
+    B.x = B2.x * B1.x; B.y = B2.y * B1.y; B.z = B2.z * B1.z; B.w = B2.w * B1.w;
+    out[2 * i] = A;
+    out[2 * i + 1] = B;
+}
+
+// image_dst[k][i] = A + B * C0[i] on this rank's final strip, stored into every destination image (own frame
+// and/or peers' frames over NVLink): the gather of the strips costs no extra pass.
+constexpr int SWAP_MAX_DST = 8;
+struct SwapDst { double4 *img[SWAP_MAX_DST]; int n; };
+
+template <typename V4>
+__global__ void apply_store_kernel(const V4 *__restrict__ partial, const double4 *__restrict__ c0, SwapDst dst, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V4 A = partial[2 * i], B = partial[2 * i + 1];
+    const double4 c = c0[i];
+    const double4 v = make_double4(fma((double)B.x, c.x, (double)A.x), fma((double)B.y, c.y, (double)A.y),
+                                   fma((double)B.z, c.z, (double)A.z), fma((double)B.w, c.w, (double)A.w));
+    for (int k = 0; k < dst.n; k++) dst.img[k][i] = v;
+}
+
+struct SwapSignal { unsigned long long *flag[SWAP_MAX_DST]; int n; };
+
+__global__ void swap_signal_kernel(SwapSignal s, unsigned long long seq)
+{
+    __threadfence_system();
+    if (threadIdx.x < s.n) *reinterpret_cast<volatile unsigned long long *>(s.flag[threadIdx.x]) = seq;
+    __threadfence_system();
+}
+
+// Spin (locally) until every flag has reached `seq`; gives up after ~10 s and records the failure.
+__global__ void swap_wait_kernel(const unsigned long long *flags, int n, unsigned long long seq, int *error)
+{
+    if (threadIdx.x >= n) return;
+    const volatile unsigned long long *f = flags + threadIdx.x;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*f < seq) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 10000000000ULL) { *error = 1; break; }
+        __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 __global__ void f64_to_f32_kernel(const double *src, float *dst, long long n)

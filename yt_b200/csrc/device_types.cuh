@@ -74,7 +74,8 @@ struct CastParams {
     double inv_ns;          // 1 / n_samples
     double *image;          // (nx,ny,4) fp64, in/out
     const double *zbuffer;  // (nx,ny) fp64 or nullptr (== ones)
-    double *partial;        // (nx,ny,8) fp64 affine map output, or nullptr
+    double *partial;        // (nx,ny,8) affine map output (fp64, or fp32 when partial_f32), or nullptr
+    int partial_f32;
     DevTF tf;
     unsigned long long *counters;  // [0] cells handed to sample()
 };

@@ -75,6 +75,9 @@ struct ytb200_frame {
     ytb200_ctx *ctx = nullptr;
     DevCamera cam{};
     double *image = nullptr, *zbuffer = nullptr;
+    // page-locked host arrays bound as INPUTS (ytb200_frame_bind_host): device aliases read in place over PCIe
+    const double *c0_in = nullptr, *zbuffer_in = nullptr;
+    bool zbuffer_in_ones = false;
     double *pos_px = nullptr, *dir_px = nullptr;
     int *order_dev = nullptr;
     int4 *extent_dev = nullptr;
@@ -726,7 +729,8 @@ static cudaError_t launch_kind(const CastParams &p, unsigned grid, size_t smem, 
 }
 
 static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order, int64_t n_order,
-                       const ytb200_tf *tf, int n_samples, int precision, double *partial, ytb200_stats *stats)
+                       const ytb200_tf *tf, int n_samples, int precision, double *partial, ytb200_stats *stats,
+                       bool partial_f32 = false)
 {
     if (!f || !set || (!order && n_order > 0)) return fail(E_ARG, "NULL argument");
     if (kind < 0 || kind > 2) return fail(E_ARG, "bad sampler kind %d", kind);
@@ -756,7 +760,9 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
         p.bricks = set->dev; p.order = f->order_dev; p.extent = f->extent_dev; p.n_order = (int)n_order;
         p.n_samples = n_samples < 1 ? 1 : n_samples;
         p.inv_ns = 1.0 / (double)p.n_samples;
-        p.image = f->image; p.zbuffer = f->zbuffer; p.partial = partial;
+        p.image = f->image; p.zbuffer = f->zbuffer; p.partial = partial; p.partial_f32 = partial_f32 ? 1 : 0;
+        if (partial && f->zbuffer_in) p.zbuffer = f->zbuffer_in;
+        if (partial && f->zbuffer_in_ones) p.zbuffer = nullptr;
         if (tf) p.tf = tf->d;
         p.counters = f->ctx->counters;
         const unsigned grid = (unsigned)(((f->cam.nx + TILE_I - 1) / TILE_I) * ((f->cam.ny + TILE_J - 1) / TILE_J));
@@ -819,6 +825,15 @@ extern "C" int ytb200_frame_cast_partial(ytb200_frame *f, int kind, const ytb200
     return cast_common(f, kind, set, order, n_order, tf, n_samples, precision, partial_dev, stats);
 }
 
+extern "C" int ytb200_frame_cast_partial_f32(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
+                                             int64_t n_order, const ytb200_tf *tf, int n_samples, int precision,
+                                             float *partial_dev, ytb200_stats *stats)
+{
+    if (!partial_dev) return fail(E_ARG, "partial_dev is NULL");
+    if (precision != YTB200_PREC_FAST) return fail(E_ARG, "fp32 partial images are for FAST precision only");
+    return cast_common(f, kind, set, order, n_order, tf, n_samples, precision, reinterpret_cast<double *>(partial_dev), stats, true);
+}
+
 extern "C" int ytb200_frame_count(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
                                   int64_t n_order, int n_samples, ytb200_stats *stats)
 {
@@ -871,6 +886,213 @@ extern "C" int ytb200_partial_apply(ytb200_ctx *ctx, const double *partial, doub
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// binary swap over NVLink peer memory (replaces AMRKDTree.reduce_tree_images, amr_kdtree.py:297-323)
+// ------------------------------------------------------------------------------------------------
+// Per rank ONE cudaMalloc'd slab, shared with the peers through a CUDA IPC handle:
+//   [0, 512)            64 x u64: flag[j] (j < 16) "partner_j's buffer_j of frame `seq` is complete" (pushed by that
+//                       partner), final[w] at 16 + w "rank w has stored its strip of frame `seq` into my image",
+//                       error word at 56
+//   two parity sets of buffers: buffer_0 (n_pixels, the cast's output), buffer_{j+1} (ceil(cap_j / 2)) ...
+// The layout is identical on every rank, so a peer's buffer address is its slab base + the same offset.
+struct SwapRound { int partner; int64_t p0, p1, k0, k1; int earlier; };
+
+struct ytb200_swap {
+    ytb200_ctx *ctx = nullptr;
+    int64_t npx = 0;
+    int rank = 0, world = 1, bpp = 32, k = 0;
+    unsigned char *slab = nullptr;
+    size_t slab_bytes = 0, set_bytes = 0;
+    std::vector<size_t> buf_off;             // offset of buffer_j inside one parity set
+    std::vector<unsigned char *> peer_slab;  // [world], own slab at [rank]
+    std::vector<double *> peer_image;        // [world], frame images of the destinations (nullptr if unknown)
+    std::vector<SwapRound> rounds;
+    unsigned long long seq = 0;
+};
+
+static const size_t SWAP_HDR = 512;
+
+static unsigned long long *swap_flag(unsigned char *slab, int idx) { return reinterpret_cast<unsigned long long *>(slab) + idx; }
+
+extern "C" int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, int world, int bytes_per_pixel, ytb200_swap **out)
+{
+    if (!ctx || !out) return fail(E_ARG, "NULL argument");
+    if (world < 1 || world > SWAP_MAX_DST || (world & (world - 1))) return fail(E_ARG, "world must be a power of two <= %d", SWAP_MAX_DST);
+    if (rank < 0 || rank >= world || n_pixels < 1) return fail(E_ARG, "bad rank / n_pixels");
+    if (bytes_per_pixel != 32 && bytes_per_pixel != 64) return fail(E_ARG, "bytes_per_pixel must be 32 (fp32 A,B) or 64 (fp64 A,B)");
+    DeviceGuard g(ctx->device);
+    auto *s = new ytb200_swap;
+    s->ctx = ctx; s->npx = n_pixels; s->rank = rank; s->world = world; s->bpp = bytes_per_pixel;
+    int k = 0;
+    while ((1 << k) < world) k++;
+    s->k = k;
+    size_t off = 0;
+    int64_t cap = n_pixels;
+    for (int j = 0; j <= k; j++) {
+        s->buf_off.push_back(off);
+        off += ((size_t)cap * (size_t)bytes_per_pixel + 255) / 256 * 256;
+        cap = (cap + 1) / 2;
+    }
+    s->set_bytes = off;
+    s->slab_bytes = SWAP_HDR + 2 * off;
+    CK(cudaMalloc(&s->slab, s->slab_bytes));
+    CK(cudaMemsetAsync(s->slab, 0, SWAP_HDR, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    s->peer_slab.assign((size_t)world, nullptr);
+    s->peer_image.assign((size_t)world, nullptr);
+    s->peer_slab[(size_t)rank] = s->slab;
+    *out = s;
+    return 0;
+}
+
+extern "C" int ytb200_swap_destroy(ytb200_swap *s)
+{
+    if (!s) return 0;
+    DeviceGuard g(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (int w = 0; w < s->world; w++) {
+        if (w == s->rank) continue;
+        if (s->peer_slab[(size_t)w]) cudaIpcCloseMemHandle(s->peer_slab[(size_t)w]);
+        if (s->peer_image[(size_t)w]) cudaIpcCloseMemHandle(s->peer_image[(size_t)w]);
+    }
+    cudaFree(s->slab);
+    delete s;
+    return 0;
+}
+
+extern "C" int ytb200_swap_handle(ytb200_swap *s, void *handle64)
+{
+    if (!s || !handle64) return fail(E_ARG, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(s->ctx->device);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, s->slab));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+extern "C" int ytb200_frame_image_handle(ytb200_frame *f, void *handle64)
+{
+    if (!f || !handle64) return fail(E_ARG, "NULL argument");
+    DeviceGuard g(f->ctx->device);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, f->image));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+extern "C" int ytb200_swap_open(ytb200_swap *s, int peer_rank, const void *slab_handle64, const void *image_handle64)
+{
+    if (!s || !slab_handle64) return fail(E_ARG, "NULL argument");
+    if (peer_rank < 0 || peer_rank >= s->world || peer_rank == s->rank) return fail(E_ARG, "bad peer rank %d", peer_rank);
+    DeviceGuard g(s->ctx->device);
+    cudaIpcMemHandle_t h;
+    void *p = nullptr;
+    memcpy(&h, slab_handle64, 64);
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_slab[(size_t)peer_rank] = static_cast<unsigned char *>(p);
+    if (image_handle64) {
+        memcpy(&h, image_handle64, 64);
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_image[(size_t)peer_rank] = static_cast<double *>(p);
+    }
+    return 0;
+}
+
+extern "C" int ytb200_swap_plan(ytb200_swap *s, int n_rounds, const int32_t *partner, const int64_t *p0, const int64_t *p1,
+                                const int64_t *k0, const int64_t *k1, const int32_t *mine_is_earlier)
+{
+    if (!s || (n_rounds > 0 && (!partner || !p0 || !p1 || !k0 || !k1 || !mine_is_earlier))) return fail(E_ARG, "NULL argument");
+    if (n_rounds != s->k) return fail(E_ARG, "%d rounds given, log2(world) = %d", n_rounds, s->k);
+    s->rounds.clear();
+    int64_t cap = s->npx, q0 = 0, q1 = s->npx;
+    for (int j = 0; j < n_rounds; j++) {
+        if (partner[j] < 0 || partner[j] >= s->world || partner[j] == s->rank) return fail(E_ARG, "round %d: bad partner %d", j, partner[j]);
+        if (p0[j] != q0 || p1[j] != q1) return fail(E_ARG, "round %d: region [%lld,%lld) does not continue the previous keep", j, (long long)p0[j], (long long)p1[j]);
+        if (k0[j] < p0[j] || k1[j] > p1[j] || k1[j] < k0[j] || (k0[j] != p0[j] && k1[j] != p1[j])) return fail(E_ARG, "round %d: bad keep range", j);
+        cap = (cap + 1) / 2;
+        if (k1[j] - k0[j] > cap) return fail(E_ARG, "round %d: keep range longer than its buffer", j);
+        s->rounds.push_back({partner[j], p0[j], p1[j], k0[j], k1[j], mine_is_earlier[j] ? 1 : 0});
+        q0 = k0[j]; q1 = k1[j];
+    }
+    return 0;
+}
+
+extern "C" void *ytb200_swap_partial(ytb200_swap *s)
+{
+    if (!s) return nullptr;
+    const unsigned long long next = s->seq + 1;
+    return s->slab + SWAP_HDR + (size_t)(next & 1) * s->set_bytes + s->buf_off[0];
+}
+
+template <typename V4>
+static int swap_run(ytb200_swap *s, ytb200_frame *f, int broadcast)
+{
+    cudaStream_t st = s->ctx->stream;
+    const unsigned long long seq = ++s->seq;
+    const size_t set = SWAP_HDR + (size_t)(seq & 1) * s->set_bytes;
+    int *err = reinterpret_cast<int *>(swap_flag(s->slab, 56));
+    auto buf = [&](unsigned char *slab, int j) { return reinterpret_cast<V4 *>(slab + set + s->buf_off[(size_t)j]); };
+    auto signal_one = [&](unsigned char *slab, int idx) {
+        SwapSignal sg{};
+        sg.n = 1; sg.flag[0] = swap_flag(slab, idx);
+        swap_signal_kernel<<<1, 32, 0, st>>>(sg, seq);
+    };
+    for (int j = 0; j < s->k; j++)
+        if (!s->peer_slab[(size_t)s->rounds[(size_t)j].partner]) return fail(E_STATE, "peer %d not opened", s->rounds[(size_t)j].partner);
+    if (s->k > 0) signal_one(s->peer_slab[(size_t)s->rounds[0].partner], 0);   // my buffer_0 (the cast's output) is complete
+    int64_t f0 = 0, f1 = s->npx;
+    for (int j = 0; j < s->k; j++) {
+        const SwapRound &r = s->rounds[(size_t)j];
+        swap_wait_kernel<<<1, 32, 0, st>>>(swap_flag(s->slab, j), 1, seq, err);
+        const long long n = (long long)(r.k1 - r.k0);
+        if (n > 0) {
+            const V4 *mine = buf(s->slab, j) + 2 * (r.k0 - r.p0);
+            const V4 *theirs = buf(s->peer_slab[(size_t)r.partner], j) + 2 * (r.k0 - r.p0);
+            compose_peer_kernel<V4><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mine, theirs, buf(s->slab, j + 1), n, r.earlier);
+        }
+        if (j + 1 < s->k) signal_one(s->peer_slab[(size_t)s->rounds[(size_t)j + 1].partner], j + 1);
+        f0 = r.k0; f1 = r.k1;
+    }
+    // final strip -> every destination image, then tell the destinations
+    SwapDst dst{};
+    SwapSignal fin{};
+    for (int w = 0; w < s->world; w++) {
+        if (!broadcast && w != 0) continue;
+        double *img = (w == s->rank) ? f->image : s->peer_image[(size_t)w];
+        if (!img) return fail(E_STATE, "image of destination rank %d not opened", w);
+        dst.img[dst.n++] = reinterpret_cast<double4 *>(img) + f0;
+        fin.flag[fin.n++] = swap_flag(s->peer_slab[(size_t)w], 16 + s->rank);
+    }
+    const long long nf = (long long)(f1 - f0);
+    if (nf > 0 && dst.n > 0)
+        apply_store_kernel<V4><<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(buf(s->slab, s->k), reinterpret_cast<const double4 *>(f->c0_in ? f->c0_in : f->image) + f0, dst, nf);
+    if (fin.n > 0) swap_signal_kernel<<<1, 32, 0, st>>>(fin, seq);
+    if (broadcast || s->rank == 0) swap_wait_kernel<<<1, 32, 0, st>>>(swap_flag(s->slab, 16), s->world, seq, err);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int ytb200_swap_composite(ytb200_swap *s, ytb200_frame *f, int broadcast)
+{
+    if (!s || !f) return fail(E_ARG, "NULL argument");
+    if ((int64_t)f->cam.nx * f->cam.ny != s->npx) return fail(E_ARG, "frame has %lld pixels, swap was created for %lld", (long long)f->cam.nx * f->cam.ny, (long long)s->npx);
+    if ((int)s->rounds.size() != s->k) return fail(E_STATE, "ytb200_swap_plan has not been called");
+    if (f->ctx != s->ctx) return fail(E_ARG, "frame and swap use different contexts");
+    DeviceGuard g(s->ctx->device);
+    return s->bpp == 32 ? swap_run<float4>(s, f, broadcast) : swap_run<double4>(s, f, broadcast);
+}
+
+extern "C" int ytb200_swap_error(ytb200_swap *s, int *error_out)
+{
+    if (!s || !error_out) return fail(E_ARG, "NULL argument");
+    DeviceGuard g(s->ctx->device);
+    CK(cudaStreamSynchronize(s->ctx->stream));
+    CK(cudaMemcpy(error_out, swap_flag(s->slab, 56), sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 // Device-visible alias of a page-locked host allocation (cudaHostAlloc / cudaHostRegister), or nullptr.
 static double *mapped_host_alias(const void *host)
 {
@@ -879,6 +1101,22 @@ static double *mapped_host_alias(const void *host)
     if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
     return static_cast<double *>(a.devicePointer);
+}
+
+extern "C" int ytb200_frame_bind_host(ytb200_frame *f, const double *image_host, const double *zbuffer_host)
+{
+    if (!f) return fail(E_ARG, "frame is NULL");
+    f->c0_in = nullptr; f->zbuffer_in = nullptr; f->zbuffer_in_ones = false;
+    if (!image_host) return 0;   // unbind
+    const double *img = mapped_host_alias(image_host);
+    if (!img) return fail(E_ARG, "image_host is not page-locked (ytb200_host_alloc / cudaHostRegister)");
+    if (zbuffer_host) {
+        const double *zb = mapped_host_alias(zbuffer_host);
+        if (!zb) return fail(E_ARG, "zbuffer_host is not page-locked");
+        f->zbuffer_in = zb;
+    } else f->zbuffer_in_ones = true;
+    f->c0_in = img;
+    return 0;
 }
 
 extern "C" int ytb200_render(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order, int64_t n_order,

@@ -214,6 +214,14 @@ class Frame:
     def clear(self):
         L.check(L.load().ytb200_frame_clear(self.handle))
 
+    def bind_host(self, image=None, zbuffer=None):
+        """Multi-GPU frames: read the initial colours / z-buffer from these PAGE-LOCKED host arrays in place
+        (``ytb200_frame_bind_host``); ``image=None`` unbinds."""
+        L.check(L.load().ytb200_frame_bind_host(
+            self.handle, image.ctypes.data if image is not None else None,
+            zbuffer.ctypes.data if (image is not None and zbuffer is not None) else None))
+        self._bound = (image, zbuffer)
+
     def _order(self, order):
         o = np.ascontiguousarray(order, dtype=np.int64)
         return o, o.ctypes.data_as(L.i64p), int(o.shape[0])
@@ -226,10 +234,12 @@ class Frame:
             int(n_samples), int(precision), C.byref(st) if timed else None))
         return st
 
-    def cast_partial(self, kind, bricks, order, partial_ptr, tf=None, n_samples=10, precision=L.PREC_FAST, timed=False):
+    def cast_partial(self, kind, bricks, order, partial_ptr, tf=None, n_samples=10, precision=L.PREC_FAST, timed=False,
+                     f32=False):
         o, op, n = self._order(order)
         st = L.Stats() if timed else None
-        L.check(L.load().ytb200_frame_cast_partial(
+        fn = L.load().ytb200_frame_cast_partial_f32 if f32 else L.load().ytb200_frame_cast_partial
+        L.check(fn(
             self.handle, int(kind), bricks.handle, op, n, tf.handle if tf is not None else None,
             int(n_samples), int(precision), C.c_void_p(int(partial_ptr)), C.byref(st) if timed else None))
         return st

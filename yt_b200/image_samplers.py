@@ -181,6 +181,12 @@ class ImageSampler:
         fr.download(self.aimage_host)
         self._pending, self._batches, self._dirty = [], [], False
 
+    def peer_swap(self, path, viewpoint, rank, world):
+        """The NVLink peer-memory compositor for this sampler's frame (fp32 partials for the FAST volume render)."""
+        from .parallel import PeerSwap
+        f32 = self.kind == L.VOLUME_RENDER and self._precision == L.PREC_FAST
+        return PeerSwap(self._ctx, self._frame, path, viewpoint, rank, world, f32=f32)
+
     def flush_parallel(self, swap, broadcast=True):
         """Multi-GPU flush: cast this rank's bricks into an affine partial image, composite the partials
         of all ranks in view order (binary swap), leave the result in the host image of rank 0 (of every
@@ -195,18 +201,26 @@ class ImageSampler:
         nx, ny = self.aimage_host.shape[:2]
         dev = torch.device("cuda", self._ctx.device)
         stream = torch.cuda.ExternalStream(self._ctx.stream, device=dev)
-        with torch.cuda.stream(stream):
-            partial = torch.empty((nx * ny, 8), dtype=torch.float64, device=dev)
-            if len(work) > 1:
-                raise NotImplementedError("one brick set per parallel flush")
-            if work:
-                bs, order = work[0]
-            else:
-                bs, order = self._empty_set(), np.zeros(0, dtype=np.int64)
-            fr.cast_partial(self.kind, bs, order, partial.data_ptr(), tf=self._tables, n_samples=self.n_samples,
-                            precision=self._precision)
-            swap.composite(partial, fr, broadcast=broadcast)
-            stream.synchronize()
+        if len(work) > 1:
+            raise NotImplementedError("one brick set per parallel flush")
+        if work:
+            bs, order = work[0]
+        else:
+            bs, order = self._empty_set(), np.zeros(0, dtype=np.int64)
+        from .parallel import PeerSwap
+        if isinstance(swap, PeerSwap):
+            # NVLink peer-memory route: no collective, the swap rounds read the partners' HBM directly
+            fr.cast_partial(self.kind, bs, order, swap.partial_ptr, tf=self._tables, n_samples=self.n_samples,
+                            precision=self._precision, f32=swap.f32)
+            swap.composite(fr, broadcast=broadcast)
+            swap.check()
+        else:
+            with torch.cuda.stream(stream):
+                partial = torch.empty((nx * ny, 8), dtype=torch.float64, device=dev)
+                fr.cast_partial(self.kind, bs, order, partial.data_ptr(), tf=self._tables, n_samples=self.n_samples,
+                                precision=self._precision)
+                swap.composite(partial, fr, broadcast=broadcast)
+                stream.synchronize()
         if broadcast or swap.rank == 0:
             fr.download(self.aimage_host)
         self._pending, self._batches, self._dirty = [], [], False

@@ -13,6 +13,9 @@ child is applied first follows the reference's traversal rule (amr_kdtools.pyx:7
 """
 import os
 
+import ctypes as C
+import weakref
+
 import numpy as np
 
 # ---- communicator: one process per GPU (torchrun), torch.distributed for the plumbing -------------------
@@ -214,3 +217,73 @@ class BinarySwap:
         for r, (p0, p1) in enumerate(self.strips):
             if p1 > p0:
                 dist.broadcast(image[p0:p1], src=r, group=self.group)
+
+
+class PeerSwap:
+    """Binary swap over NVLink peer memory (``ytb200_swap_*``): the same schedule as :class:`BinarySwap`, but each
+    round is one CUDA kernel that reads the partner's half directly from its HBM, and the final strips are stored
+    straight into the destination frame(s).  torch.distributed is used once, at construction, to pass the CUDA IPC
+    handles around; a frame issues no collective at all.
+
+        swap = PeerSwap(ctx, frame, path, viewpoint, rank, world)
+        frame.cast_partial(kind, bricks, order, swap.partial_ptr, ..., f32=swap.f32)
+        swap.composite(frame)            # result in rank 0's frame image (every rank's with broadcast=True)
+    """
+
+    def __init__(self, ctx, frame, path, viewpoint, rank, world, f32=True, group=None):
+        import torch.distributed as dist
+        from . import _lib as L
+        lib = L.load()
+        self.ctx, self.rank, self.world, self.f32 = ctx, rank, world, bool(f32)
+        self.npx = frame.nx * frame.ny
+        h = C.c_void_p()
+        L.check(lib.ytb200_swap_create(ctx.handle, self.npx, rank, world, 32 if f32 else 64, C.byref(h)))
+        self.handle = h
+        self._fin = weakref.finalize(self, lib.ytb200_swap_destroy, h)
+        if world > 1:
+            mine_slab, mine_img = C.create_string_buffer(64), C.create_string_buffer(64)
+            L.check(lib.ytb200_swap_handle(h, mine_slab))
+            L.check(lib.ytb200_frame_image_handle(frame.handle, mine_img))
+            everyone = [None] * world
+            dist.all_gather_object(everyone, (rank, mine_slab.raw, mine_img.raw), group=group)
+            for r, slab, img in everyone:
+                if r != rank:
+                    L.check(lib.ytb200_swap_open(h, int(r), slab, img))
+        self.set_view(path, viewpoint)
+        self.launches_per_composite = 3 * len(self.rounds) + 3
+
+    def set_view(self, path, viewpoint):
+        """(Re)plan the rounds for a viewpoint: which side of every kd split is composited first."""
+        from . import _lib as L
+        self.rounds, self.strip = plan_binary_swap(self.rank, self.world, self.npx, path, viewpoint)
+        n = len(self.rounds)
+        partner = np.ascontiguousarray([int(r["partner"]) for r in self.rounds], dtype=np.int32)
+        earlier = np.ascontiguousarray([1 if r["earlier"] else 0 for r in self.rounds], dtype=np.int32)
+        p0 = np.zeros(n, dtype=np.int64)
+        p1 = np.zeros(n, dtype=np.int64)
+        k0 = np.ascontiguousarray([r["keep"][0] for r in self.rounds], dtype=np.int64)
+        k1 = np.ascontiguousarray([r["keep"][1] for r in self.rounds], dtype=np.int64)
+        for j, r in enumerate(self.rounds):
+            p0[j] = min(r["keep"][0], r["send"][0])
+            p1[j] = max(r["keep"][1], r["send"][1])
+        L.check(L.load().ytb200_swap_plan(self.handle, n, partner.ctypes.data_as(L.i32p), p0.ctypes.data_as(L.i64p),
+                                          p1.ctypes.data_as(L.i64p), k0.ctypes.data_as(L.i64p), k1.ctypes.data_as(L.i64p),
+                                          earlier.ctypes.data_as(L.i32p)))
+
+    @property
+    def partial_ptr(self):
+        """Device pointer the NEXT frame's partial cast must write to (alternates between two buffer sets)."""
+        from . import _lib as L
+        return int(L.load().ytb200_swap_partial(self.handle))
+
+    def composite(self, frame, broadcast=False):
+        from . import _lib as L
+        L.check(L.load().ytb200_swap_composite(self.handle, frame.handle, 1 if broadcast else 0))
+
+    def check(self):
+        """Synchronise and raise if a peer failed to arrive (the device-side waits give up after 10 s)."""
+        from . import _lib as L
+        e = C.c_int(0)
+        L.check(L.load().ytb200_swap_error(self.handle, C.byref(e)))
+        if e.value:
+            raise RuntimeError("binary swap: a peer did not signal within 10 s")

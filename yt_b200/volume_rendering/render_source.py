@@ -8,6 +8,7 @@ frame (``batched=True``, the default); ``batched=False`` drives the sampler bric
 like the reference does.
 """
 import abc
+import os
 
 import numpy as np
 
@@ -278,8 +279,12 @@ class KDTreeVolumeSource(VolumeSource):
             if len(self.volume.tree.traverse()) > 0:
                 bricks = self.volume.device_bricks(self.sampler._ctx, self.sampler._storage)
                 self.sampler.cast_bricks(bricks, self.volume.view_order(camera.lens.viewpoint))
-            swap = BinarySwap(self.sampler._ctx, nx, ny, self.volume.kd_path(), camera.lens.viewpoint,
-                              self.volume.comm_rank, self.volume.comm_size)
+            if os.environ.get("YTB200_SWAP", "peer") == "nccl":
+                swap = BinarySwap(self.sampler._ctx, nx, ny, self.volume.kd_path(), camera.lens.viewpoint,
+                                  self.volume.comm_rank, self.volume.comm_size)
+            else:
+                swap = self.sampler.peer_swap(self.volume.kd_path(), camera.lens.viewpoint,
+                                              self.volume.comm_rank, self.volume.comm_size)
             self.sampler.flush_parallel(swap, broadcast=True)
         elif self.batched:
             bricks = self.volume.device_bricks(self.sampler._ctx, self.sampler._storage)
