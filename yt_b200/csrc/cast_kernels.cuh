@@ -531,8 +531,14 @@ struct FastSampler {
         const double tmid = fma(0.5, dt64, enter_t);
         const double xd = fma(tmid, dc[0], ob[0]), yd = fma(tmid, dc[1], ob[1]), zd = fma(tmid, dc[2], ob[2]);
         if (KIND == KIND_IPROJ) {
-            // the projection family carries the 1e-6 bar: sample in fp64 (contraction allowed)
+            // The projection family carries the 1e-6 bar: fp64.  Along the ray the trilinear interpolant
+            // (fixed_interpolator.cpp:34-52) is a cubic in the sample index s, so the n_samples midpoint samples
+            // of image_samplers.pyx:393-401 sum in closed form: sum_s (c0 + c1 s + c2 s^2 + c3 s^3) =
+            // n c0 + c1 S1 + c2 S2 + c3 S3 with the power sums of 0..n-1 -- O(1) per cell instead of O(n_samples),
+            // equal to the sample loop up to fp64 rounding.
             const double sxd = dc[0] * dt64, syd = dc[1] * dt64, szd = dc[2] * dt64;
+            const double nn = (double)n_samples;
+            const double S1 = 0.5 * nn * (nn - 1.0), S2 = nn * (nn - 1.0) * (2.0 * nn - 1.0) * (1.0 / 6.0), S3 = S1 * S1;
             const int nf = NF1 ? 1 : (n_fields < 3 ? n_fields : 3);
 #pragma unroll
             for (int j = 0; j < 3; j++) {
@@ -540,14 +546,22 @@ struct FastSampler {
                     const T *d = (const T *)br->data[j] + off;
                     const double a0 = (double)__ldg(d), a1 = (double)__ldg(d + 1), b0 = (double)__ldg(d + sy), b1 = (double)__ldg(d + sy + 1);
                     const double e0 = (double)__ldg(d + sx), e1 = (double)__ldg(d + sx + 1), f0 = (double)__ldg(d + sx + sy), f1 = (double)__ldg(d + sx + sy + 1);
-                    double x = xd, y = yd, z = zd, sum = 0.0;
-                    for (int s = 0; s < n_samples; s++) {
-                        const double v00 = fma(z, a1 - a0, a0), v01 = fma(z, b1 - b0, b0);
-                        const double v10 = fma(z, e1 - e0, e0), v11 = fma(z, f1 - f0, f0);
-                        const double v0 = fma(y, v01 - v00, v00), v1 = fma(y, v11 - v10, v10);
-                        sum += fma(x, v1 - v0, v0);
-                        x += sxd; y += syd; z += szd;
-                    }
+                    // z-edges, linear in s: v = p + q s
+                    const double pa = fma(zd, a1 - a0, a0), qa = szd * (a1 - a0);
+                    const double pb = fma(zd, b1 - b0, b0), qb = szd * (b1 - b0);
+                    const double pe = fma(zd, e1 - e0, e0), qe = szd * (e1 - e0);
+                    const double pf = fma(zd, f1 - f0, f0), qf = szd * (f1 - f0);
+                    // faces x0 | x1, quadratic in s: v = u0 + u1 s + u2 s^2  (y-lerp of two z-edges)
+                    const double d0p = pb - pa, d0q = qb - qa, d1p = pf - pe, d1q = qf - qe;
+                    const double u00 = fma(yd, d0p, pa), u01 = fma(syd, d0p, fma(yd, d0q, qa)), u02 = syd * d0q;
+                    const double u10 = fma(yd, d1p, pe), u11 = fma(syd, d1p, fma(yd, d1q, qe)), u12 = syd * d1q;
+                    // x-lerp: cubic
+                    const double g0 = u10 - u00, g1 = u11 - u01, g2 = u12 - u02;
+                    const double c0 = fma(xd, g0, u00);
+                    const double c1 = fma(sxd, g0, fma(xd, g1, u01));
+                    const double c2 = fma(sxd, g1, fma(xd, g2, u02));
+                    const double c3 = sxd * g2;
+                    const double sum = fma(c3, S3, fma(c2, S2, fma(c1, S1, c0 * nn)));
                     acc[j] = fma(sum, dt64, acc[j]);
                 }
             }
