@@ -199,6 +199,18 @@ void *ytb200_swap_partial(ytb200_swap *swap);   /* where the NEXT frame's partia
 int ytb200_swap_composite(ytb200_swap *swap, ytb200_frame *f, int broadcast);
 int ytb200_swap_error(ytb200_swap *swap, int *error_out);   /* synchronises; 1 = a peer did not arrive within 10 s */
 
+/* ---- opaque sources: zlines / zpoints (yt/utilities/lib/misc_utilities.pyx:244-404) -------------------
+ * Depth-tested painters of line segments (consecutive point pairs) and discs into the HOST (nx,ny,4) image and
+ * (nx,ny) z-buffer that the cast then starts from / stops at (render_source.py:1062-1252, scene.py:581-625).
+ * Order-dependent serial host code, as in the reference; statement-for-statement equal results.
+ * `order` (zpoints) is np.argsort(zs) of the caller.  Returns 0 or -1 (bad argument). */
+int ytb200_zlines(double *image, double *zbuffer, int64_t nx, int64_t ny, const int64_t *xs, const int64_t *ys,
+                  const double *zs, int64_t n_points, const double *colors /* n_colors x 4 */, int64_t n_colors,
+                  int points_per_color, int thick, int flip, int crop);
+int ytb200_zpoints(double *image, double *zbuffer, int64_t nx, int64_t ny, const int64_t *xs, const int64_t *ys,
+                   const double *zs, int64_t n_points, const int64_t *order, const double *colors, int64_t n_colors,
+                   const int64_t *radii, int points_per_color, int flip);
+
 /* ---- one-shot convenience: everything above for host buffers --------------------------------
  * upload image+zbuffer -> cast -> download.  This is the call the e2e benchmark times.
  * When `image_host_inout` (and `zbuffer_host`, if given) are page-locked (ytb200_host_alloc, cudaHostAlloc,

@@ -100,6 +100,10 @@ SIGNATURES = {
     "ytb200_kdtree_node_count": (C.c_int64, [C.c_void_p]),
     "ytb200_kdtree_nodes": (C.c_int, [C.c_void_p, i64p, i64p, i32p, i32p, i32p, dp, dp, dp]),
     "ytb200_kdtree_traverse": (C.c_int64, [C.c_void_p, dp, i32p, C.c_int64]),
+    "ytb200_zlines": (C.c_int, [dp, dp, C.c_int64, C.c_int64, i64p, i64p, dp, C.c_int64, dp, C.c_int64, C.c_int, C.c_int,
+                                C.c_int, C.c_int]),
+    "ytb200_zpoints": (C.c_int, [dp, dp, C.c_int64, C.c_int64, i64p, i64p, dp, C.c_int64, i64p, dp, C.c_int64, i64p,
+                                 C.c_int, C.c_int]),
     "ytb200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "ytb200_host_free": (C.c_int, [C.c_void_p]),
 }

@@ -3,7 +3,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", "ytb200.cu"), os.path.join(HERE, "csrc", "kdtree.cpp")]
+SRC = [os.path.join(HERE, "csrc", "ytb200.cu"), os.path.join(HERE, "csrc", "kdtree.cpp"), os.path.join(HERE, "csrc", "zraster.cpp")]
 OUT = os.path.join(HERE, "libytb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -7,7 +7,17 @@ from .camera import Camera  # noqa: F401
 from .image_array import ImageArray  # noqa: F401
 from .lens import PerspectiveLens, PlaneParallelLens, lenses  # noqa: F401
 from .off_axis_projection import off_axis_projection  # noqa: F401
-from .render_source import KDTreeVolumeSource, VolumeSource, create_volume_source  # noqa: F401
+from .render_source import (  # noqa: F401
+    BoxSource,
+    CoordinateVectorSource,
+    GridSource,
+    KDTreeVolumeSource,
+    LineSource,
+    OpaqueSource,
+    PointSource,
+    VolumeSource,
+    create_volume_source,
+)
 from .scene import Scene  # noqa: F401
 from .transfer_function_helper import TransferFunctionHelper  # noqa: F401
 from .transfer_functions import (  # noqa: F401

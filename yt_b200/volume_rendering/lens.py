@@ -111,5 +111,34 @@ class PerspectiveLens(Lens):
     def set_viewpoint(self, camera):
         self.viewpoint = self.front_center  # lens.py:236-240 -- NOT the camera position
 
+    def project_to_plane(self, camera, pos, res=None):
+        """Pinhole projection of points onto the image plane (lens.py:242-288), operation for operation;
+        points behind the camera are pushed outside the image instead of being dropped."""
+        res = camera.resolution if res is None else res
+        width = np.array(camera.width, dtype="float64")
+        position = np.array(camera.position, dtype="float64")
+        width[1] = width[0] * res[1] / res[0]
+        sight_vector = np.array(pos, dtype="float64") - position
+        pos1 = sight_vector          # the reference aliases these two arrays (lens.py:251-253)
+        for i in range(sight_vector.shape[0]):
+            norm = np.sqrt(np.dot(sight_vector[i], sight_vector[i]))
+            if norm != 0:
+                sight_vector[i] = sight_vector[i] / norm
+        sight_center = camera.position + camera.width[2] * camera.unit_vectors[2]
+        for i in range(sight_vector.shape[0]):
+            sight_angle_cos = np.clip(np.dot(sight_vector[i], camera.unit_vectors[2]), -1.0, 1.0)
+            if np.arccos(sight_angle_cos) < 0.5 * np.pi:
+                sight_length = width[2] / sight_angle_cos
+            else:
+                sight_length = np.sqrt(width[0] ** 2 + width[1] ** 2)
+                sight_length = sight_length / np.sqrt(1 - sight_angle_cos ** 2)
+            pos1[i] = position + sight_length * sight_vector[i]
+        dx = np.dot(pos1 - sight_center, camera.unit_vectors[0])
+        dy = np.dot(pos1 - sight_center, camera.unit_vectors[1])
+        dz = np.dot(np.asarray(pos, dtype="float64") - position, camera.unit_vectors[2])
+        px = (res[0] * 0.5 + res[0] / width[0] * dx).astype("int64")
+        py = (res[1] * 0.5 + res[1] / width[1] * dy).astype("int64")
+        return px, py, dz
+
 
 lenses = {"plane-parallel": PlaneParallelLens, "perspective": PerspectiveLens}

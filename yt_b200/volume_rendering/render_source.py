@@ -301,3 +301,179 @@ class KDTreeVolumeSource(VolumeSource):
         if self._volume is not None:
             image = self.volume.reduce_tree_images(image, camera.lens.viewpoint, use_opacity=self.transfer_function.grey_opacity)
         return super().finalize_image(camera, image)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# opaque sources (render_source.py:989-1591): painted into the ZBuffer before the volume is cast
+# ---------------------------------------------------------------------------------------------------------
+def _fresh_zbuffer(camera, zbuffer):
+    if zbuffer is None:
+        empty = camera.lens.new_image(camera)
+        empty[:] = 0.0
+        return ZBuffer(empty, np.full(empty.shape[:2], np.inf, dtype="float64"))
+    return zbuffer
+
+
+class PointSource(OpaqueSource):
+    """Depth-tested points (render_source.py:989-1103): ``positions`` (N,3), ``colors`` (N,4) RGBA, ``radii`` pixels."""
+    data_source = None
+
+    def __init__(self, positions, colors=None, color_stride=1, radii=None):
+        super().__init__()
+        positions = np.asarray(positions, dtype="float64")
+        assert positions.ndim == 2 and positions.shape[1] == 3
+        if colors is not None:
+            colors = np.asarray(colors, dtype="float64")
+            assert colors.ndim == 2 and colors.shape[1] == 4
+            assert colors.shape[0] == positions.shape[0]
+        if radii is None or np.ndim(radii) == 0:
+            radii = (0 if radii is None else radii) * np.ones(positions.shape[0], dtype="int64")
+        else:
+            radii = np.asarray(radii, dtype="int64")
+            assert radii.ndim == 1 and radii.shape[0] == positions.shape[0]
+        self.positions = positions
+        self.colors = np.ones((len(positions), 4)) if colors is None else colors
+        self.color_stride = color_stride
+        self.radii = radii
+
+    def _validate(self):
+        pass
+
+    def render(self, camera, zbuffer=None):
+        from ..zraster import zpoints
+        zbuffer = _fresh_zbuffer(camera, zbuffer)
+        camera.lens.setup_box_properties(camera)
+        px, py, dz = camera.lens.project_to_plane(camera, self.positions)
+        zpoints(zbuffer.rgba, zbuffer.z, px, py, dz, self.colors, self.radii, self.color_stride)
+        self.zbuffer = zbuffer
+        return zbuffer
+
+    def __repr__(self):
+        return "<Point Source>"
+
+
+class LineSource(OpaqueSource):
+    """Depth-tested line segments (render_source.py:1106-1254): ``positions`` (N,2,3) end points, ``colors`` (N,4)."""
+    data_source = None
+
+    def __init__(self, positions, colors=None, color_stride=1):
+        super().__init__()
+        positions = np.asarray(positions, dtype="float64")
+        assert positions.ndim == 3 and positions.shape[1] == 2 and positions.shape[2] == 3
+        if colors is not None:
+            colors = np.asarray(colors, dtype="float64")
+            assert colors.ndim == 2 and colors.shape[1] == 4
+        n = positions.shape[0]
+        self.positions = positions.reshape((2 * n, 3))
+        # the reference sizes the default colours by the RESHAPED positions (render_source.py:1176-1181)
+        self.colors = np.ones((len(self.positions), 4)) if colors is None else colors
+        self.color_stride = color_stride
+
+    def _validate(self):
+        pass
+
+    def render(self, camera, zbuffer=None):
+        from ..zraster import zlines
+        zbuffer = _fresh_zbuffer(camera, zbuffer)
+        camera.lens.setup_box_properties(camera)
+        px, py, dz = camera.lens.project_to_plane(camera, self.positions)
+        zlines(zbuffer.rgba, zbuffer.z, px.astype("int64"), py.astype("int64"), dz, self.colors.astype("float64"), self.color_stride)
+        self.zbuffer = zbuffer
+        return zbuffer
+
+    def __repr__(self):
+        return "<Line Source>"
+
+
+_BOX_EDGES = [0, 1, 1, 2, 2, 3, 3, 0] + [4, 5, 5, 6, 6, 7, 7, 4] + [0, 4, 1, 5, 2, 6, 3, 7]
+
+
+def _box_vertices(corners):
+    """corners (8,3,nboxes) -> (12*nboxes, 2, 3) edge end points, the reference's ordering (render_source.py:1302-1309)."""
+    nb = corners.shape[2]
+    vertices = np.empty([nb * 24, 3])
+    for i in range(3):
+        vertices[:, i] = corners[_BOX_EDGES, i, ...].ravel(order="F")
+    return vertices.reshape((nb * 12, 2, 3))
+
+
+class BoxSource(LineSource):
+    """The 12 edges of a box (render_source.py:1257-1316)."""
+
+    def __init__(self, left_edge, right_edge, color=None):
+        left_edge, right_edge = np.asarray(left_edge, dtype="float64"), np.asarray(right_edge, dtype="float64")
+        assert left_edge.shape == (3,) and right_edge.shape == (3,)
+        color = np.array([[1.0, 1.0, 1.0, 1.0]]) if color is None else np.atleast_2d(np.asarray(color, dtype="float64"))
+        assert color.shape == (1, 4)
+        from .utils import get_corners
+        corners = get_corners(left_edge.copy(), right_edge.copy())
+        super().__init__(_box_vertices(corners[:, :, None]), color, color_stride=24)
+
+
+class GridSource(LineSource):
+    """The edges of every grid of a data source, coloured by level (render_source.py:1318-1430)."""
+
+    def __init__(self, data_source, alpha=0.3, cmap=None, min_level=None, max_level=None):
+        from . import colormaps
+        self.data_source = data_source_or_all(data_source)
+        corners, levels = [], []
+        for block, _mask in self.data_source.blocks:
+            le, re = block.LeftEdge, block.RightEdge
+            corners.append(np.array([[le[0], le[1], le[2]], [re[0], le[1], le[2]], [re[0], re[1], le[2]], [le[0], re[1], le[2]],
+                                     [le[0], le[1], re[2]], [re[0], le[1], re[2]], [re[0], re[1], re[2]], [le[0], re[1], re[2]]],
+                                    dtype="float64"))
+            levels.append(block.Level)
+        corners = np.dstack(corners)
+        levels = np.array(levels)
+        if max_level is not None:
+            subset = levels <= max_level
+            levels, corners = levels[subset], corners[:, :, subset]
+        if min_level is not None:
+            subset = levels >= min_level
+            levels, corners = levels[subset], corners[:, :, subset]
+        top = max(float(self.data_source.ds.index.max_level), 1e-300)
+        # apply_colormap quantises to 8 bits (image_writer.py); the map itself is an input to both sides
+        rgba = colormaps.get(cmap or "arbre")(np.clip(levels / top, 0.0, 1.0))
+        colors = np.floor(np.asarray(rgba, dtype="float64") * 255.0) / 255.0
+        colors[:, 3] = alpha
+        LineSource.__init__(self, _box_vertices(corners), colors, color_stride=24)
+
+
+class CoordinateVectorSource(OpaqueSource):
+    """Small x/y/z axes triad in the image corner (render_source.py:1432-1593)."""
+    data_source = None
+
+    def __init__(self, colors=None, alpha=1.0, *, thickness=1):
+        super().__init__()
+        if colors is None:
+            colors = np.zeros((3, 4))
+            colors[0, 0] = colors[1, 1] = colors[2, 2] = 1.0
+            colors[:, 3] = alpha
+        self.colors = np.asarray(colors, dtype="float64")
+        self.thick = thickness
+
+    def _validate(self):
+        pass
+
+    def render(self, camera, zbuffer=None):
+        from ..zraster import zlines
+        camera.lens.setup_box_properties(camera)
+        positions = np.zeros([6, 3])
+        positions[:] = camera.focus
+        for i in range(3):
+            positions[2 * i + 1, i] += camera.width[i] / 16.0
+        px, py, dz = camera.lens.project_to_plane(camera, positions)
+        dpx, dpy = px[1::2] - px[::2], py[1::2] - py[::2]
+        lpx = camera.resolution[0] / 8
+        lpy = camera.resolution[1] - camera.resolution[1] / 8
+        px, py = px.astype("float64"), py.astype("float64")
+        px[::2], px[1::2] = lpx, lpx + dpx
+        py[::2], py[1::2] = lpy, lpy + dpy
+        dz = np.zeros_like(dz)
+        zbuffer = _fresh_zbuffer(camera, zbuffer)
+        zlines(zbuffer.rgba, zbuffer.z, px.astype("int64"), py.astype("int64"), dz, self.colors.astype("float64"), thick=self.thick)
+        self.zbuffer = zbuffer
+        return zbuffer
+
+    def __repr__(self):
+        return "<Coordinate Vector Source>"

@@ -76,6 +76,22 @@ class Scene:
         # rotate 180 degrees so the orientation agrees with a PlotWindow plot
         return ImageArray(np.rot90(im, k=2), info={"imtype": "rendering"})
 
+    # -- annotations (scene.py:755-880): opaque sources added under fixed keys -------------------------------
+    def annotate_domain(self, ds, color=None):
+        from .render_source import BoxSource
+        self.add_source(BoxSource(ds.domain_left_edge, ds.domain_right_edge, color=color))
+        return self
+
+    def annotate_grids(self, data_source, alpha=0.3, cmap=None, min_level=None, max_level=None):
+        from .render_source import GridSource
+        self.add_source(GridSource(data_source, alpha=alpha, cmap=cmap, min_level=min_level, max_level=max_level))
+        return self
+
+    def annotate_axes(self, colors=None, alpha=1.0, *, thickness=1):
+        from .render_source import CoordinateVectorSource
+        self.add_source(CoordinateVectorSource(colors, alpha, thickness=thickness))
+        return self
+
     def save(self, fname=None, sigma_clip=None, render=True):
         if fname is None:
             fname = "Render_opaque.png"
