@@ -268,6 +268,7 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus %d needs torchrun with --nproc-per-node %d" % (args.gpus, args.gpus))
+    local = local % max(torch.cuda.device_count(), 1)   # a launcher may expose one device per rank
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -330,9 +331,19 @@ def run_ours(args):
         peer = world > 1 and os.environ.get("YTB200_SWAP", "peer") != "nccl"
         swap = partial = None
         if peer:
+            # CUDA IPC needs every rank to see its peers' devices; if any rank cannot map a peer, ALL ranks take the
+            # NCCL send/recv compositor instead (still entirely on the GPUs)
             from yt_b200.parallel import PeerSwap
-            swap = PeerSwap(ctx, frame, path, cam.lens.viewpoint, rank, world, f32=(kind == "vr"))
-        elif world > 1:
+            ok = 1
+            try:
+                swap = PeerSwap(ctx, frame, path, cam.lens.viewpoint, rank, world, f32=(kind == "vr"))
+            except Exception as exc:  # noqa: BLE001
+                sys.stderr.write("rank %d: peer-memory swap unavailable (%s); using the NCCL compositor\n" % (rank, exc))
+                ok, swap = 0, None
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            peer = bool(flag.item())
+        if world > 1 and not peer:
             swap = BinarySwap(ctx, res, res, path, cam.lens.viewpoint, rank, world)
             partial = torch.empty((res, res, 8), dtype=torch.float64, device=dev)
 

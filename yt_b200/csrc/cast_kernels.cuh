@@ -717,7 +717,7 @@ cast_kernel(const __grid_constant__ CastParams p)
 #pragma unroll
             for (int c = 0; c < 4; c++) { smp.acc[c] = init[c]; smp.rgba[c] = (float)init[c]; smp.B[c] = 1.f; }
             smp.ca.c01 = make_float2((float)init[0], (float)init[1]); smp.ca.c2 = (float)init[2]; smp.ca.c3 = (float)init[3];
-            smp.ca.b01 = make_float2(1.f, 1.f); smp.ca.b2 = 1.f; smp.ca.b3 = 1.f;
+            smp.ca.fired = 0u;
             smp.prm = &p;
         }
     }
@@ -761,15 +761,15 @@ cast_kernel(const __grid_constant__ CastParams p)
                     // accumulators at brick entry, parked in local memory for the (rare) careful re-walk
                     volatile float entry[8];
                     entry[0] = smp.ca.c01.x; entry[1] = smp.ca.c01.y; entry[2] = smp.ca.c2; entry[3] = smp.ca.c3;
-                    if (PARTIAL) { entry[4] = smp.ca.b01.x; entry[5] = smp.ca.b01.y; entry[6] = smp.ca.b2; entry[7] = smp.ca.b3; }
+                    if (PARTIAL) entry[4] = __uint_as_float(smp.ca.fired);
                     smp.doubt = false;
                     cast_colour(g, vp, vd, max_t, smp, masked);
                     if (smp.doubt) {
                         CarefulSampler<PARTIAL, tfm_grey(TFM), T> cs;
                         cs.ray = s_ray; cs.br = br; cs.tf = &p.tf; cs.base = smp.ct.base; cs.n_samples = p.n_samples;
                         cs.ca.c01 = make_float2(entry[0], entry[1]); cs.ca.c2 = entry[2]; cs.ca.c3 = entry[3];
-                        cs.ca.b01 = make_float2(1.f, 1.f); cs.ca.b2 = 1.f; cs.ca.b3 = 1.f;
-                        if (PARTIAL) { cs.ca.b01 = make_float2(entry[4], entry[5]); cs.ca.b2 = entry[6]; cs.ca.b3 = entry[7]; }
+                        cs.ca.fired = 0u;
+                        if (PARTIAL) cs.ca.fired = __float_as_uint(entry[4]);
                         // reload geometry and ray so that nothing of them stays live across the fast walk
                         BrickGeom g2;
                         load_geom(g2, br);
@@ -812,7 +812,17 @@ cast_kernel(const __grid_constant__ CastParams p)
     } else if (KIND == KIND_VR) {
         if (tfm_is_colour(TFM)) {
             smp.rgba[0] = smp.ca.c01.x; smp.rgba[1] = smp.ca.c01.y; smp.rgba[2] = smp.ca.c2; smp.rgba[3] = smp.ca.c3;
-            smp.B[0] = smp.ca.b01.x; smp.B[1] = smp.ca.b01.y; smp.B[2] = smp.ca.b2; smp.B[3] = smp.ca.b3;
+            // transmittance of the partial: B = 1 - A unless a clamp fired for the channel (see ColourAcc)
+            const unsigned fz = smp.ca.fired;
+            if (tfm_grey(TFM)) {
+                const float b = (fz & 1u) ? 0.f : 1.f - smp.ca.c3;
+                smp.B[0] = smp.B[1] = smp.B[2] = smp.B[3] = b;
+            } else {
+                smp.B[0] = (fz & 1u) ? 0.f : 1.f - smp.ca.c01.x;
+                smp.B[1] = (fz & 2u) ? 0.f : 1.f - smp.ca.c01.y;
+                smp.B[2] = (fz & 4u) ? 0.f : 1.f - smp.ca.c2;
+                smp.B[3] = 1.f;
+            }
         }
 #pragma unroll
         for (int c = 0; c < 4; c++) { out[c] = (double)smp.rgba[c]; Bout[c] = (double)smp.B[c]; }

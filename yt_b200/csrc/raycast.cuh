@@ -447,10 +447,15 @@ __device__ __forceinline__ bool rows_from_raw(CornersP &c, const RawCorners &r, 
     return (bits << 1) == 0u;
 }
 
-// Accumulators of one ray on the ColorTransferFunction path: colour C and (PARTIAL) transmittance B.
+// Accumulators of one ray on the ColorTransferFunction path.  For an affine partial (PARTIAL: C -> A + B*C, the
+// accumulators start at A = 0, B = 1) the transmittance needs no arithmetic of its own: each step is
+// A <- e + a*A, B <- a*B with a = max(1 - e, 0), and while no clamp has fired a = 1 - e gives 1 - A' = (1 - e)(1 - A),
+// i.e. B = 1 - A at every step (per channel; grey: B = 1 - A_alpha for all four).  A clamp that fires (e > 1) zeroes B
+// for good; `fired` keeps one sticky bit per channel for that.  (Tracking B explicitly cost 2 of 35 instructions per
+// sample and 4 registers in the multi-GPU casts.)
 struct ColourAcc {
     float2 c01; float c2, c3;
-    float2 b01; float b2, b3;
+    unsigned fired;
 };
 
 // All n_samples samples of one cell: trilinear value -> 4-table lookup -> composite
@@ -501,18 +506,22 @@ __device__ __forceinline__ float colour_cell_run(const CornersP &c, const Colour
         const float e2 = ba.x * adt;
         if (GREY) {
             float ta = 1.f - adt;
-            if (CLAMP) ta = fmaxf(ta, 0.f);
+            if (CLAMP) {
+                if (PARTIAL && ta < 0.f) A.fired |= 15u;
+                ta = fmaxf(ta, 0.f);
+            }
             A.c01 = fma2(bcast2(ta), A.c01, e01);
             A.c2 = fmaf(ta, A.c2, e2);
             A.c3 = fmaf(ta, A.c3, adt);
-            if (PARTIAL) { A.b01 = mul2(A.b01, bcast2(ta)); A.b2 *= ta; A.b3 *= ta; }
         } else {
             float2 a01 = fma2(e01, neg1, one2);
             float a2 = 1.f - e2;
-            if (CLAMP) { a01.x = fmaxf(a01.x, 0.f); a01.y = fmaxf(a01.y, 0.f); a2 = fmaxf(a2, 0.f); }
+            if (CLAMP) {
+                if (PARTIAL) A.fired |= (a01.x < 0.f ? 1u : 0u) | (a01.y < 0.f ? 2u : 0u) | (a2 < 0.f ? 4u : 0u);
+                a01.x = fmaxf(a01.x, 0.f); a01.y = fmaxf(a01.y, 0.f); a2 = fmaxf(a2, 0.f);
+            }
             A.c01 = fma2(a01, A.c01, e01);
             A.c2 = fmaf(a2, A.c2, e2);
-            if (PARTIAL) { A.b01 = mul2(A.b01, a01); A.b2 *= a2; }
         }
     };
 #if defined(YTB_TRILINEAR_STEP)
@@ -582,13 +591,13 @@ __device__ __forceinline__ void colour_sample(const ColourTable &ct, float fs, f
     const float adt = fmaf(fr, t1.w, t0.w) * dt;
     const float e0 = r * adt, e1 = g * adt, e2 = b * adt;
     if (GREY) {
+        if (PARTIAL && 1.f - adt < 0.f) A.fired |= 15u;
         const float ta = fmaxf(1.f - adt, 0.f);
         A.c01.x = fmaf(ta, A.c01.x, e0); A.c01.y = fmaf(ta, A.c01.y, e1); A.c2 = fmaf(ta, A.c2, e2); A.c3 = fmaf(ta, A.c3, adt);
-        if (PARTIAL) { A.b01.x *= ta; A.b01.y *= ta; A.b2 *= ta; A.b3 *= ta; }
     } else {
+        if (PARTIAL) A.fired |= (1.f - e0 < 0.f ? 1u : 0u) | (1.f - e1 < 0.f ? 2u : 0u) | (1.f - e2 < 0.f ? 4u : 0u);
         const float a0 = fmaxf(1.f - e0, 0.f), a1 = fmaxf(1.f - e1, 0.f), a2 = fmaxf(1.f - e2, 0.f);
         A.c01.x = fmaf(a0, A.c01.x, e0); A.c01.y = fmaf(a1, A.c01.y, e1); A.c2 = fmaf(a2, A.c2, e2);
-        if (PARTIAL) { A.b01.x *= a0; A.b01.y *= a1; A.b2 *= a2; }
     }
 }
 
