@@ -163,3 +163,29 @@ def test_off_axis_projection_matches_oracle(weight, gpu):
     scale = np.abs(want).max()
     assert scale > 0
     assert np.abs(got - want).max() / scale <= 1e-6
+
+
+@pytest.mark.parametrize("lens", ["plane-parallel", "perspective"])
+@pytest.mark.parametrize("grey", [False, True])
+def test_oversized_leaves_are_cut_into_pieces(lens, grey, gpu, monkeypatch):
+    """A leaf with more elements than 32-bit offsets allow is cut into cell-aligned pieces that are cast in
+    increasing t (amr_kdtree.split_box / view_order): same image as the uncut leaf and as the oracle."""
+    from yt_b200 import amr_kdtree
+    arr = np.random.default_rng(21).random((24, 20, 28)) + 0.2
+    images = {}
+    for limit in (2 ** 31, 1500):
+        monkeypatch.setattr(amr_kdtree, "MAX_BRICK_ELEMS", limit)
+        ds = yt.load_uniform_grid({"density": arr}, arr.shape)
+        sc = yt.create_scene(ds, lens_type=lens)
+        sc.camera.resolution = (80, 72)
+        if lens == "perspective":
+            sc.camera.position = [1.9, 1.3, 1.6]
+            sc.camera.width = [0.8, 0.8, 1.0]
+        sc.get_source().tfh.grey_opacity = grey
+        images[limit] = np.array(sc.render())
+        if limit == 1500:
+            vol = sc.get_source().volume
+            assert len(vol._piece_plan) == 1 and vol.device_bricks(sc.get_source().sampler._ctx, sc.get_source().sampler._storage).n >= 8
+            want, _ = oracle_render(sc)
+    assert T.normalised_diff(images[1500], images[2 ** 31], grey) <= 2e-5
+    assert T.normalised_diff(images[1500], want, grey) <= 1e-4

@@ -15,6 +15,32 @@ from . import _lib as L
 from .partitioned_grid import PartitionedGrid, build_brickset
 
 
+#: the kernels follow a ray with 32-bit running offsets: a leaf with more stored elements than this is cut into
+#: cell-aligned pieces (which reproduce the single-brick image when composited in increasing t -- SURVEY.md finding 6)
+MAX_BRICK_ELEMS = 2 ** 31
+
+
+def split_box(lo, hi, max_elems):
+    """kd bisection (longest axis, cell boundary) of the vertex box lo..hi until every piece stores <= max_elems
+    vertices.  Returns a tree: ("leaf", lo, hi) | ("split", axis, cut_index, lower, upper)."""
+    lo, hi = [int(v) for v in lo], [int(v) for v in hi]
+    ext = [hi[a] - lo[a] for a in range(3)]
+    if float(np.prod([e + 1 for e in ext])) <= max_elems or max(ext) <= 1:
+        return ("leaf", lo, hi)
+    ax = int(np.argmax(ext))
+    mid = lo[ax] + ext[ax] // 2
+    lower_hi, upper_lo = list(hi), list(lo)
+    lower_hi[ax] = mid
+    upper_lo[ax] = mid
+    return ("split", ax, mid, split_box(lo, lower_hi, max_elems), split_box(upper_lo, hi, max_elems))
+
+
+def _tree_leaves(tree):
+    if tree[0] == "leaf":
+        return [tree]
+    return _tree_leaves(tree[3]) + _tree_leaves(tree[4])
+
+
 class Tree:
     """Native kd-tree handle; ``build()`` adds the grids level by level (amr_kdtree.py:110-118)."""
 
@@ -215,10 +241,43 @@ class AMRKDTree:
         if not self.no_ghost:
             raise NotImplementedError("ghost-zone vertex centring is not on the device path")
         nd = self.tree.nodes
-        out = D.BrickSet(ctx, len(leaves), len(self.fields), L.VERTEX_CENTRED, storage)
-        cells_of_grid = {}
-        for slot, node in enumerate(leaves):
+        # leaves too large for 32-bit offsets become several device bricks (pieces of ONE reference brick)
+        plans, n_slots = [], 0
+        for node in leaves:
             grid = self.ds.index.grids[nd["grid"][node] - self._id_offset]
+            li = np.rint((nd["left_edge"][node] - grid.LeftEdge) / grid.dds).astype("int64")
+            ri = np.rint((nd["right_edge"][node] - grid.LeftEdge) / grid.dds).astype("int64")
+            tree = split_box(li, ri, MAX_BRICK_ELEMS)
+            pieces = _tree_leaves(tree)
+            plans.append((node, grid, tree, pieces, n_slots))
+            n_slots += len(pieces)
+        self._piece_plan = {}
+        if n_slots != len(leaves):
+            slot_of = {}
+            for node, grid, tree, pieces, first in plans:
+                for k, pc in enumerate(pieces):
+                    slot_of[id(pc)] = first + k
+                if len(pieces) > 1:
+                    self._piece_plan[node] = (tree, grid, slot_of)
+                self._leaf_slot[node] = first
+        out = D.BrickSet(ctx, n_slots, len(self.fields), L.VERTEX_CENTRED, storage)
+        cells_of_grid = {}
+        for node, grid, tree, pieces, first in plans:
+            if len(pieces) > 1:
+                if grid.id not in cells_of_grid:
+                    cells_of_grid[grid.id] = [D.DeviceCells(ctx, grid[f]) for f in self.fields]
+                for k, (_, plo, phi) in enumerate(pieces):
+                    ple = grid.LeftEdge + np.array(plo) * grid.dds
+                    pre = grid.LeftEdge + np.array(phi) * grid.dds
+                    mask = None
+                    if self.data_source.selector is not None:
+                        mask, _ = self.data_source.selector.fill_mask_regular_grid(grid)
+                        mask = mask[plo[0]:phi[0], plo[1]:phi[1], plo[2]:phi[2]].astype("uint8")
+                    out.from_cells(first + k, [c.ptr for c in cells_of_grid[grid.id]], grid.ActiveDimensions, plo, phi, ple, pre,
+                                   log_fields=self.log_fields, mask=mask)
+        for node, grid, tree, pieces, slot in plans:
+            if len(pieces) > 1:
+                continue
             if grid.id not in cells_of_grid:
                 if np.any(np.asarray(grid.ActiveDimensions) < 2):
                     raise NotImplementedError("no-ghost vertex centring needs >= 2 cells per grid axis")
@@ -237,11 +296,43 @@ class AMRKDTree:
         ctx.synchronize()   # the cell arrays may be released once every leaf has been centred
         return out.commit()
 
-    def view_order(self, viewpoint):
-        """Positions in the device brick table, back to front w.r.t. ``viewpoint``."""
+    def view_order(self, viewpoint, camera=None):
+        """Positions in the device brick table, in the order ``traverse(viewpoint)`` yields the leaves.  A leaf that
+        was cut into pieces expands to its pieces in increasing ray parameter t (what walk_volume does inside ONE
+        brick): along the ray direction for a plane-parallel lens, away from the common ray origin
+        (the camera position) otherwise."""
         if self._leaf_slot is None:
             raise RuntimeError("device_bricks() must be called first")
-        return self._leaf_slot[self.tree.traverse(viewpoint)]
+        leaves = self.tree.traverse(viewpoint)
+        plan = getattr(self, "_piece_plan", None)
+        if not plan:
+            return self._leaf_slot[leaves]
+        if camera is not None and camera.lens.lens_type == "plane-parallel":
+            direction = np.asarray(camera.unit_vectors[2], dtype="float64") * float(camera.width[2])
+            lower_first = lambda grid, ax, cut: direction[ax] >= 0          # noqa: E731
+        else:
+            origin = np.asarray(camera.position if camera is not None else viewpoint, dtype="float64")
+            if camera is None:   # only the kd viewpoint is known: its far side first, like the tree itself
+                lower_first = lambda grid, ax, cut: not (origin[ax] <= grid.LeftEdge[ax] + cut * grid.dds[ax])   # noqa: E731
+            else:
+                lower_first = lambda grid, ax, cut: origin[ax] < grid.LeftEdge[ax] + cut * grid.dds[ax]          # noqa: E731
+        out = []
+        for node in leaves:
+            node = int(node)
+            if node not in plan:
+                out.append(int(self._leaf_slot[node]))
+                continue
+            tree, grid, slot_of = plan[node]
+
+            def walk(t):
+                if t[0] == "leaf":
+                    out.append(slot_of[id(t)])
+                    return
+                first, second = (t[3], t[4]) if lower_first(grid, t[1], t[2]) else (t[4], t[3])
+                walk(first)
+                walk(second)
+            walk(tree)
+        return np.asarray(out, dtype="int64")
 
     # -- parallel reduction -------------------------------------------------------------------------------
     def reduce_tree_images(self, image, viewpoint, *, use_opacity=True):

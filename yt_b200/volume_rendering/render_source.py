@@ -278,7 +278,7 @@ class KDTreeVolumeSource(VolumeSource):
             nx, ny = camera.resolution
             if len(self.volume.tree.traverse()) > 0:
                 bricks = self.volume.device_bricks(self.sampler._ctx, self.sampler._storage)
-                self.sampler.cast_bricks(bricks, self.volume.view_order(camera.lens.viewpoint))
+                self.sampler.cast_bricks(bricks, self.volume.view_order(camera.lens.viewpoint, camera))
             if os.environ.get("YTB200_SWAP", "peer") == "nccl":
                 swap = BinarySwap(self.sampler._ctx, nx, ny, self.volume.kd_path(), camera.lens.viewpoint,
                                   self.volume.comm_rank, self.volume.comm_size)
@@ -288,7 +288,7 @@ class KDTreeVolumeSource(VolumeSource):
             self.sampler.flush_parallel(swap, broadcast=True)
         elif self.batched:
             bricks = self.volume.device_bricks(self.sampler._ctx, self.sampler._storage)
-            self.sampler.cast_bricks(bricks, self.volume.view_order(camera.lens.viewpoint))
+            self.sampler.cast_bricks(bricks, self.volume.view_order(camera.lens.viewpoint, camera))
         else:
             for brick in self.volume.traverse(camera.lens.viewpoint):
                 self.sampler(brick, num_threads=self.num_threads)
