@@ -319,10 +319,13 @@ def run_ours(args):
             bricks = D.BrickSet(ctx, len(pieces), 1, L.VERTEX_CENTRED if kind == "vr" else L.CELL_CENTRED, L.STORE_F32)
             my_elems = 0.0
             for i, (plo, phi) in enumerate(pieces):
-                vol = synthetic.vertex_slab(n, plo, phi, SEED, dev) if kind == "vr" else synthetic.cell_slab(n, plo, phi, SEED, dev)
+                if kind == "vr":
+                    vol, pitch = synthetic.vertex_slab(n, plo, phi, SEED, dev), None
+                else:
+                    vol, pitch = synthetic.cell_slab(n, plo, phi, SEED, dev)   # rows padded off the 4096-byte stride
                 my_elems += float(vol.numel())
                 bricks.attach(i, [vol.data_ptr()], 0, [plo[a] / n for a in range(3)], [phi[a] / n for a in range(3)],
-                              [phi[a] - plo[a] for a in range(3)], keep=vol)
+                              [phi[a] - plo[a] for a in range(3)], keep=vol, row_pitch=pitch)
             bricks.commit()
             order = np.arange(len(pieces), dtype=np.int64)
             n_bricks = len(pieces)

@@ -96,6 +96,16 @@ int ytb200_brick_upload(ytb200_brickset *set, int64_t index, const int64_t dims[
 /* Same, but data[f] / mask are DEVICE pointers already in the set's storage type; not copied, not owned. */
 int ytb200_brick_attach(ytb200_brickset *set, int64_t index, const int64_t dims[3], const double left_edge[3],
                         const double right_edge[3], const void *const *dev_data, const uint8_t *dev_mask);
+/* As ytb200_brick_attach, for device arrays whose z-rows are `row_pitch` elements apart (>= the row length; the plane
+ * pitch is rows-per-plane * row_pitch).  Arrays the library allocates itself (brick_upload, brick_from_cells) pad a
+ * row whose byte length is a multiple of 256 B by one 32-byte sector: power-of-two row strides put all rows a ray
+ * packet touches into the same L1 sets (1024^3 fp32 cells cast 24 % slower than 1032-pitched ones). */
+int ytb200_brick_attach_pitched(ytb200_brickset *set, int64_t index, const int64_t dims[3], const double left_edge[3],
+                                const double right_edge[3], const void *const *dev_data, const uint8_t *dev_mask,
+                                int64_t row_pitch);
+/* Element strides of brick `index`'s data arrays (plane pitch, row pitch). */
+int ytb200_brick_pitch(const ytb200_brickset *set, int64_t index, int64_t *plane_pitch, int64_t *row_pitch);
+
 /* ---- vertex centring on the device (replaces the host passes that feed PartitionedGrid) -------
  * grid.get_vertex_centered_data(fields, no_ghost=True)  grid_patch.py:270-296 -> ghost_zone_interpolate,
  *                                                       interpolators.pyx:177-227 (rf=1, input_left=0.5)

@@ -63,9 +63,17 @@ def _device_brick(cells, lo, hi, take_log, storage, cells_f32=False):
     bs.commit()
     ctx.synchronize()
     shape = tuple(int(h - l + 1) for l, h in zip(lo, hi))
-    ptrs, _ = bs.device_ptrs(0)
-    arr = torch.as_tensor(_DevArray(ptrs[0], shape, "<f8" if storage == "f64" else "<f4"), device="cuda:%d" % ctx.device)
-    return arr.cpu().numpy().copy()
+    return read_brick(bs, 0, shape, storage, ctx)
+
+
+def read_brick(bs, index, shape, storage, ctx):
+    """Device array of a brick as a contiguous numpy array (library-owned arrays may have padded rows)."""
+    import torch
+    from yt_b200.parallel import _DevArray
+    ptrs, _ = bs.device_ptrs(index)
+    _, row = bs.pitch(index)
+    arr = torch.as_tensor(_DevArray(ptrs[0], (shape[0], shape[1], row), "<f8" if storage == "f64" else "<f4"), device="cuda:%d" % ctx.device)
+    return arr[:, :, :shape[2]].cpu().numpy().copy()
 
 
 @pytest.mark.gpu
@@ -106,6 +114,17 @@ def test_device_vertex_centring_from_fp32_cells(gpu):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("storage", ["f32", "f64"])
+def test_rows_of_a_multiple_of_256_bytes_are_padded(gpu, storage):
+    """63 cells -> 64 vertices per row = 256 B (fp32) / 512 B (fp64): the library pads the row by one sector and the
+    values are unchanged."""
+    cells = cells_for((5, 6, 63), 13)
+    want = O.vertex_centre(cells)
+    got = _device_brick(cells, (0, 0, 0), cells.shape, False, storage)
+    assert np.array_equal(got, want.astype("float32") if storage == "f32" else want)
+
+
+@pytest.mark.gpu
 def test_one_cell_axis_is_refused(gpu):
     from yt_b200 import _lib as L
     with pytest.raises(L.YTB200Error, match="2 cells"):
@@ -132,8 +151,7 @@ def test_kdtree_device_route_equals_host_route(gpu):
     assert dev.n == len(leaves) > 8
     for slot in (0, 1, len(leaves) // 2, len(leaves) - 1):
         host = kd.get_brick_data(leaves[slot]).my_data[0]
-        ptrs, _ = dev.device_ptrs(slot)
-        got = torch.as_tensor(_DevArray(ptrs[0], host.shape, "<f8"), device="cuda:%d" % ctx.device).cpu().numpy()
+        got = read_brick(dev, slot, host.shape, "f64", ctx)
         assert np.array_equal(np.isnan(got), np.isnan(host))
         ok = ~np.isnan(host)
         assert np.allclose(got[ok], host[ok], rtol=1e-14, atol=1e-14)

@@ -59,6 +59,8 @@ SIGNATURES = {
     "ytb200_cells_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ytb200_brick_from_cells": (C.c_int, [C.c_void_p, C.c_int64, i64p, i64p, i64p, dp, dp, C.POINTER(C.c_void_p), C.c_int,
                                           i32p, u8p, C.POINTER(Stats)]),
+    "ytb200_brick_attach_pitched": (C.c_int, [C.c_void_p, C.c_int64, i64p, dp, dp, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64]),
+    "ytb200_brick_pitch": (C.c_int, [C.c_void_p, C.c_int64, i64p, i64p]),
     "ytb200_bricks_commit": (C.c_int, [C.c_void_p]),
     "ytb200_bricks_destroy": (C.c_int, [C.c_void_p]),
     "ytb200_brick_device_ptrs": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
@@ -121,6 +123,8 @@ def load():
                 "(nvcc, sm_100a).  yt_b200 has no CPU fallback.")
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if os.environ.get("YTB200_LIB") and not hasattr(lib, name):
+                continue   # kernel-experiment builds of an older source may lack newer entry points
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args

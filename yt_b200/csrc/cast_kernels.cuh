@@ -84,7 +84,7 @@ struct ExactSampler {
         const int ix = cur[0], iy = cur[1], iz = cur[2];
         if (KIND == KIND_PROJ) {
             const double dl = dsub(exit_t, enter_t);
-            const size_t di = ((size_t)ix * ny + iy) * nz + iz;
+            const size_t di = (size_t)ix * br->pitch_x + (size_t)iy * br->pitch_y + iz;
             const int nf = n_fields < 4 ? n_fields : 4;
 #pragma unroll
             for (int f = 0; f < 4; f++)
@@ -94,7 +94,7 @@ struct ExactSampler {
         if (KIND == KIND_VR && MASKED) {
             if (mask[((size_t)ix * ny + iy) * nz + iz] != 1) return;
         }
-        const int sy = nz + 1, sx = (ny + 1) * (nz + 1);
+        const int sy = br->pitch_y, sx = br->pitch_x;
         const size_t offset = (size_t)ix * sx + (size_t)iy * sy + iz;
         double dp[3], ds[3], dvs[6];
         const double dt = ddiv(dsub(exit_t, enter_t), (double)n_samples);
@@ -162,7 +162,7 @@ struct CarefulSampler {
         if (MASKED) {
             if (br->mask[((size_t)cur[0] * ny + cur[1]) * nz + cur[2]] != 1) return;
         }
-        const int sy = nz + 1, sx = (ny + 1) * (nz + 1);
+        const int sy = br->pitch_y, sx = br->pitch_x;
         const T *d = (const T *)br->data[0] + ((size_t)cur[0] * sx + (size_t)cur[1] * sy + cur[2]);
         const double c000 = (double)__ldg(d), c001 = (double)__ldg(d + 1), c010 = (double)__ldg(d + sy), c011 = (double)__ldg(d + sy + 1);
         const double c100 = (double)__ldg(d + sx), c101 = (double)__ldg(d + sx + 1), c110 = (double)__ldg(d + sx + sy), c111 = (double)__ldg(d + sx + sy + 1);
@@ -243,10 +243,8 @@ struct FastSampler {
     __device__ __forceinline__ void begin(const int (&c)[3], const int (&s)[3])
     {
         const int ny = br->dims[1], nz = br->dims[2];
-        if (KIND == KIND_PROJ) {
-            sx = ny * nz; sy = nz;
-        } else {
-            sx = (ny + 1) * (nz + 1); sy = nz + 1;
+        sx = br->pitch_x; sy = br->pitch_y;
+        if (KIND != KIND_PROJ) {
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 const double idds = br->idds[i];
@@ -295,7 +293,9 @@ struct FastSampler {
     __device__ __forceinline__ void walk_colour(const WalkState &w)
     {
         const int ny = br->dims[1], nz = br->dims[2];
-        const int vsx = (ny + 1) * (nz + 1), vsy = nz + 1;
+        // (plane pitch = rows per plane * row pitch by construction; written this way the compiler keeps the relation
+        // between the two strides -- loading both cost 3 % of the north-star frame)
+        const int vsy = br->pitch_y, vsx = (ny + 1) * vsy;
         float dcx[3], bse[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
@@ -424,9 +424,9 @@ struct FastSampler {
     template <int NF, int DEPTH>
     __device__ __forceinline__ void walk_proj(const WalkState &w)
     {
-        const int ny = br->dims[1], nz = br->dims[2];
-        unsigned o = ((unsigned)w.cur[0] * (unsigned)ny + (unsigned)w.cur[1]) * (unsigned)nz + (unsigned)w.cur[2];
-        const int st0 = w.step[0] * ny * nz, st1 = w.step[1] * nz, st2 = w.step[2];
+        const int px = br->pitch_x, py = br->pitch_y;
+        unsigned o = (unsigned)w.cur[0] * (unsigned)px + (unsigned)w.cur[1] * (unsigned)py + (unsigned)w.cur[2];
+        const int st0 = w.step[0] * px, st1 = w.step[1] * py, st2 = w.step[2];
         double t0 = w.t0, t1 = w.t1, t2 = w.t2;
         const double d0 = w.d0, d1 = w.d1, d2 = w.d2, max_t = w.max_t;
         int rem0 = w.rem0, rem1 = w.rem1, rem2 = w.rem2;
@@ -1020,7 +1020,7 @@ constexpr int VC_THREADS = 128, VC_ZSPAN = VC_THREADS, VC_XCHUNK = 32;
 template <typename TIN, typename TOUT>
 __global__ void __launch_bounds__(VC_THREADS) vertex_centre_kernel(const TIN *__restrict__ cells, TOUT *__restrict__ out,
                                                                     int nx, int ny, int nz, int lo0, int lo1, int lo2,
-                                                                    int m0, int m1, int m2, int take_log)
+                                                                    int m0, int m1, int m2, int take_log, int out_px, int out_py)
 {
     const int oz = blockIdx.x * VC_THREADS + threadIdx.x;
     const int oy = blockIdx.y;
@@ -1031,8 +1031,8 @@ __global__ void __launch_bounds__(VC_THREADS) vertex_centre_kernel(const TIN *__
     const size_t sx = (size_t)ny * nz;
     // cell (x = 0, gy - 1, gz - 1) of this column; only dereferenced when col_ok
     const TIN *col = cells + (col_ok ? (size_t)(gy - 1) * nz + (size_t)(gz - 1) : 0);
-    TOUT *dst = out + ((size_t)ox0 * m1 + oy) * m2 + oz;
-    const size_t dstep = (size_t)m1 * m2;
+    TOUT *dst = out + (size_t)ox0 * out_px + (size_t)oy * out_py + oz;
+    const size_t dstep = (size_t)out_px;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     double a0m = 0.0, a0 = 0.0, b0m = 0.0, b0 = 0.0;
     int gx = lo0 + ox0;
@@ -1135,6 +1135,16 @@ __global__ void f64_to_f32_kernel(const double *src, float *dst, long long n)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (float)src[i];
+}
+
+// host fp64 rows (contiguous, `row` elements each) -> device rows with pitch `pitch`, converted to TOUT
+template <typename TOUT>
+__global__ void repitch_kernel(const double *src, TOUT *dst, long long n, int row, int pitch, long long first_row)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long r = i / row;
+    dst[(first_row + r) * pitch + (i - r * row)] = (TOUT)src[i];
 }
 
 __global__ void fill_f64_kernel(double *dst, double v, long long n)

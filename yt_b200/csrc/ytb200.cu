@@ -185,7 +185,28 @@ static int fill_geometry(ytb200_brickset *s, int64_t index, const int64_t dims[3
         return fail(E_UNSUPPORTED, "brick %lld has %.3g elements per field; split it on cell boundaries below 2^32 "
                     "(sub-bricks reproduce the single-brick image, SURVEY.md finding 6)", (long long)index, nelem);
     b.n_fields = s->n_fields;
+    const int c = s->centring == YTB200_VERTEX_CENTRED ? 1 : 0;
+    b.pitch_y = (int)dims[2] + c;
+    b.pitch_x = ((int)dims[1] + c) * b.pitch_y;
     s->committed = false;
+    return 0;
+}
+
+// Row pitch (elements) for an array the library allocates itself: rows whose byte length is a multiple of 256 B are
+// padded by one 32-byte sector (see DevBrick::pitch_y).
+static int padded_row(int row_elems, size_t elem_bytes)
+{
+    if (((size_t)row_elems * elem_bytes) % 256 == 0) return row_elems + (int)(32 / elem_bytes);
+    return row_elems;
+}
+
+static int set_pitch(ytb200_brickset *s, DevBrick &b, int pitch_y, int64_t index)
+{
+    const int c = s->centring == YTB200_VERTEX_CENTRED ? 1 : 0;
+    const double total = ((double)b.dims[0] + c) * ((double)b.dims[1] + c) * (double)pitch_y;
+    if (total >= 4294967296.0) return fail(E_UNSUPPORTED, "brick %lld has %.3g stored elements per field (>= 2^32)", (long long)index, total);
+    b.pitch_y = pitch_y;
+    b.pitch_x = (b.dims[1] + c) * pitch_y;
     return 0;
 }
 
@@ -198,29 +219,35 @@ extern "C" int ytb200_brick_upload(ytb200_brickset *s, int64_t index, const int6
     DeviceGuard g(s->ctx->device);
     cudaStream_t st = s->ctx->stream;
     const int c = s->centring == YTB200_VERTEX_CENTRED ? 1 : 0;
-    const size_t nelem = (size_t)(dims[0] + c) * (size_t)(dims[1] + c) * (size_t)(dims[2] + c);
     const size_t ncell = (size_t)dims[0] * (size_t)dims[1] * (size_t)dims[2];
     DevBrick &b = s->host[(size_t)index];
-    const size_t chunk = (size_t)1 << 24;  // 16 Mi elements = 128 MiB fp64 staging
+    const size_t esz = s->storage == YTB200_STORE_F64 ? sizeof(double) : sizeof(float);
+    const int row = (int)dims[2] + c;
+    rc = set_pitch(s, b, padded_row(row, esz), index);
+    if (rc) return rc;
+    const int pitch = b.pitch_y;
+    const size_t nrows = (size_t)(dims[0] + c) * (size_t)(dims[1] + c);
+    const size_t nstored = nrows * (size_t)pitch;
+    // staging: whole rows, at most ~16 Mi elements (128 MiB of fp64) per chunk
+    const size_t rows_per_chunk = std::max<size_t>(1, ((size_t)1 << 24) / (size_t)row);
     double *stage = nullptr;
-    if (s->storage == YTB200_STORE_F32) CK(cudaMalloc(&stage, sizeof(double) * (nelem < chunk ? nelem : chunk)));
+    if (s->storage == YTB200_STORE_F32) CK(cudaMalloc(&stage, sizeof(double) * std::min(nrows, rows_per_chunk) * (size_t)row));
     for (int f = 0; f < s->n_fields; f++) {
         if (!data[f]) { cudaFree(stage); return fail(E_ARG, "data[%d] is NULL", f); }
         void *dst = nullptr;
+        CK(cudaMalloc(&dst, nstored * esz));
+        if (pitch != row) CK(cudaMemsetAsync(dst, 0, nstored * esz, st));
         if (s->storage == YTB200_STORE_F64) {
-            CK(cudaMalloc(&dst, nelem * sizeof(double)));
-            CK(cudaMemcpyAsync(dst, data[f], nelem * sizeof(double), cudaMemcpyHostToDevice, st));
-            s->bytes += (int64_t)(nelem * sizeof(double));
+            CK(cudaMemcpy2DAsync(dst, (size_t)pitch * 8, data[f], (size_t)row * 8, (size_t)row * 8, nrows, cudaMemcpyHostToDevice, st));
         } else {
-            CK(cudaMalloc(&dst, nelem * sizeof(float)));
-            for (size_t o = 0; o < nelem; o += chunk) {
-                const size_t m = nelem - o < chunk ? nelem - o : chunk;
-                CK(cudaMemcpyAsync(stage, data[f] + o, m * sizeof(double), cudaMemcpyHostToDevice, st));
-                f64_to_f32_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(stage, (float *)dst + o, (long long)m);
+            for (size_t r0 = 0; r0 < nrows; r0 += rows_per_chunk) {
+                const size_t m = std::min(rows_per_chunk, nrows - r0) * (size_t)row;
+                CK(cudaMemcpyAsync(stage, data[f] + r0 * (size_t)row, m * sizeof(double), cudaMemcpyHostToDevice, st));
+                repitch_kernel<float><<<(unsigned)((m + 255) / 256), 256, 0, st>>>(stage, (float *)dst, (long long)m, row, pitch, (long long)r0);
                 CK(cudaGetLastError());
             }
-            s->bytes += (int64_t)(nelem * sizeof(float));
         }
+        s->bytes += (int64_t)(nstored * esz);
         s->owned.push_back(dst);
         b.data[f] = dst;
     }
@@ -287,7 +314,10 @@ extern "C" int ytb200_brick_from_cells(ytb200_brickset *s, int64_t index, const 
     cudaStream_t st = s->ctx->stream;
     DevBrick &b = s->host[(size_t)index];
     const int m0 = (int)dims[0] + 1, m1 = (int)dims[1] + 1, m2 = (int)dims[2] + 1;
-    const size_t nelem = (size_t)m0 * (size_t)m1 * (size_t)m2;
+    rc = set_pitch(s, b, padded_row(m2, s->storage == YTB200_STORE_F64 ? 8 : 4), index);
+    if (rc) return rc;
+    const int opy = b.pitch_y, opx = b.pitch_x;
+    const size_t nelem = (size_t)m0 * (size_t)opx;
     const size_t ncell = (size_t)dims[0] * (size_t)dims[1] * (size_t)dims[2];
     if (m1 > 65535 || (m0 + VC_XCHUNK - 1) / VC_XCHUNK > 65535) return fail(E_UNSUPPORTED, "brick too large for one centring launch");
     const dim3 grid((unsigned)((m2 + VC_ZSPAN - 1) / VC_ZSPAN), (unsigned)m1, (unsigned)((m0 + VC_XCHUNK - 1) / VC_XCHUNK));
@@ -298,16 +328,17 @@ extern "C" int ytb200_brick_from_cells(ytb200_brickset *s, int64_t index, const 
         const bool f64 = s->storage == YTB200_STORE_F64;
         void *dst = nullptr;
         CK(cudaMalloc(&dst, nelem * (f64 ? sizeof(double) : sizeof(float))));
+        if (opy != m2) CK(cudaMemsetAsync(dst, 0, nelem * (f64 ? sizeof(double) : sizeof(float)), st));
         s->owned.push_back(dst);
         s->bytes += (int64_t)(nelem * (f64 ? 8 : 4));
         const int nx = (int)grid_dims[0], ny = (int)grid_dims[1], nz = (int)grid_dims[2];
         const int l0 = (int)lo[0], l1 = (int)lo[1], l2 = (int)lo[2];
         if (cells_are_f32) {
-            if (f64) vertex_centre_kernel<float, double><<<grid, VC_THREADS, 0, st>>>((const float *)cells_dev[f], (double *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg);
-            else vertex_centre_kernel<float, float><<<grid, VC_THREADS, 0, st>>>((const float *)cells_dev[f], (float *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg);
+            if (f64) vertex_centre_kernel<float, double><<<grid, VC_THREADS, 0, st>>>((const float *)cells_dev[f], (double *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg, opx, opy);
+            else vertex_centre_kernel<float, float><<<grid, VC_THREADS, 0, st>>>((const float *)cells_dev[f], (float *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg, opx, opy);
         } else {
-            if (f64) vertex_centre_kernel<double, double><<<grid, VC_THREADS, 0, st>>>((const double *)cells_dev[f], (double *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg);
-            else vertex_centre_kernel<double, float><<<grid, VC_THREADS, 0, st>>>((const double *)cells_dev[f], (float *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg);
+            if (f64) vertex_centre_kernel<double, double><<<grid, VC_THREADS, 0, st>>>((const double *)cells_dev[f], (double *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg, opx, opy);
+            else vertex_centre_kernel<double, float><<<grid, VC_THREADS, 0, st>>>((const double *)cells_dev[f], (float *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg, opx, opy);
         }
         CK(cudaGetLastError());
         b.data[f] = dst;
@@ -353,6 +384,26 @@ extern "C" int ytb200_brick_attach(ytb200_brickset *s, int64_t index, const int6
     }
     b.mask = dev_mask;
     if (dev_mask) s->any_mask = true;
+    return 0;
+}
+
+extern "C" int ytb200_brick_attach_pitched(ytb200_brickset *s, int64_t index, const int64_t dims[3], const double le[3],
+                                           const double re[3], const void *const *dev_data, const uint8_t *dev_mask,
+                                           int64_t row_pitch)
+{
+    int rc = ytb200_brick_attach(s, index, dims, le, re, dev_data, dev_mask);
+    if (rc) return rc;
+    const int c = s->centring == YTB200_VERTEX_CENTRED ? 1 : 0;
+    if (row_pitch < dims[2] + c || row_pitch > 0x7fffffff) return fail(E_ARG, "row_pitch %lld shorter than a row", (long long)row_pitch);
+    return set_pitch(s, s->host[(size_t)index], (int)row_pitch, index);
+}
+
+extern "C" int ytb200_brick_pitch(const ytb200_brickset *s, int64_t index, int64_t *plane_pitch, int64_t *row_pitch)
+{
+    if (!s || !plane_pitch || !row_pitch) return fail(E_ARG, "NULL argument");
+    if (index < 0 || index >= s->n) return fail(E_ARG, "brick index %lld out of range", (long long)index);
+    *plane_pitch = s->host[(size_t)index].pitch_x;
+    *row_pitch = s->host[(size_t)index].pitch_y;
     return 0;
 }
 

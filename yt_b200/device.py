@@ -139,14 +139,20 @@ class BrickSet:
             self._keep.append(keep)
         return st
 
-    def attach(self, index, dev_ptrs, dev_mask, left_edge, right_edge, dims, keep=None):
-        """Borrow device arrays (already in this set's storage type); `keep` is kept alive."""
+    def attach(self, index, dev_ptrs, dev_mask, left_edge, right_edge, dims, keep=None, row_pitch=None):
+        """Borrow device arrays (already in this set's storage type); `keep` is kept alive.  ``row_pitch``: elements
+        between consecutive z-rows when the arrays are padded (default: contiguous)."""
         dims = np.ascontiguousarray(dims, dtype=np.int64)
         ptrs = (C.c_void_p * self.n_fields)(*[C.c_void_p(int(p)) for p in dev_ptrs])
         le, re = _f64(left_edge), _f64(right_edge)
-        L.check(L.load().ytb200_brick_attach(
-            self.handle, int(index), dims.ctypes.data_as(L.i64p), _dptr(le), _dptr(re), ptrs,
-            C.c_void_p(int(dev_mask)) if dev_mask else None))
+        if row_pitch is None:
+            L.check(L.load().ytb200_brick_attach(
+                self.handle, int(index), dims.ctypes.data_as(L.i64p), _dptr(le), _dptr(re), ptrs,
+                C.c_void_p(int(dev_mask)) if dev_mask else None))
+        else:
+            L.check(L.load().ytb200_brick_attach_pitched(
+                self.handle, int(index), dims.ctypes.data_as(L.i64p), _dptr(le), _dptr(re), ptrs,
+                C.c_void_p(int(dev_mask)) if dev_mask else None, int(row_pitch)))
         if keep is not None:
             self._keep.append(keep)
 
@@ -159,6 +165,12 @@ class BrickSet:
         mask = C.c_void_p()
         L.check(L.load().ytb200_brick_device_ptrs(self.handle, int(index), data, C.byref(mask)))
         return [int(p or 0) for p in data], int(mask.value or 0)
+
+    def pitch(self, index):
+        """(plane pitch, row pitch) of brick `index`'s arrays, in elements."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        L.check(L.load().ytb200_brick_pitch(self.handle, int(index), C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     @property
     def device_bytes(self):

@@ -65,5 +65,5 @@ def build_brickset(bricks, ctx=None, storage=L.STORE_F32):
             raise ValueError("all bricks of a set need the same field count and centring")
         one = b.upload(ctx, storage)
         ptrs, mask = one.device_ptrs(0)
-        out.attach(i, ptrs, mask, b.LeftEdge, b.RightEdge, b.dims, keep=one)
+        out.attach(i, ptrs, mask, b.LeftEdge, b.RightEdge, b.dims, keep=one, row_pitch=one.pitch(0)[1])
     return out.commit()

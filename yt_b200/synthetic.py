@@ -61,10 +61,23 @@ def vertex_slab(n, lo, hi, seed, device):
     return v.contiguous()
 
 
-def cell_slab(n, lo, hi, seed, device):
-    """Cell-centred fp32 block [lo, hi) of the global field (ProjectionSampler input)."""
+def padded_row(row_elems, elem_bytes=4):
+    """Row pitch the library uses for arrays it owns: rows that are a multiple of 256 B get one 32-byte sector of
+    padding (power-of-two row strides thrash the L1 sets, see DevBrick::pitch_y)."""
+    return row_elems + 32 // elem_bytes if (row_elems * elem_bytes) % 256 == 0 else row_elems
+
+
+def cell_slab(n, lo, hi, seed, device, pad=True):
+    """Cell-centred fp32 block [lo, hi) of the global field (ProjectionSampler input).  Returns (tensor, row_pitch):
+    the tensor is a view of shape (hi-lo) whose z-rows are `row_pitch` elements apart."""
+    torch = _torch()
     c = cell_planes(n, int(lo[0]), int(hi[0]), seed, device)
-    return c[:, int(lo[1]):int(hi[1]), int(lo[2]):int(hi[2])].contiguous()
+    c = c[:, int(lo[1]):int(hi[1]), int(lo[2]):int(hi[2])]
+    nz = c.shape[2]
+    pitch = padded_row(nz) if pad else nz
+    out = torch.zeros((c.shape[0], c.shape[1], pitch), dtype=c.dtype, device=c.device)
+    out[:, :, :nz] = c
+    return out[:, :, :nz], pitch
 
 
 def host_cells(n, seed):
