@@ -23,7 +23,8 @@ def oracle_render(sc, camera=None):
         src._volume_valid = True
     params = camera._get_sampler_params(src)
     args = [np.atleast_3d(np.array(params["vp_pos"], dtype="float64")), np.atleast_3d(np.array(params["vp_dir"], dtype="float64")),
-            np.array(params["center"], dtype="float64"), params["bounds"], np.zeros(tuple(camera.resolution) + (4,)),
+            np.zeros(3) if params["center"] is None else np.array(params["center"], dtype="float64"), params["bounds"],
+            np.zeros(tuple(camera.resolution) + (4,)),
             np.array(params["x_vec"], dtype="float64"), np.array(params["y_vec"], dtype="float64"),
             np.array(params["width"], dtype="float64"), "KDTree"]
     kw = {"lens_type": params["lens_type"], "zbuffer": np.ones(tuple(camera.resolution))}

@@ -59,7 +59,8 @@ class ImageSampler:
             raise TypeError("Argument 'volume_method' has incorrect type (expected str)")
         vp_pos = _memview3(vp_pos, "vp_pos")
         vp_dir = _memview3(vp_dir, "vp_dir")
-        center = _ndarray(center, 1, "center")
+        if center is not None:   # FisheyeLens passes None (lens.py:530,559); Cython's typed ndarray arguments accept it
+            center = _ndarray(center, 1, "center")
         image = _ndarray(image, 3, "image")
         x_vec = _ndarray(x_vec, 1, "x_vec")
         y_vec = _ndarray(y_vec, 1, "y_vec")
@@ -118,7 +119,8 @@ class ImageSampler:
             cam.vp_pos_px = p.ctypes.data_as(L.dp)
             cam.vp_dir_px = d.ctypes.data_as(L.dp)
         for i in range(3):
-            cam.center[i], cam.x_vec[i], cam.y_vec[i], cam.width[i] = center[i], x_vec[i], y_vec[i], width[i]
+            cam.center[i] = 0.0 if center is None else center[i]
+            cam.x_vec[i], cam.y_vec[i], cam.width[i] = x_vec[i], y_vec[i], width[i]
         for i in range(4):
             cam.bounds[i] = self.bounds[i]
         if self.camera_data is not None:

@@ -32,7 +32,7 @@ def ensure_code_unit_params(params):
 
 def _common_args(params, render_source):
     return [np.atleast_3d(np.array(params["vp_pos"], dtype="float64")), np.atleast_3d(np.array(params["vp_dir"], dtype="float64")),
-            np.array(params["center"], dtype="float64"), params["bounds"], params["image"],
+            None if params["center"] is None else np.array(params["center"], dtype="float64"), params["bounds"], params["image"],
             np.array(params["x_vec"], dtype="float64"), np.array(params["y_vec"], dtype="float64"),
             np.array(params["width"], dtype="float64"), render_source.volume_method]
 
