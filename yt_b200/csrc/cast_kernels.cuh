@@ -620,11 +620,12 @@ __device__ __forceinline__ void make_ray(const DevCamera &cam, int vi, int vj, d
 }
 
 // walk_volume for the ColorTransferFunction fast path: reference entry logic, then the fused walk
-template <class S>
-__device__ __forceinline__ void cast_colour(const BrickGeom &g, const double (&vp)[3], const double (&vd)[3], double max_t, S &smp, bool masked)
+template <bool HAVE_IV = false, class S>
+__device__ __forceinline__ void cast_colour(const BrickGeom &g, const double (&vp)[3], const double (&vd)[3], double max_t, S &smp, bool masked,
+                                            const double *ivp = nullptr)
 {
     WalkState w;
-    if (!walk_setup(g, vp, vd, max_t, smp, w)) return;
+    if (!walk_setup<HAVE_IV>(g, vp, vd, max_t, smp, w, ivp)) return;
     if (masked) smp.template walk_colour<true>(w);
     else smp.template walk_colour<false>(w);
 }
@@ -632,7 +633,11 @@ __device__ __forceinline__ void cast_colour(const BrickGeom &g, const double (&v
 template <bool EXACT, class A, class B> struct pick_sampler { using type = A; };
 template <class A, class B> struct pick_sampler<false, A, B> { using type = B; };
 
-template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T>
+// MANY: instantiation for long brick lists (AMR: thousands of small bricks per frame; ncu r01z6: 1800 thread-instructions
+// of set-up per (ray, brick) against ~4900 of sampling).  It skips, warp-wide, the bricks whose pixel footprint misses the
+// warp's 4x8 patch, and computes 1 / v_dir once per ray.  A separate instantiation so that the single-brick kernel of the
+// north-star frame keeps its register allocation (an in-place attempt cost it 13 %).
+template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T, bool MANY = false>
 __global__ void __launch_bounds__(CTA_THREADS, (KIND == KIND_PROJ && !EXACT) ? YTB_MIN_BLOCKS_PROJ : YTB_MIN_BLOCKS)
 cast_kernel(const __grid_constant__ CastParams p)
 {
@@ -641,7 +646,8 @@ cast_kernel(const __grid_constant__ CastParams p)
     __shared__ int s_warp_cnt[CTA_THREADS / 32];
     // the rays of this tile, component-major: only needed when a ray enters a brick, so they live here
     // instead of in 12 registers per thread
-    __shared__ double s_ray[6 * CTA_THREADS];
+    __shared__ double s_ray[(MANY ? 9 : 6) * CTA_THREADS];
+    __shared__ int4 s_ext[MANY ? CTA_THREADS : 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -710,6 +716,10 @@ cast_kernel(const __grid_constant__ CastParams p)
         }
 #pragma unroll
         for (int i = 0; i < 3; i++) { s_ray[i * CTA_THREADS + tid] = vp[i]; s_ray[(3 + i) * CTA_THREADS + tid] = vd[i]; }
+        if constexpr (MANY) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) s_ray[(6 + i) * CTA_THREADS + tid] = vd[i] == 0.0 ? 0.0 : ddiv(1.0, vd[i]);   // grid_traversal.pyx:60
+        }
         if constexpr (EXACT) {
 #pragma unroll
             for (int c = 0; c < 4; c++) { smp.acc[c] = init[c]; smp.B64[c] = 1.0; }
@@ -726,12 +736,14 @@ cast_kernel(const __grid_constant__ CastParams p)
 
     // ---- walk the ordered brick list; cull bricks whose pixel footprint misses this tile ----
     const int ti1 = ti0 + TILE_I, tj1 = tj0 + TILE_J;
+    const int wi0 = ti0 + (warp >> 1) * 4, wj0 = tj0 + (warp & 1) * 8;   // this warp's 4x8 pixel patch
     for (int base = 0; base < p.n_order; base += CTA_THREADS) {
         const int k = base + tid;
         bool hit = false;
         int b = -1;
+        int4 e = make_int4(0, 0, 0, 0);
         if (k < p.n_order) {
-            const int4 e = p.extent[k];
+            e = p.extent[k];
             hit = e.x < ti1 && e.y > ti0 && e.z < tj1 && e.w > tj0;
             b = p.order[k];
         }
@@ -745,10 +757,18 @@ cast_kernel(const __grid_constant__ CastParams p)
             if (w < warp) off += cnt;
             total += cnt;
         }
-        if (hit) s_list[off + __popc(m & ((1u << lane) - 1u))] = b;
+        if (hit) {
+            const int slot = off + __popc(m & ((1u << lane) - 1u));
+            s_list[slot] = b;
+            if constexpr (MANY) s_ext[slot] = e;
+        }
         __syncthreads();
         if (active) {
             for (int q = 0; q < total; q++) {
+                if constexpr (MANY) {
+                    const int4 we = s_ext[q];   // warp-uniform: the footprint misses every pixel of this warp
+                    if (!(we.x < wi0 + 4 && we.y > wi0 && we.z < wj0 + 8 && we.w > wj0)) continue;
+                }
                 const DevBrick *br = p.bricks + s_list[q];
                 BrickGeom g;
                 load_geom(g, br);
@@ -781,7 +801,12 @@ cast_kernel(const __grid_constant__ CastParams p)
                         smp.ca = cs.ca;
                     }
                 } else if constexpr (!EXACT && KIND == KIND_VR && tfm_is_colour(TFM)) {
-                    cast_colour(g, vp, vd, max_t, smp, masked);
+                    if constexpr (MANY) {
+                        const double iv[3] = {s_ray[6 * CTA_THREADS + tid], s_ray[7 * CTA_THREADS + tid], s_ray[8 * CTA_THREADS + tid]};
+                        cast_colour<true>(g, vp, vd, max_t, smp, masked, iv);
+                    } else {
+                        cast_colour(g, vp, vd, max_t, smp, masked);
+                    }
                 } else if constexpr (!EXACT && KIND == KIND_PROJ) {
                     // image_samplers.pyx:337-343 sums the first min(4, n_fields) fields
                     WalkState w;

@@ -69,9 +69,10 @@ struct WalkState {
 
 // Everything of walk_volume up to the first sampled cell (grid_traversal.pyx:40-117).  Returns false when
 // the ray does not sample the brick at all; w.hit then holds the return value of walk_volume.
-template <class S>
+// HAVE_IV: 1 / v_dir was computed once per ray by the caller (`ivp`, same expression) instead of once per (ray, brick).
+template <bool HAVE_IV = false, class S>
 __device__ __forceinline__ bool walk_setup(const BrickGeom &g, const double (&vp)[3], const double (&vd)[3],
-                                           double max_t, S &smp, WalkState &w)
+                                           double max_t, S &smp, WalkState &w, const double *ivp = nullptr)
 {
     w.hit = 0;
     if (max_t > 1.0) max_t = 1.0;
@@ -90,7 +91,7 @@ __device__ __forceinline__ bool walk_setup(const BrickGeom &g, const double (&vp
         if (vd[i] < 0.0) step[i] = -1;
         else if (vd[i] == 0.0) { step[i] = 0; continue; }
         else step[i] = 1;
-        iv[i] = ddiv(1.0, vd[i]);
+        iv[i] = HAVE_IV ? ivp[i] : ddiv(1.0, vd[i]);
         if (direction == 3) continue;
         const int x = (i + 1) % 3, y = (i + 2) % 3;
         const double face = step[i] > 0 ? g.le[i] : g.re[i];

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "cast_kernels.cuh"
@@ -749,7 +750,11 @@ static int prepare_order(ytb200_frame *f, const ytb200_brickset *set, const int6
 template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T>
 static cudaError_t launch_one(const CastParams &p, unsigned grid, size_t smem, cudaStream_t st)
 {
-    auto k = cast_kernel<KIND, EXACT, TFM, PARTIAL, NF1, T>;
+    void (*k)(const CastParams) = cast_kernel<KIND, EXACT, TFM, PARTIAL, NF1, T>;
+    // long brick lists (AMR) take the MANY instantiation of the colour volume render (see cast_kernel)
+    if constexpr (KIND == KIND_VR && !EXACT && tfm_is_colour(TFM) && std::is_same<T, float>::value) {
+        if (p.n_order > 32) k = cast_kernel<KIND, EXACT, TFM, PARTIAL, NF1, T, true>;
+    }
     if (smem > 32 * 1024) {  // static shared memory counts against the 48 KiB default too
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
