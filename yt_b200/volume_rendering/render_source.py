@@ -19,36 +19,8 @@ from .utils import data_source_or_all, new_interpolated_projection_sampler, new_
 from .zbuffer_array import ZBuffer
 
 
-def invalidate_volume(f):
-    def wrapper(*args, **kwargs):
-        ret = f(*args, **kwargs)
-        obj = args[0]
-        if isinstance(obj._transfer_function, ProjectionTransferFunction):
-            obj.sampler_type = "projection"
-            obj._log_field = False
-            obj._use_ghost_zones = False
-        del obj.volume
-        obj._volume_valid = False
-        return ret
-    return wrapper
-
-
-def validate_volume(f):
-    def wrapper(*args, **kwargs):
-        obj = args[0]
-        fields = [obj.field]
-        log_fields = [obj.log_field]
-        if obj.weight_field is not None:
-            fields.append(obj.weight_field)
-            log_fields.append(obj.log_field)
-        if not obj._volume_valid:
-            obj.volume.set_fields(fields, log_fields, no_ghost=(not obj.use_ghost_zones))
-        obj._volume_valid = True
-        return f(*args, **kwargs)
-    return wrapper
-
-
 class RenderSource(abc.ABC):
+    """Anything a Scene can render: ``render(camera, zbuffer)`` and ``_validate()``."""
     volume_method = None
 
     def __init__(self):
@@ -57,14 +29,16 @@ class RenderSource(abc.ABC):
 
     @abc.abstractmethod
     def render(self, camera, zbuffer=None):
-        pass
+        ...
 
     @abc.abstractmethod
     def _validate(self):
-        pass
+        ...
 
 
 class OpaqueSource(RenderSource):
+    """Sources that paint the ZBuffer before the volume is cast."""
+
     def __init__(self):
         super().__init__()
         self.opaque = True
@@ -75,55 +49,80 @@ class OpaqueSource(RenderSource):
 
 def create_volume_source(data_source, field):
     data_source = data_source_or_all(data_source)
-    if hasattr(data_source.ds.index, "grids"):
-        return KDTreeVolumeSource(data_source, field)
-    raise NotImplementedError("only grid (kd-tree) datasets are on the B200 hot path")
+    if not hasattr(data_source.ds.index, "grids"):
+        raise NotImplementedError("only grid (kd-tree) datasets are on the B200 hot path")
+    return KDTreeVolumeSource(data_source, field)
+
+
+_SAMPLER_FACTORY = {          # (sampler_type, interpolated) -> factory of utils.py:55-139
+    ("volume-render", True): new_volume_render_sampler, ("volume-render", False): new_volume_render_sampler,
+    ("projection", True): new_interpolated_projection_sampler, ("projection", False): new_projection_sampler,
+}
+_TF_TYPES = (TransferFunction, ColorTransferFunction, ProjectionTransferFunction, type(None))
 
 
 class VolumeSource(RenderSource, abc.ABC):
+    """State of one volume to be cast: data source, field, log / ghost-zone / weight choices, transfer function and
+    the brick decomposition ("volume") they imply.  Same attributes, setters and invalidation rules as the reference
+    (render_source.py:209-536): changing the field, the log flag, the ghost-zone flag or the weight field drops the
+    decomposition (it is rebuilt, with the new fields, at the next render); a ProjectionTransferFunction switches the
+    source to the projection samplers with a linear field and no ghost zones."""
     _image = None
     data_source = None
 
     def __init__(self, data_source, field):
         super().__init__()
         self.data_source = data_source_or_all(data_source)
-        field = self.data_source._determine_fields(field)[0]
-        self.current_image = None
-        self.check_nans = False
-        self.num_threads = 0
-        self.num_samples = 10
-        self.sampler_type = "volume-render"
-        self.batched = True
-        self._volume_valid = False
-        self._volume = None
-        self._transfer_function = None
-        self._field = field
-        self._log_field = self.data_source.ds.field_info[field].take_log
+        self._field = self.data_source._determine_fields(field)[0]
+        self._log_field = self.data_source.ds.field_info[self._field].take_log
         self._use_ghost_zones = False
         self._weight_field = None
+        self._transfer_function = None
+        self._volume, self._volume_valid = None, False
+        self.current_image = None
+        self.check_nans = False
+        self.num_threads, self.num_samples = 0, 10
+        self.sampler_type = "volume-render"
+        self.batched = True          # ours: all bricks in one launch (False: sampler(brick) per brick, like the reference loop)
         self.tfh = TransferFunctionHelper(self.data_source.pf)
-        self.tfh.set_field(self.field)
+        self.tfh.set_field(self._field)
+
+    # -- invalidation -----------------------------------------------------------------------------------
+    def _drop_volume(self):
+        """What the reference's @invalidate_volume does after a setter (render_source.py:66-81)."""
+        if isinstance(self._transfer_function, ProjectionTransferFunction):
+            self.sampler_type = "projection"
+            self._log_field = False
+            self._use_ghost_zones = False
+        self._volume = None
+        self._volume_valid = False
+
+    def _ensure_volume_fields(self):
+        """What @validate_volume does before a render (render_source.py:84-103)."""
+        if not self._volume_valid:
+            fields, logs = [self.field], [self.log_field]
+            if self.weight_field is not None:
+                fields.append(self.weight_field)
+                logs.append(self.log_field)
+            self.volume.set_fields(fields, logs, no_ghost=(not self.use_ghost_zones))
+        self._volume_valid = True
 
     # -- transfer function ------------------------------------------------------------------------------
     @property
     def transfer_function(self):
-        if self._transfer_function is not None:
-            return self._transfer_function
-        if self.tfh.tf is not None:
+        if self._transfer_function is None:
+            if self.tfh.tf is None:      # build the default: 10 layers over the field's extrema
+                self.tfh.set_field(self.field)
+                self.tfh.set_log(self.log_field)
+                self.tfh.build_transfer_function()
+                self.tfh.setup_default()
             self._transfer_function = self.tfh.tf
-            return self._transfer_function
-        self.tfh.set_field(self.field)
-        self.tfh.set_log(self.log_field)
-        self.tfh.build_transfer_function()
-        self.tfh.setup_default()
-        self._transfer_function = self.tfh.tf
         return self._transfer_function
 
     @transfer_function.setter
     def transfer_function(self, value):
         self.tfh.tf = None
-        valid_types = (TransferFunction, ColorTransferFunction, ProjectionTransferFunction, type(None))
-        if not isinstance(value, valid_types):
+        if not isinstance(value, _TF_TYPES):
             raise RuntimeError("transfer_function not a valid type, received object of type %s" % type(value))
         if isinstance(value, ProjectionTransferFunction):
             self.sampler_type = "projection"
@@ -131,7 +130,7 @@ class VolumeSource(RenderSource, abc.ABC):
                 self._volume_valid = False
         self._transfer_function = value
 
-    # -- volume ---------------------------------------------------------------------------------------------
+    # -- the brick decomposition ------------------------------------------------------------------------
     @property
     def volume(self):
         return self._get_volume()
@@ -139,8 +138,7 @@ class VolumeSource(RenderSource, abc.ABC):
     @volume.setter
     def volume(self, value):
         assert isinstance(value, AMRKDTree)
-        self._field = value.fields
-        self._log_field = value.log_fields
+        self._field, self._log_field = value.fields, value.log_fields
         self._volume = value
         assert self._volume_valid
 
@@ -148,105 +146,90 @@ class VolumeSource(RenderSource, abc.ABC):
     def volume(self):
         self._volume = None
 
+    @abc.abstractmethod
+    def _get_volume(self):
+        ...
+
+    # -- what is rendered -------------------------------------------------------------------------------
     @property
     def field(self):
         return self._field
 
     @field.setter
-    @invalidate_volume
     def field(self, value):
-        field = self.data_source._determine_fields(value)
-        if len(field) > 1:
-            raise RuntimeError("VolumeSource.field can only be a single field but received multiple fields: %s" % field)
-        field = field[0]
-        if self._field != field:
-            log_field = self.data_source.ds.field_info[field].take_log
+        found = self.data_source._determine_fields(value)
+        if len(found) > 1:
+            raise RuntimeError("VolumeSource.field can only be a single field but received multiple fields: %s" % found)
+        new = found[0]
+        if new != self._field:       # another field: its own log default, and new table bounds
+            self._log_field = self.data_source.ds.field_info[new].take_log
             self.tfh.bounds = None
-        else:
-            log_field = self._log_field
-        self._log_field = log_field
-        self._field = field
+        self._field = new
         self.transfer_function = None
-        self.tfh.set_field(field)
-        self.tfh.set_log(log_field)
+        self.tfh.set_field(new)
+        self.tfh.set_log(self._log_field)
+        self._drop_volume()
 
     @property
     def log_field(self):
         return self._log_field
 
     @log_field.setter
-    @invalidate_volume
     def log_field(self, value):
         self.transfer_function = None
         self.tfh.set_log(value)
         self._log_field = value
+        self._drop_volume()
 
     @property
     def use_ghost_zones(self):
         return self._use_ghost_zones
 
     @use_ghost_zones.setter
-    @invalidate_volume
     def use_ghost_zones(self, value):
         self._use_ghost_zones = value
+        self._drop_volume()
 
     @property
     def weight_field(self):
         return self._weight_field
 
     @weight_field.setter
-    @invalidate_volume
     def weight_field(self, value):
         self._weight_field = value
+        self._drop_volume()
 
-    def set_transfer_function(self, transfer_function):
-        self.transfer_function = transfer_function
-        return self
+    # chainable setters of the reference API (render_source.py:398-476)
+    def _chain(attr):      # noqa: N805 -- helper evaluated at class-body time
+        def setter(self, value):
+            setattr(self, attr, value)
+            return self
+        return setter
 
+    set_transfer_function = _chain("transfer_function")
+    set_volume = _chain("volume")
+    set_field = _chain("field")
+    set_log = _chain("log_field")
+    set_weight_field = _chain("weight_field")
+    set_use_ghost_zones = _chain("use_ghost_zones")
+    del _chain
+
+    # -- sampler ----------------------------------------------------------------------------------------
     def _validate(self):
         if self.data_source is None:
             raise RuntimeError("Data source not initialized")
 
-    def set_volume(self, volume):
-        self.volume = volume
-        return self
-
-    def set_field(self, field):
-        self.field = field
-        return self
-
-    def set_log(self, log_field):
-        self.log_field = log_field
-        return self
-
-    def set_weight_field(self, weight_field):
-        self.weight_field = weight_field
-        return self
-
-    def set_use_ghost_zones(self, use_ghost_zones):
-        self.use_ghost_zones = use_ghost_zones
-        return self
-
     def set_sampler(self, camera, interpolated=True):
-        if self.sampler_type == "volume-render":
-            sampler = new_volume_render_sampler(camera, self)
-        elif self.sampler_type == "projection" and interpolated:
-            sampler = new_interpolated_projection_sampler(camera, self)
-        elif self.sampler_type == "projection":
-            sampler = new_projection_sampler(camera, self)
-        else:
+        factory = _SAMPLER_FACTORY.get((self.sampler_type, bool(interpolated)))
+        if factory is None:
             raise NotImplementedError("%s not implemented yet" % self.sampler_type)
-        self.sampler = sampler
+        self.sampler = factory(camera, self)
         assert self.sampler is not None
-
-    @abc.abstractmethod
-    def _get_volume(self):
-        pass
 
     def finalize_image(self, camera, image):
         image = image.reshape(*camera.resolution, 4)
         if not self.transfer_function.grey_opacity:
-            image[:, :, 3] = 1
+            image[:, :, 3] = 1          # the non-grey composite never touches alpha (render_source.py:535-536)
         return image
 
     def __repr__(self):
@@ -261,8 +244,8 @@ class KDTreeVolumeSource(VolumeSource):
             self._volume = AMRKDTree(self.data_source.ds, data_source=self.data_source)
         return self._volume
 
-    @validate_volume
     def render(self, camera, zbuffer=None):
+        self._ensure_volume_fields()
         self.zbuffer = zbuffer
         self.set_sampler(camera)
         assert self.sampler is not None

@@ -1,6 +1,10 @@
-"""Scene -- yt/visualization/volume_rendering/scene.py:29-760 (sources, camera, render, composite, save)."""
-from collections import OrderedDict
+"""Scene -- the container a user drives: sources + camera -> image.
 
+Interface of yt/visualization/volume_rendering/scene.py:29-880 restricted to what reaches the ray caster:
+``add_source / get_source / [] / opaque_sources / transparent_sources``, ``add_camera / camera``,
+``render / composite / save`` and the ``annotate_*`` helpers.  Compositing order and the final 180-degree rotation
+are the reference's (scene.py:611-625); all rendering work happens inside the sources.
+"""
 import numpy as np
 
 from .camera import Camera
@@ -14,96 +18,39 @@ class Scene:
     _camera = None
 
     def __init__(self):
-        self.sources = OrderedDict()
+        self.sources = {}              # insertion-ordered: the order sources are rendered in
         self._last_render = None
         self._sigma_clip = None
 
+    # -- sources ----------------------------------------------------------------------------------------
+    def add_source(self, render_source, keyname=None):
+        key = "source_%02d" % len(self.sources) if keyname is None else keyname
+        self.sources[key] = render_source
+        return self
+
+    __setitem__ = lambda self, key, value: self.add_source(value, key)   # noqa: E731
+
     def get_source(self, source_num=0):
-        return list(self.sources.values())[source_num]
+        return tuple(self.sources.values())[source_num]
 
     def __getitem__(self, item):
-        if item in self.sources:
-            return self.sources[item]
-        return self.get_source(item)
+        return self.sources[item] if item in self.sources else self.get_source(item)
+
+    def _sources_where(self, opaque):
+        return ((k, s) for k, s in self.sources.items() if isinstance(s, OpaqueSource) == opaque)
 
     @property
     def opaque_sources(self):
-        for k, source in self.sources.items():
-            if isinstance(source, OpaqueSource):
-                yield k, source
+        return self._sources_where(True)
 
     @property
     def transparent_sources(self):
-        for k, source in self.sources.items():
-            if not isinstance(source, OpaqueSource):
-                yield k, source
+        return self._sources_where(False)
 
-    def add_source(self, render_source, keyname=None):
-        if keyname is None:
-            keyname = "source_%02d" % len(self.sources)
-        self.sources[keyname] = render_source
-        return self
-
-    def __setitem__(self, key, value):
-        return self.add_source(value, key)
-
-    def render(self, camera=None):
-        if camera is None:
-            camera = self.camera
-        assert camera is not None
-        self._validate()
-        bmp = self.composite(camera=camera)
-        self._last_render = bmp
-        return bmp
-
-    def _validate(self):
-        for source in self.sources.values():
-            source._validate()
-
-    def composite(self, camera=None):
-        """Opaque sources fill the z-buffer; transparent sources render from it (scene.py:581-625)."""
-        if camera is None:
-            camera = self.camera
-        empty = camera.lens.new_image(camera)
-        opaque = ZBuffer(empty, np.full(empty.shape[:2], np.inf))
-        im = empty
-        for _, source in self.opaque_sources:
-            source.render(camera, zbuffer=opaque)
-            im = source.zbuffer.rgba
-        for _, source in self.transparent_sources:
-            im = source.render(camera, zbuffer=opaque)
-            opaque.rgba = im
-        # rotate 180 degrees so the orientation agrees with a PlotWindow plot
-        return ImageArray(np.rot90(im, k=2), info={"imtype": "rendering"})
-
-    # -- annotations (scene.py:755-880): opaque sources added under fixed keys -------------------------------
-    def annotate_domain(self, ds, color=None):
-        from .render_source import BoxSource
-        self.add_source(BoxSource(ds.domain_left_edge, ds.domain_right_edge, color=color))
-        return self
-
-    def annotate_grids(self, data_source, alpha=0.3, cmap=None, min_level=None, max_level=None):
-        from .render_source import GridSource
-        self.add_source(GridSource(data_source, alpha=alpha, cmap=cmap, min_level=min_level, max_level=max_level))
-        return self
-
-    def annotate_axes(self, colors=None, alpha=1.0, *, thickness=1):
-        from .render_source import CoordinateVectorSource
-        self.add_source(CoordinateVectorSource(colors, alpha, thickness=thickness))
-        return self
-
-    def save(self, fname=None, sigma_clip=None, render=True):
-        if fname is None:
-            fname = "Render_opaque.png"
-        if not fname.endswith(".png"):
-            fname += ".png"
-        if render or self._last_render is None:
-            self.render()
-        return ImageArray(self._last_render).write_png(fname, sigma_clip=sigma_clip, background="black")
-
+    # -- camera -----------------------------------------------------------------------------------------
     def add_camera(self, data_source=None, lens_type="plane-parallel", auto=False):
         self._camera = Camera(self, data_source, lens_type, auto)
-        return self.camera
+        return self._camera
 
     @property
     def camera(self):
@@ -117,12 +64,59 @@ class Scene:
     def camera(self):
         self._camera = None
 
+    # -- rendering --------------------------------------------------------------------------------------
+    def _validate(self):
+        for source in self.sources.values():
+            source._validate()
+
+    def render(self, camera=None):
+        camera = self.camera if camera is None else camera
+        assert camera is not None
+        self._validate()
+        self._last_render = self.composite(camera=camera)
+        return self._last_render
+
+    def composite(self, camera=None):
+        """Opaque sources paint one shared ZBuffer, in order; every transparent source is then cast from that
+        buffer (initial colours + per-pixel stopping depth) and its result becomes the buffer's colours for the
+        next one (scene.py:611-622).  The image is rotated by 180 degrees to agree with a PlotWindow plot."""
+        camera = self.camera if camera is None else camera
+        canvas = camera.lens.new_image(camera)
+        depth = ZBuffer(canvas, np.full(canvas.shape[:2], np.inf))
+        image = canvas
+        for _, source in self.opaque_sources:
+            source.render(camera, zbuffer=depth)
+            image = source.zbuffer.rgba
+        for _, source in self.transparent_sources:
+            image = source.render(camera, zbuffer=depth)
+            depth.rgba = image
+        return ImageArray(np.rot90(image, k=2), info={"imtype": "rendering"})
+
+    def save(self, fname=None, sigma_clip=None, render=True):
+        fname = "Render_opaque.png" if fname is None else fname
+        if not fname.endswith(".png"):
+            fname += ".png"
+        if render or self._last_render is None:
+            self.render()
+        return ImageArray(self._last_render).write_png(fname, sigma_clip=sigma_clip, background="black")
+
+    # -- annotations: opaque sources with the reference's defaults (scene.py:755-880) --------------------------
+    def annotate_domain(self, ds, color=None):
+        from .render_source import BoxSource
+        return self.add_source(BoxSource(ds.domain_left_edge, ds.domain_right_edge, color=color))
+
+    def annotate_grids(self, data_source, alpha=0.3, cmap=None, min_level=None, max_level=None):
+        from .render_source import GridSource
+        return self.add_source(GridSource(data_source, alpha=alpha, cmap=cmap, min_level=min_level, max_level=max_level))
+
+    def annotate_axes(self, colors=None, alpha=1.0, *, thickness=1):
+        from .render_source import CoordinateVectorSource
+        return self.add_source(CoordinateVectorSource(colors, alpha, thickness=thickness))
+
+    # -- misc -------------------------------------------------------------------------------------------
     def arr(self, x, units=None):
         return np.asarray(x, dtype="float64")
 
     def __repr__(self):
-        disp = "<Scene Object>:\nSources: \n"
-        for k, v in self.sources.items():
-            disp += "    %s: %s\n" % (k, v)
-        disp += "Camera: \n    %s" % self.camera
-        return disp
+        listing = "".join("    %s: %s\n" % kv for kv in self.sources.items())
+        return "<Scene Object>:\nSources: \n%sCamera: \n    %s" % (listing, self.camera)

@@ -1,40 +1,45 @@
-"""ZBuffer -- an RGBA image with a per-pixel depth (yt/visualization/volume_rendering/zbuffer_array.py:4-79).
+"""ZBuffer -- an RGBA image with a depth per pixel (interface of
+yt/visualization/volume_rendering/zbuffer_array.py:4-79).
 
-Opaque sources paint into it; the volume sampler then stops each ray at ``clip(z, 0, 1)``
-(image_samplers.pyx:185) and starts from the painted colours (utils.py:79-84).
+Opaque sources paint into it; the volume cast then starts from the painted colours (utils.py:79-84) and stops each
+ray at ``clip(z, 0, 1)`` (image_samplers.pyx:185).
 """
 import numpy as np
 
 
 class ZBuffer:
     def __init__(self, rgba, z):
-        assert rgba.shape[: len(z.shape)] == z.shape
-        self.rgba = rgba
-        self.z = z
+        if rgba.shape[: z.ndim] != z.shape:
+            raise AssertionError("rgba %s and z %s do not describe the same pixels" % (rgba.shape, z.shape))
+        self.rgba, self.z = rgba, z
         self.shape = z.shape
 
-    def __add__(self, other):
-        """Per pixel, keep whichever buffer is nearer."""
-        assert self.shape == other.shape
-        nearer = self.z < other.z
-        if self.z.shape[1] == 1:  # non-rectangular buffers
-            rgba = self.rgba * nearer[:, None, :] + other.rgba * (1.0 - nearer)[:, None, :]
+    def _merge(self, other):
+        """Per pixel the nearer of the two buffers; where the depths tie the colour is left black, as in the
+        reference (neither ``<`` nor ``>`` selects it, zbuffer_array.py:52-58)."""
+        if self.shape != other.shape:
+            raise AssertionError("buffers of different shape")
+        mine = self.z < other.z
+        if self.z.shape[1] == 1:      # flattened (non-rectangular) buffers: blend by the mask
+            rgba = self.rgba * mine[:, None, :] + other.rgba * (1.0 - mine)[:, None, :]
         else:
-            farther = self.z > other.z
+            theirs = other.z < self.z
             rgba = np.zeros(self.rgba.shape)
-            rgba[nearer] = self.rgba[nearer]
-            rgba[farther] = other.rgba[farther]
-        return ZBuffer(rgba, np.min([self.z, other.z], axis=0))
+            rgba[mine] = self.rgba[mine]
+            rgba[theirs] = other.rgba[theirs]
+        return rgba, np.minimum(self.z, other.z)
+
+    def __add__(self, other):
+        return ZBuffer(*self._merge(other))
 
     def __iadd__(self, other):
-        merged = self + other
-        self.rgba, self.z = merged.rgba, merged.z
+        self.rgba, self.z = self._merge(other)
         return self
 
     def __eq__(self, other):
-        return bool(np.all(self.rgba == other.rgba) and np.all(self.z == other.z))
+        return bool((self.rgba == other.rgba).all() and (self.z == other.z).all())
 
     def paint(self, ind, value, z):
+        """Set pixel ``ind`` to ``value`` if ``z`` is in front of what is there."""
         if z < self.z[ind]:
-            self.rgba[ind] = value
-            self.z[ind] = z
+            self.rgba[ind], self.z[ind] = value, z
