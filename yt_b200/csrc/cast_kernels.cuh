@@ -851,7 +851,16 @@ cast_kernel(const __grid_constant__ CastParams p)
         }
 #pragma unroll
         for (int c = 0; c < 4; c++) { out[c] = (double)smp.rgba[c]; Bout[c] = (double)smp.B[c]; }
-        if (!PARTIAL && !p.tf.grey) out[3] = p.image[pix * 4 + 3];  // non-grey never touches alpha (H9)
+        if (!PARTIAL) {
+            // A channel whose fp32 accumulator still holds the (rounded) initial colour was not changed by any sample:
+            // give it back its fp64 value, so that pixels no ray touches -- and the alpha of a non-grey render (H9) --
+            // come back bit-identical, as in the reference where they are never written with anything else.
+            const double4 c0 = *reinterpret_cast<const double4 *>(p.image + pix * 4);
+            if (smp.rgba[0] == (float)c0.x) out[0] = c0.x;
+            if (smp.rgba[1] == (float)c0.y) out[1] = c0.y;
+            if (smp.rgba[2] == (float)c0.z) out[2] = c0.z;
+            if (smp.rgba[3] == (float)c0.w || !p.tf.grey) out[3] = c0.w;
+        }
     } else {
 #pragma unroll
         for (int c = 0; c < 4; c++) { out[c] = smp.acc[c]; Bout[c] = 1.0; }
