@@ -139,6 +139,11 @@ int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nbins, const 
                      const double *bounds /* n_tables x 2 */, const int32_t field_ids[6],
                      const int32_t weight_field_ids[6], const int32_t weight_table_ids[6],
                      const int32_t field_table_ids[6], int grey_opacity, ytb200_tf **out);
+/* LightSourceRenderSampler.__cinit__ (image_samplers.pyx:496-549): switches the volume render of this table set to
+ * the lit sampler -- gradient of field 0 by eval_gradient (fixed_interpolator.cpp:116-148), composite by
+ * FIT_eval_transfer_with_light (field_interpolation_tables.pxd:115-143), no cell-mask test (image_samplers.pyx:551-589).
+ * light_dir must already be normalised (the reference normalises it in place); NULL switches the light off. */
+int ytb200_tf_set_light(ytb200_tf *tf, const double light_dir[3], const double light_rgba[4]);
 int ytb200_tf_destroy(ytb200_tf *tf);
 
 /* ---- frame: the image / z-buffer / ray set one ImageSampler instance owns ------------------- */

@@ -25,7 +25,7 @@ _SO = os.path.join(HERE, "_build", "libytray_oracle.so")
 _SRC = os.path.join(HERE, "ytray_oracle.c")
 _lib = None
 
-PROJ, IPROJ, VR = 0, 1, 2
+PROJ, IPROJ, VR, LIGHT = 0, 1, 2, 3
 LENS_PP, LENS_PERSPECTIVE, LENS_GENERIC = 0, 1, 2
 
 
@@ -57,7 +57,7 @@ def lib():
         _lib.orc_cast_brick.argtypes = [
             C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp,
             C.c_int, C.POINTER(dp), C.POINTER(C.c_uint8), dp, dp, C.POINTER(C.c_int64),
-            C.POINTER(_TFDesc), C.c_int, C.c_int]
+            C.POINTER(_TFDesc), C.c_int, C.c_int, dp, dp]
         _lib.orc_max_threads.restype = C.c_int
         i64p = C.POINTER(C.c_int64)
         _lib.orc_ghost_zone_interpolate.restype = None
@@ -132,7 +132,8 @@ class ImageSampler:
             _dptr(self.camera_data), _dptr(self.aimage), _dptr(self.azbuffer),
             nf, arr, pg.source_mask.ctypes.data_as(C.POINTER(C.c_uint8)),
             _dptr(pg.LeftEdge), _dptr(pg.RightEdge), pg.dims.ctypes.data_as(C.POINTER(C.c_int64)),
-            C.byref(self._tf) if self._tf is not None else None, int(self.n_samples), int(num_threads))
+            C.byref(self._tf) if self._tf is not None else None, int(self.n_samples), int(num_threads),
+            _dptr(getattr(self, "light_dir", None)), _dptr(getattr(self, "light_rgba", None)))
         if n < 0:
             raise RuntimeError("oracle error %d" % n)
         self.cells += n
@@ -177,6 +178,19 @@ class VolumeRenderSampler(ImageSampler):
             d.field_table_ids[i] = tf_obj.field_table_ids[i]
         d.grey_opacity = int(getattr(tf_obj, "grey_opacity", 0))
         self._tf = d
+
+
+class LightSourceRenderSampler(VolumeRenderSampler):
+    """image_samplers.pyx:496-600: the volume render lit by one directional light (gradient shading)."""
+    kind = LIGHT
+
+    def __init__(self, vp_pos, vp_dir, center, bounds, image, x_vec, y_vec, width, volume_method,
+                 tf_obj, n_samples=10, light_dir=(1., 1., 1.), light_rgba=(1., 1., 1., 1.), **kwargs):
+        super().__init__(vp_pos, vp_dir, center, bounds, image, x_vec, y_vec, width, volume_method, tf_obj, n_samples, **kwargs)
+        ld = np.array(light_dir, dtype="float64")
+        ld /= np.sqrt(ld[0] * ld[0] + ld[1] * ld[1] + ld[2] * ld[2])     # image_samplers.pyx:526-528
+        self.light_dir = np.ascontiguousarray(ld)
+        self.light_rgba = np.ascontiguousarray(np.array(light_rgba, dtype="float64"))
 
 
 def vertex_centre(cells):

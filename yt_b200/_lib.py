@@ -67,6 +67,7 @@ SIGNATURES = {
     "ytb200_bricks_device_bytes": (C.c_int64, [C.c_void_p]),
     "ytb200_tf_create": (C.c_int, [C.c_void_p, C.c_int, i32p, C.POINTER(dp), dp, i32p, i32p, i32p, i32p, C.c_int,
                                    C.POINTER(C.c_void_p)]),
+    "ytb200_tf_set_light": (C.c_int, [C.c_void_p, dp, dp]),
     "ytb200_tf_destroy": (C.c_int, [C.c_void_p]),
     "ytb200_frame_create": (C.c_int, [C.c_void_p, C.POINTER(Camera), C.POINTER(C.c_void_p)]),
     "ytb200_frame_destroy": (C.c_int, [C.c_void_p]),

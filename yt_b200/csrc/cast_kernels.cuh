@@ -91,7 +91,7 @@ struct ExactSampler {
                 if (f < nf) acc[f] = dadd(acc[f], dmul(((const double *)br->data[f])[di], dl));
             return;
         }
-        if (KIND == KIND_VR && MASKED) {
+        if (KIND == KIND_VR && MASKED && !tf->light_on) {   // LightSourceRenderSampler.sample has no mask test (image_samplers.pyx:551-589)
             if (mask[((size_t)ix * ny + iy) * nz + iz] != 1) return;
         }
         const int sy = br->pitch_y, sx = br->pitch_x;
@@ -109,7 +109,11 @@ struct ExactSampler {
 #pragma unroll
             for (int j = 0; j < 6; j++)
                 dvs[j] = (j < n_fields) ? offset_interpolate64((const double *)br->data[j] + offset, sx, sy, dp) : 0.0;
-            if (KIND == KIND_VR) {
+            if (KIND == KIND_VR && tf->light_on) {
+                double grad[3];
+                eval_gradient_t((const double *)br->data[0] + offset, sx, sy, dp, grad);
+                eval_transfer64_light<PARTIAL>(*tf, t64, dt, dvs, grad, acc, B64);
+            } else if (KIND == KIND_VR) {
                 eval_transfer64<PARTIAL>(*tf, t64, dt, dvs, acc, B64);
             } else {
                 const int nf = n_fields < 3 ? n_fields : 3;
@@ -524,7 +528,7 @@ struct FastSampler {
                 if (f < nf) acc[f] = fma((double)__ldg((const T *)br->data[f] + off), dl, acc[f]);
             return;
         }
-        if (KIND == KIND_VR && MASKED) {
+        if (KIND == KIND_VR && MASKED && !(!tfm_is_colour(TFM) && tf->light_on)) {
             if (mask[moff] != 1) return;
         }
         const double dt64 = (exit_t - enter_t) * prm->inv_ns;
@@ -572,6 +576,22 @@ struct FastSampler {
         const float sxs = dcf[0] * dt, sys = dcf[1] * dt, szs = dcf[2] * dt;
         if (tfm_is_colour(TFM)) {
             // the ColorTransferFunction path has its own fused walk (walk_colour)
+        } else if (KIND == KIND_VR && tf->light_on) {
+            // LightSourceRenderSampler (image_samplers.pyx:551-589): positions and the gradient of field 0 in fp64, table
+            // lookups and the lit composite in fp32.  General, not tuned (the reference reaches it from old_camera only).
+            double dp[3] = {xd, yd, zd};
+            const double st[3] = {dc[0] * dt64, dc[1] * dt64, dc[2] * dt64};
+            for (int s = 0; s < n_samples; s++) {
+                float dvs[6];
+#pragma unroll
+                for (int j = 0; j < 6; j++)
+                    dvs[j] = j < n_fields ? (float)offset_interpolate_t((const T *)br->data[j] + off, sx, sy, dp) : 0.f;
+                double grad[3];
+                eval_gradient_t((const T *)br->data[0] + off, sx, sy, dp, grad);
+                eval_transfer32_light<PARTIAL>(*tf, pairs, dt, dvs, grad, rgba, B);
+#pragma unroll
+                for (int i = 0; i < 3; i++) dp[i] += st[i];
+            }
         } else if (NF1) {
             Corners c;
             load_corners(c, (const T *)br->data[0] + off, sx, sy);

@@ -66,6 +66,9 @@ struct DevTF {
     float colour_c0, colour_clamp_bound, colour_lo, colour_hi, colour_mid, colour_half, colour_band, colour_zrow;
     float colour_clamp_hi;   // delta layout: row coordinates are clamped to [0.5, nbins + 1.5]
     int colour_zero_inside, colour_edge, colour_delta, colour_rows;
+    // LightSourceRenderSampler (image_samplers.pyx:496-600): one directional light, gradient shading
+    int light_on;
+    double light_dir[3], light_rgba[4];
 };
 
 struct CastParams {

@@ -281,6 +281,83 @@ __device__ __forceinline__ void eval_transfer64(const DevTF &tf, const TFShared6
     }
 }
 
+// ---- LightSourceRenderSampler pieces (fp64, reference evaluation order; not a tuned path) ----------------
+// trilinear interpolation from the brick's stored type (fixed_interpolator.cpp:34-52)
+template <typename T>
+__device__ __forceinline__ double offset_interpolate_t(const T *d, int sx, int sy, const double (&dp)[3])
+{
+    double dv = dsub(1.0, dp[2]);
+    double v0 = dadd(dmul(dv, (double)__ldg(d)),           dmul(dp[2], (double)__ldg(d + 1)));
+    double v1 = dadd(dmul(dv, (double)__ldg(d + sy)),      dmul(dp[2], (double)__ldg(d + sy + 1)));
+    double v2 = dadd(dmul(dv, (double)__ldg(d + sx)),      dmul(dp[2], (double)__ldg(d + sx + 1)));
+    double v3 = dadd(dmul(dv, (double)__ldg(d + sx + sy)), dmul(dp[2], (double)__ldg(d + sx + sy + 1)));
+    dv = dsub(1.0, dp[1]);
+    v0 = dadd(dmul(dv, v0), dmul(dp[1], v1));
+    v1 = dadd(dmul(dv, v2), dmul(dp[1], v3));
+    dv = dsub(1.0, dp[0]);
+    return dadd(dmul(dv, v0), dmul(dp[0], v1));
+}
+
+// eval_gradient (fixed_interpolator.cpp:116-148)
+template <typename T>
+__device__ __forceinline__ void eval_gradient_t(const T *d, int sx, int sy, double (&dp)[3], double (&grad)[3])
+{
+    double normval = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double backup = dp[i];
+        double plus, minus;
+        if (dp[i] >= 0.95) { plus = dp[i]; minus = dsub(dp[i], 0.05); }
+        else if (dp[i] <= 0.05) { plus = dadd(dp[i], 0.05); minus = 0.0; }
+        else { plus = dadd(dp[i], 0.05); minus = dsub(dp[i], 0.05); }
+        const double denom = dsub(plus, minus);
+        dp[i] = plus;
+        double g = dadd(0.0, ddiv(offset_interpolate_t(d, sx, sy, dp), denom));
+        dp[i] = minus;
+        g = dsub(g, ddiv(offset_interpolate_t(d, sx, sy, dp), denom));
+        dp[i] = backup;
+        grad[i] = g;
+        normval = dadd(normval, dmul(g, g));
+    }
+    if (normval != 0.0) {
+        normval = __dsqrt_rn(normval);
+#pragma unroll
+        for (int i = 0; i < 3; i++) grad[i] = ddiv(grad[i], -normval);
+    } else {
+        grad[0] = grad[1] = grad[2] = 0.0;
+    }
+}
+
+// FIT_eval_transfer_with_light (field_interpolation_tables.pxd:115-143); B only when PARTIAL
+template <bool PARTIAL>
+__device__ __forceinline__ void eval_transfer64_light(const DevTF &tf, const TFShared64 &t, double dt, const double (&dvs)[6],
+                                                      const double (&grad)[3], double (&rgba)[4], double (&B)[4])
+{
+    double dot_prod = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) dot_prod = dadd(dot_prod, dmul(tf.light_dir[i], grad[i]));
+    double ist[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) ist[i] = (i < tf.n_fits) ? fit_get_value64(tf, t, i, dvs) : 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        if (i < tf.n_fits) {
+            const int fid = tf.weight_table_id[i];
+            if (fid != -1) ist[i] = dmul(ist[i], pick6(ist, fid));
+        }
+    }
+    const double t0 = pick6(ist, tf.field_table_id[0]), t1 = pick6(ist, tf.field_table_id[1]), t2 = pick6(ist, tf.field_table_id[2]);
+    const double tc[3] = {t0, t1, t2};
+    const double ta_grey = fmax(dsub(1.0, dmul(dt, dadd(dadd(t0, t1), t2))), 0.0);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double ta = tf.grey ? ta_grey : fmax(dsub(1.0, dmul(dt, tc[c])), 0.0);
+        const double lit = dadd(1., dmul(dot_prod, tf.light_rgba[c]));
+        rgba[c] = dadd(dmul(dmul(dsub(1., ta), tc[c]), lit), dmul(ta, rgba[c]));
+        if (PARTIAL) B[c] = dmul(B[c], ta);
+    }
+}
+
 // ---- FAST (fp32) pieces ---------------------------------------------------------------------------
 struct Corners {
     float c000, dz00, c010, dz01, c100, dz10, c110, dz11;  // low-z value and z-increment of the 4 z-edges
@@ -357,6 +434,32 @@ __device__ __forceinline__ void eval_transfer32(const DevTF &tf, const float2 *p
             rgba[c] = fmaf(ta, rgba[c], t);
             if (PARTIAL) B[c] *= ta;
         }
+    }
+}
+
+// FIT_eval_transfer_with_light in fp32 (FAST precision; the gradient comes in fp64)
+template <bool PARTIAL>
+__device__ __forceinline__ void eval_transfer32_light(const DevTF &tf, const float2 *pairs, float dt, const float (&dvs)[6],
+                                                      const double (&grad)[3], float (&rgba)[4], float (&B)[4])
+{
+    const float dot_prod = (float)(tf.light_dir[0] * grad[0] + tf.light_dir[1] * grad[1] + tf.light_dir[2] * grad[2]);
+    float ist[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) ist[i] = (i < tf.n_fits) ? fit_get_value32(tf, pairs, i, dvs) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        if (i < tf.n_fits) {
+            const int fid = tf.weight_table_id[i];
+            if (fid != -1) ist[i] *= pick6(ist, fid);
+        }
+    }
+    const float tc[3] = {pick6(ist, tf.field_table_id[0]), pick6(ist, tf.field_table_id[1]), pick6(ist, tf.field_table_id[2])};
+    const float ta_grey = fmaxf(1.f - dt * (tc[0] + tc[1] + tc[2]), 0.f);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float ta = tf.grey ? ta_grey : fmaxf(1.f - dt * tc[c], 0.f);
+        rgba[c] = fmaf(ta, rgba[c], (1.f - ta) * tc[c] * (1.f + dot_prod * (float)tf.light_rgba[c]));
+        if (PARTIAL) B[c] *= ta;
     }
 }
 

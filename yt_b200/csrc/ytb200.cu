@@ -581,6 +581,16 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
     return 0;
 }
 
+extern "C" int ytb200_tf_set_light(ytb200_tf *t, const double *light_dir, const double *light_rgba)
+{
+    if (!t) return fail(E_ARG, "tf is NULL");
+    if (!light_dir || !light_rgba) { t->d.light_on = 0; return 0; }
+    for (int i = 0; i < 3; i++) t->d.light_dir[i] = light_dir[i];
+    for (int i = 0; i < 4; i++) t->d.light_rgba[i] = light_rgba[i];
+    t->d.light_on = 1;
+    return 0;
+}
+
 extern "C" int ytb200_tf_destroy(ytb200_tf *t)
 {
     if (!t) return 0;
@@ -827,7 +837,7 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
         size_t smem = 0;
         cudaError_t e;
         if (kind == YTB200_VOLUME_RENDER) {
-            const bool colour = !exact && nf1 && tf->d.colour_fast;
+            const bool colour = !exact && nf1 && tf->d.colour_fast && !tf->d.light_on;
             if (exact) smem = (size_t)tf->d.total_bins * 3 * sizeof(double);
             else if (colour) smem = ((size_t)tf->d.colour_rows << tf->d.colour_copy_shift) * sizeof(float4) * (tf->d.colour_delta ? 2 : 1);
             else smem = (size_t)tf->d.total_bins * sizeof(float2);

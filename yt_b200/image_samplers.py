@@ -285,3 +285,19 @@ class VolumeRenderSampler(ImageSampler):
         self.tf_obj = tf_obj
         self.my_field_tables = [(tf_obj.tables[i], tf_obj.tables[i].y) for i in range(tf_obj.n_field_tables)]
         self._tables = D.TransferTables(self._ctx, tf_obj)
+
+
+class LightSourceRenderSampler(VolumeRenderSampler):
+    """image_samplers.pyx:496-600: the volume render lit by one directional light (shading by the normalised gradient of
+    field 0).  Same constructor as the reference, including the in-place normalisation of ``light_dir``."""
+
+    def __init__(self, vp_pos, vp_dir, center, bounds, image, x_vec, y_vec, width, volume_method, tf_obj,
+                 n_samples=10, light_dir=(1., 1., 1.), light_rgba=(1., 1., 1., 1.), **kwargs):
+        super().__init__(vp_pos, vp_dir, center, bounds, image, x_vec, y_vec, width, volume_method, tf_obj, n_samples, **kwargs)
+        light_dir /= np.sqrt(light_dir[0] * light_dir[0] + light_dir[1] * light_dir[1] + light_dir[2] * light_dir[2])
+        self.light_dir = np.ascontiguousarray(light_dir, dtype=np.float64)
+        self.light_rgba = np.ascontiguousarray(light_rgba, dtype=np.float64)
+        if self.light_dir.shape != (3,) or self.light_rgba.shape != (4,):
+            raise ValueError("light_dir needs 3 components and light_rgba 4")
+        L.check(L.load().ytb200_tf_set_light(self._tables.handle, self.light_dir.ctypes.data_as(L.dp),
+                                             self.light_rgba.ctypes.data_as(L.dp)))
