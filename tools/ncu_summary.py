@@ -38,6 +38,7 @@ l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum
 l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum
 sass__inst_executed_shared_loads
 l1tex__data_pipe_lsu_wavefronts_mem_shared.sum
+l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed
 l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum
 smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio
 smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio
