@@ -38,6 +38,7 @@ WORKLOADS = {
     "northstar_vr_1024c_2048px": (1024, 2048, "vr"),
     "cfg2_vr_512c_1024px": (512, 1024, "vr"),
     "cfg3_proj_1024c_2048px": (1024, 2048, "proj"),
+    "iproj_1024c_2048px": (1024, 2048, "iproj"),               # InterpolatedProjectionSampler on the north-star volume
     "cfg4_amr_vr_15kbricks_persp_2048px": (128, 2048, "vr"),   # nested-box AMR, PerspectiveLens (BASELINE configs[3])
     "cfg5_vr_2048c_4096px": (2048, 4096, "vr"),                # BASELINE configs[4]; 34.4 GB of vertex data
     "tiny_vr_64c_256px": (64, 256, "vr"),
@@ -212,6 +213,8 @@ def cpu_render_sample(kind, n=256, res=512, threads=0, repeats=1):
         args, kwargs = sampler_call_args(cam, img, None)
         if kind == "vr":
             s = S.VolumeRenderSampler(*args, bench_tf(), N_SAMPLES, **kwargs)
+        elif kind == "iproj":
+            s = S.InterpolatedProjectionSampler(*args, N_SAMPLES, **kwargs)
         else:
             s = S.ProjectionSampler(*args, N_SAMPLES, **kwargs)
         t0 = time.perf_counter()
@@ -221,10 +224,11 @@ def cpu_render_sample(kind, n=256, res=512, threads=0, repeats=1):
     # exact sample count of the sample frame from the C oracle's counter
     img = np.zeros((res, res, 4))
     args, kwargs = sampler_call_args(cam, img, None)
-    oc = (O.VolumeRenderSampler(*args, bench_tf(), N_SAMPLES, **kwargs) if kind == "vr" else O.ProjectionSampler(*args, N_SAMPLES, **kwargs))
+    oc = (O.VolumeRenderSampler(*args, bench_tf(), N_SAMPLES, **kwargs) if kind == "vr" else
+          (O.InterpolatedProjectionSampler(*args, N_SAMPLES, **kwargs) if kind == "iproj" else O.ProjectionSampler(*args, N_SAMPLES, **kwargs)))
     oc(O.PartitionedGrid(0, [np.ascontiguousarray(data)], np.ones((n, n, n), "uint8"), np.zeros(3), np.ones(3), np.array([n] * 3, "int64")),
        num_threads=0)
-    samples = oc.cells * (N_SAMPLES if kind == "vr" else 1)
+    samples = oc.cells * (1 if kind == "proj" else N_SAMPLES)
     return {"seconds": best, "samples": samples, "kind": label, "cores": threads,
             "sample": "%d^3 brick @ %d^2, same view/tables/n_samples=%d, best of %d" % (n, res, N_SAMPLES, repeats)}
 
@@ -276,7 +280,7 @@ def run_ours(args):
     n, res, kind = WORKLOADS[args.workload]
     stream = torch.cuda.Stream(device=dev)
     ctx = D.Context(local, stream=stream.cuda_stream)
-    kcode = L.VOLUME_RENDER if kind == "vr" else L.PROJECTION
+    kcode = {"vr": L.VOLUME_RENDER, "proj": L.PROJECTION, "iproj": L.INTERPOLATED_PROJECTION}[kind]
 
     amr = args.workload in AMR_WORKLOADS
     with torch.cuda.stream(stream):
@@ -293,9 +297,10 @@ def run_ours(args):
             skw.pop("camera_data")
         skw["context"] = ctx
         sampler = (S.VolumeRenderSampler(*sargs, bench_tf(), N_SAMPLES, **skw) if kind == "vr"
-                   else S.ProjectionSampler(*sargs, N_SAMPLES, **skw))
+                   else (S.InterpolatedProjectionSampler(*sargs, N_SAMPLES, **skw) if kind == "iproj"
+                         else S.ProjectionSampler(*sargs, N_SAMPLES, **skw)))
         frame = sampler._frame
-        centred = 1 if kind == "vr" else 0
+        centred = 0 if kind == "proj" else 1
         if amr:
             # ---- nested-box AMR hierarchy -> kd-tree leaves of this rank's subtree, resident in HBM ----
             from yt_b200 import loaders
@@ -316,10 +321,10 @@ def run_ours(args):
             lo, hi, path = kd_slab(n, rank, world)
             vd = np.asarray(sargs[1], dtype=np.float64).ravel()[:3]
             pieces = split_slab(lo, hi, vd, centred)
-            bricks = D.BrickSet(ctx, len(pieces), 1, L.VERTEX_CENTRED if kind == "vr" else L.CELL_CENTRED, L.STORE_F32)
+            bricks = D.BrickSet(ctx, len(pieces), 1, L.CELL_CENTRED if kind == "proj" else L.VERTEX_CENTRED, L.STORE_F32)
             my_elems = 0.0
             for i, (plo, phi) in enumerate(pieces):
-                if kind == "vr":
+                if kind != "proj":
                     vol, pitch = synthetic.vertex_slab(n, plo, phi, SEED, dev), None
                 else:
                     vol, pitch = synthetic.cell_slab(n, plo, phi, SEED, dev)   # rows padded off the 4096-byte stride
@@ -476,7 +481,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 samples / f64 traversal", "data": "synthetic",
         "config": {"workload": args.workload, "cells": cells_desc, "image": [res, res], "sampler": kind,
-                   "n_samples": N_SAMPLES if kind == "vr" else 1, "lens": "perspective" if amr else "plane-parallel",
+                   "n_samples": 1 if kind == "proj" else N_SAMPLES, "lens": "perspective" if amr else "plane-parallel",
                    "view": "camera at (1.6,1.4,1.2) looking at the domain centre" if amr else "default corner camera, width 1.5",
                    "bricks_per_rank": n_bricks, "samples_per_frame": total_samples, "parallelism": "kd%d" % world,
                    "composite": ("none" if world == 1 else ("binary swap over NVLink peer memory, fp32 (A,B)" if peer and kind == "vr" else
