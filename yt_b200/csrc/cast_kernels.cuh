@@ -418,6 +418,115 @@ struct FastSampler {
     }
 
     // ------------------------------------------------------------------------------------------------
+    // The fused walk of the single-field InterpolatedProjectionSampler (image_samplers.pyx:372-402 inside
+    // grid_traversal.pyx:119-138): the step block of walk_colour with fp64 outputs, the next cell's 8 corners
+    // requested before the current cell is integrated, and the cell integrated in closed form (see cell()).
+    // The first sample's cell-local coordinate along a stepping axis is base + (t_mid - tmax_axis) * dc, base = 1
+    // (stepping up) or 0 (stepping down): the ray leaves the cell through that face at t = tmax_axis.
+    // ------------------------------------------------------------------------------------------------
+    __device__ __forceinline__ void walk_iproj(const WalkState &w)
+    {
+        const int ny = br->dims[1];
+        const int vsy = br->pitch_y, vsx = (ny + 1) * vsy;
+        double dcx[3], bse[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const double idds = br->idds[i];
+            dcx[i] = ray[(3 + i) * CTA_THREADS + threadIdx.x] * idds;
+            if (w.step[i] > 0) bse[i] = 1.0;
+            else if (w.step[i] < 0) bse[i] = 0.0;
+            else bse[i] = (ray[i * CTA_THREADS + threadIdx.x] - br->le[i]) * idds - (double)w.cur[i];
+        }
+        unsigned o = (unsigned)w.cur[0] * (unsigned)vsx + (unsigned)w.cur[1] * (unsigned)vsy + (unsigned)w.cur[2];
+        const int st0 = w.step[0] * vsx, st1 = w.step[1] * vsy, st2 = w.step[2];
+        double t0 = w.step[0] == 0 ? 1e30 : w.t0, t1 = w.step[1] == 0 ? 1e30 : w.t1, t2 = w.step[2] == 0 ? 1e30 : w.t2;
+        const double d0 = w.d0, d1 = w.d1, d2 = w.d2, max_t = w.max_t, inv_ns = prm->inv_ns;
+        int rem0 = w.rem0, rem1 = w.rem1, rem2 = w.rem2;
+        double enter_t = w.enter_t;
+        const T *data = (const T *)br->data[0];
+        const double nn = (double)n_samples;
+        const double S1 = 0.5 * nn * (nn - 1.0), S2 = nn * (nn - 1.0) * (2.0 * nn - 1.0) * (1.0 / 6.0), S3 = S1 * S1;
+        double a = acc[0];
+        T c[8], nx[8];
+        auto load8 = [&](T (&v)[8], const T *d) {
+            v[0] = __ldg(d); v[1] = __ldg(d + 1); v[2] = __ldg(d + vsy); v[3] = __ldg(d + vsy + 1);
+            v[4] = __ldg(d + vsx); v[5] = __ldg(d + vsx + 1); v[6] = __ldg(d + vsx + vsy); v[7] = __ldg(d + vsx + vsy + 1);
+        };
+        load8(c, data + o);
+        unsigned cont;
+        do {
+            double dt, q0, q1, q2;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred a01, a02, a12, n01, p0, p1, p2, pc, pm;\n\t"
+                ".reg .f64 tm, ex, dl, tmid;\n\t"
+                ".reg .s32 ds, rr;\n\t"
+                "setp.lt.f64 a01, %0, %1;\n\t"
+                "setp.lt.f64 a02, %0, %2;\n\t"
+                "setp.lt.f64 a12, %1, %2;\n\t"
+                "and.pred p0, a01, a02;\n\t"
+                "not.pred n01, a01;\n\t"
+                "and.pred p1, n01, a12;\n\t"
+                "or.pred p2, p0, p1;\n\t"
+                "selp.f64 tm, %1, %2, p1;\n\t"
+                "selp.f64 tm, %0, tm, p0;\n\t"
+                "setp.lt.f64 pm, tm, %16;\n\t"
+                "selp.f64 ex, tm, %16, pm;\n\t"
+                "sub.rn.f64 dl, ex, %7;\n\t"
+                "mul.rn.f64 %8, dl, %17;\n\t"
+                "fma.rn.f64 tmid, %8, 0d3FE0000000000000, %7;\n\t"
+                "sub.rn.f64 %9, tmid, %0;\n\t"
+                "sub.rn.f64 %10, tmid, %1;\n\t"
+                "sub.rn.f64 %11, tmid, %2;\n\t"
+                "@p0 add.rn.f64 %0, %0, %13;\n\t"
+                "@p1 add.rn.f64 %1, %1, %14;\n\t"
+                "@!p2 add.rn.f64 %2, %2, %15;\n\t"
+                "@p0 add.s32 %3, %3, -1;\n\t"
+                "@p1 add.s32 %4, %4, -1;\n\t"
+                "@!p2 add.s32 %5, %5, -1;\n\t"
+                "selp.b32 ds, %19, %20, p1;\n\t"
+                "selp.b32 ds, %18, ds, p0;\n\t"
+                "add.s32 %6, %6, ds;\n\t"
+                "or.b32 rr, %3, %4;\n\t"
+                "or.b32 rr, rr, %5;\n\t"
+                "setp.ge.s32 pc, rr, 0;\n\t"
+                "setp.ge.f64 pm, tm, %16;\n\t"
+                "not.pred pm, pm;\n\t"
+                "and.pred pc, pc, pm;\n\t"
+                "selp.u32 %12, 1, 0, pc;\n\t"
+                "mov.f64 %7, tm;\n\t"
+                "}"
+                : "+d"(t0), "+d"(t1), "+d"(t2), "+r"(rem0), "+r"(rem1), "+r"(rem2), "+r"(o), "+d"(enter_t),
+                  "=&d"(dt), "=&d"(q0), "=&d"(q1), "=&d"(q2), "=&r"(cont)
+                : "d"(d0), "d"(d1), "d"(d2), "d"(max_t), "d"(inv_ns), "r"(st0), "r"(st1), "r"(st2));
+            if (cont) load8(nx, data + o);
+            {
+                const double xd = fma(q0, dcx[0], bse[0]), yd = fma(q1, dcx[1], bse[1]), zd = fma(q2, dcx[2], bse[2]);
+                const double sxd = dcx[0] * dt, syd = dcx[1] * dt, szd = dcx[2] * dt;
+                const double a0 = (double)c[0], a1 = (double)c[1], b0 = (double)c[2], b1 = (double)c[3];
+                const double e0 = (double)c[4], e1 = (double)c[5], f0 = (double)c[6], f1 = (double)c[7];
+                const double pa = fma(zd, a1 - a0, a0), qa = szd * (a1 - a0);
+                const double pb = fma(zd, b1 - b0, b0), qb = szd * (b1 - b0);
+                const double pe = fma(zd, e1 - e0, e0), qe = szd * (e1 - e0);
+                const double pf = fma(zd, f1 - f0, f0), qf = szd * (f1 - f0);
+                const double d0p = pb - pa, d0q = qb - qa, d1p = pf - pe, d1q = qf - qe;
+                const double u00 = fma(yd, d0p, pa), u01 = fma(syd, d0p, fma(yd, d0q, qa)), u02 = syd * d0q;
+                const double u10 = fma(yd, d1p, pe), u11 = fma(syd, d1p, fma(yd, d1q, qe)), u12 = syd * d1q;
+                const double g0 = u10 - u00, g1 = u11 - u01, g2 = u12 - u02;
+                const double k0 = fma(xd, g0, u00);
+                const double k1 = fma(sxd, g0, fma(xd, g1, u01));
+                const double k2 = fma(sxd, g1, fma(xd, g2, u02));
+                const double k3 = sxd * g2;
+                const double sum = fma(k3, S3, fma(k2, S2, fma(k1, S1, k0 * nn)));
+                a = fma(sum, dt, a);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) c[k] = nx[k];
+        } while (cont);
+        acc[0] = a;
+    }
+
+    // ------------------------------------------------------------------------------------------------
     // The fused walk of the single-field ProjectionSampler (image_samplers.pyx:327-343 inside
     // grid_traversal.pyx:119-138).  Same cells and the same (enter_t, exit_t) as walk_brick.  ncu r01e on
     // the generic loop: 75 instructions per cell, the data pointer re-read from the brick table for every
@@ -827,6 +936,9 @@ cast_kernel(const __grid_constant__ CastParams p)
                     } else {
                         cast_colour(g, vp, vd, max_t, smp, masked);
                     }
+                } else if constexpr (!EXACT && KIND == KIND_IPROJ && NF1) {
+                    WalkState w;
+                    if (walk_setup(g, vp, vd, max_t, smp, w)) smp.walk_iproj(w);
                 } else if constexpr (!EXACT && KIND == KIND_PROJ) {
                     // image_samplers.pyx:337-343 sums the first min(4, n_fields) fields
                     WalkState w;
