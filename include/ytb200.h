@@ -186,12 +186,13 @@ int ytb200_frame_cast_partial_f32(ytb200_frame *f, int kind, const ytb200_bricks
 
 /* ---- binary swap over NVLink peer memory: AMRKDTree.reduce_tree_images (amr_kdtree.py:297-323) -------
  * One process per GPU.  Every rank creates a swap object (one cudaMalloc'd slab holding the partial-image buffers of
- * all rounds and the ordering flags), publishes its 64-byte CUDA IPC handle (and that of its frame image, the
- * destination of the final strips) to the other ranks by any host channel, and opens theirs.  A frame is then
+ * all rounds, the final image and the ordering flags), publishes its 64-byte CUDA IPC handle to the other ranks by
+ * any host channel, and opens theirs.  A frame is then
  *   ytb200_frame_cast_partial[_f32](..., ytb200_swap_partial(swap), ...);  ytb200_swap_composite(swap, frame, broadcast);
  * Each swap round is ONE kernel that reads the partner's half straight out of its HBM through the peer mapping and
  * composes it with the local half (A = A2 + B2*A1, B = B2*B1); the final strips are applied to the
- * initial colours and stored directly into rank 0's (or, with `broadcast`, every rank's) frame image.  No NCCL call,
+ * initial colours and stored directly into rank 0's (or, with `broadcast`, every rank's) slab, from where the
+ * destination copies the finished image into the frame passed to ytb200_swap_composite.  No NCCL call,
  * no receive buffers; cross-GPU ordering is a sequence number per round pushed into the consumer's memory.
  * `bytes_per_pixel`: 32 (fp32 A,B -- cast with _f32) or 64 (fp64 A,B). */
 /* Multi-GPU frames with host inputs: bind the caller's PAGE-LOCKED image (initial colours) and z-buffer (NULL = ones)
@@ -203,8 +204,7 @@ typedef struct ytb200_swap ytb200_swap;
 int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, int world, int bytes_per_pixel, ytb200_swap **out);
 int ytb200_swap_destroy(ytb200_swap *swap);
 int ytb200_swap_handle(ytb200_swap *swap, void *handle64_out);
-int ytb200_frame_image_handle(ytb200_frame *f, void *handle64_out);
-int ytb200_swap_open(ytb200_swap *swap, int peer_rank, const void *slab_handle64, const void *image_handle64_or_null);
+int ytb200_swap_open(ytb200_swap *swap, int peer_rank, const void *slab_handle64);
 /* The schedule of this rank (yt_b200.parallel.plan_binary_swap): per round the partner, the pixel region [p0,p1) both
  * partners hold, the half [k0,k1) this rank keeps, and whether this rank's content is applied first (the far side
  * of the kd split seen from the viewpoint, amr_kdtools.pyx:708-755). */

@@ -86,8 +86,7 @@ SIGNATURES = {
     "ytb200_swap_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ytb200_swap_destroy": (C.c_int, [C.c_void_p]),
     "ytb200_swap_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "ytb200_frame_image_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "ytb200_swap_open": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "ytb200_swap_open": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ytb200_swap_plan": (C.c_int, [C.c_void_p, C.c_int, i32p, i64p, i64p, i64p, i64p, i32p]),
     "ytb200_swap_partial": (C.c_void_p, [C.c_void_p]),
     "ytb200_swap_composite": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

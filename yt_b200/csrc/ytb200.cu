@@ -961,6 +961,8 @@ extern "C" int ytb200_partial_apply(ytb200_ctx *ctx, const double *partial, doub
 //                       partner), final[w] at 16 + w "rank w has stored its strip of frame `seq` into my image",
 //                       error word at 56
 //   two parity sets of buffers: buffer_0 (n_pixels, the cast's output), buffer_{j+1} (ceil(cap_j / 2)) ...
+//   the final image (n_pixels x double4): every rank stores its finished strip into the destination ranks' copy of
+//   this region, which each destination then copies into its own frame -- frames can come and go, the slab stays
 // The layout is identical on every rank, so a peer's buffer address is its slab base + the same offset.
 struct SwapRound { int partner; int64_t p0, p1, k0, k1; int earlier; };
 
@@ -972,7 +974,7 @@ struct ytb200_swap {
     size_t slab_bytes = 0, set_bytes = 0;
     std::vector<size_t> buf_off;             // offset of buffer_j inside one parity set
     std::vector<unsigned char *> peer_slab;  // [world], own slab at [rank]
-    std::vector<double *> peer_image;        // [world], frame images of the destinations (nullptr if unknown)
+    size_t final_off = 0;                    // offset of the final-image region
     std::vector<SwapRound> rounds;
     unsigned long long seq = 0;
 };
@@ -1001,12 +1003,12 @@ extern "C" int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, i
         cap = (cap + 1) / 2;
     }
     s->set_bytes = off;
-    s->slab_bytes = SWAP_HDR + 2 * off;
+    s->final_off = SWAP_HDR + 2 * off;
+    s->slab_bytes = s->final_off + (size_t)n_pixels * sizeof(double4);
     CK(cudaMalloc(&s->slab, s->slab_bytes));
     CK(cudaMemsetAsync(s->slab, 0, SWAP_HDR, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     s->peer_slab.assign((size_t)world, nullptr);
-    s->peer_image.assign((size_t)world, nullptr);
     s->peer_slab[(size_t)rank] = s->slab;
     *out = s;
     return 0;
@@ -1020,7 +1022,6 @@ extern "C" int ytb200_swap_destroy(ytb200_swap *s)
     for (int w = 0; w < s->world; w++) {
         if (w == s->rank) continue;
         if (s->peer_slab[(size_t)w]) cudaIpcCloseMemHandle(s->peer_slab[(size_t)w]);
-        if (s->peer_image[(size_t)w]) cudaIpcCloseMemHandle(s->peer_image[(size_t)w]);
     }
     cudaFree(s->slab);
     delete s;
@@ -1038,17 +1039,7 @@ extern "C" int ytb200_swap_handle(ytb200_swap *s, void *handle64)
     return 0;
 }
 
-extern "C" int ytb200_frame_image_handle(ytb200_frame *f, void *handle64)
-{
-    if (!f || !handle64) return fail(E_ARG, "NULL argument");
-    DeviceGuard g(f->ctx->device);
-    cudaIpcMemHandle_t h;
-    CK(cudaIpcGetMemHandle(&h, f->image));
-    memcpy(handle64, &h, 64);
-    return 0;
-}
-
-extern "C" int ytb200_swap_open(ytb200_swap *s, int peer_rank, const void *slab_handle64, const void *image_handle64)
+extern "C" int ytb200_swap_open(ytb200_swap *s, int peer_rank, const void *slab_handle64)
 {
     if (!s || !slab_handle64) return fail(E_ARG, "NULL argument");
     if (peer_rank < 0 || peer_rank >= s->world || peer_rank == s->rank) return fail(E_ARG, "bad peer rank %d", peer_rank);
@@ -1058,11 +1049,6 @@ extern "C" int ytb200_swap_open(ytb200_swap *s, int peer_rank, const void *slab_
     memcpy(&h, slab_handle64, 64);
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     s->peer_slab[(size_t)peer_rank] = static_cast<unsigned char *>(p);
-    if (image_handle64) {
-        memcpy(&h, image_handle64, 64);
-        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-        s->peer_image[(size_t)peer_rank] = static_cast<double *>(p);
-    }
     return 0;
 }
 
@@ -1126,16 +1112,19 @@ static int swap_run(ytb200_swap *s, ytb200_frame *f, int broadcast)
     SwapSignal fin{};
     for (int w = 0; w < s->world; w++) {
         if (!broadcast && w != 0) continue;
-        double *img = (w == s->rank) ? f->image : s->peer_image[(size_t)w];
-        if (!img) return fail(E_STATE, "image of destination rank %d not opened", w);
-        dst.img[dst.n++] = reinterpret_cast<double4 *>(img) + f0;
+        if (!s->peer_slab[(size_t)w]) return fail(E_STATE, "destination rank %d not opened", w);
+        dst.img[dst.n++] = reinterpret_cast<double4 *>(s->peer_slab[(size_t)w] + s->final_off) + f0;
         fin.flag[fin.n++] = swap_flag(s->peer_slab[(size_t)w], 16 + s->rank);
     }
     const long long nf = (long long)(f1 - f0);
     if (nf > 0 && dst.n > 0)
         apply_store_kernel<V4><<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(buf(s->slab, s->k), reinterpret_cast<const double4 *>(f->c0_in ? f->c0_in : f->image) + f0, dst, nf);
     if (fin.n > 0) swap_signal_kernel<<<1, 32, 0, st>>>(fin, seq);
-    if (broadcast || s->rank == 0) swap_wait_kernel<<<1, 32, 0, st>>>(swap_flag(s->slab, 16), s->world, seq, err);
+    if (broadcast || s->rank == 0) {
+        // every strip of this frame has landed in my final-image region: hand it to the frame
+        swap_wait_kernel<<<1, 32, 0, st>>>(swap_flag(s->slab, 16), s->world, seq, err);
+        CK(cudaMemcpyAsync(f->image, s->slab + s->final_off, (size_t)s->npx * sizeof(double4), cudaMemcpyDeviceToDevice, st));
+    }
     CK(cudaGetLastError());
     return 0;
 }

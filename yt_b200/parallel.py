@@ -222,7 +222,8 @@ class BinarySwap:
 class PeerSwap:
     """Binary swap over NVLink peer memory (``ytb200_swap_*``): the same schedule as :class:`BinarySwap`, but each
     round is one CUDA kernel that reads the partner's half directly from its HBM, and the final strips are stored
-    straight into the destination frame(s).  torch.distributed is used once, at construction, to pass the CUDA IPC
+    straight into the destination ranks' slabs (then copied into the frame given to ``composite``).  The object is
+    independent of any one frame: create it once per (image size, world) and ``set_view`` it when the camera moves.  torch.distributed is used once, at construction, to pass the CUDA IPC
     handles around; a frame issues no collective at all.
 
         swap = PeerSwap(ctx, frame, path, viewpoint, rank, world)
@@ -241,14 +242,13 @@ class PeerSwap:
         self.handle = h
         self._fin = weakref.finalize(self, lib.ytb200_swap_destroy, h)
         if world > 1:
-            mine_slab, mine_img = C.create_string_buffer(64), C.create_string_buffer(64)
+            mine_slab = C.create_string_buffer(64)
             L.check(lib.ytb200_swap_handle(h, mine_slab))
-            L.check(lib.ytb200_frame_image_handle(frame.handle, mine_img))
             everyone = [None] * world
-            dist.all_gather_object(everyone, (rank, mine_slab.raw, mine_img.raw), group=group)
-            for r, slab, img in everyone:
+            dist.all_gather_object(everyone, (rank, mine_slab.raw), group=group)
+            for r, slab in everyone:
                 if r != rank:
-                    L.check(lib.ytb200_swap_open(h, int(r), slab, img))
+                    L.check(lib.ytb200_swap_open(h, int(r), slab))
         self.set_view(path, viewpoint)
         self.launches_per_composite = 3 * len(self.rounds) + 3
 

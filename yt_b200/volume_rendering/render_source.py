@@ -266,8 +266,14 @@ class KDTreeVolumeSource(VolumeSource):
                 swap = BinarySwap(self.sampler._ctx, nx, ny, self.volume.kd_path(), camera.lens.viewpoint,
                                   self.volume.comm_rank, self.volume.comm_size)
             else:
-                swap = self.sampler.peer_swap(self.volume.kd_path(), camera.lens.viewpoint,
-                                              self.volume.comm_rank, self.volume.comm_size)
+                # one compositor per (image size, partial type): its IPC-shared slab outlives the per-render samplers
+                key = (nx, ny, self.sampler.kind, self.sampler._precision, self.volume.comm_size)
+                cache = self.__dict__.setdefault("_peer_swaps", {})
+                if key not in cache:
+                    cache[key] = self.sampler.peer_swap(self.volume.kd_path(), camera.lens.viewpoint,
+                                                        self.volume.comm_rank, self.volume.comm_size)
+                swap = cache[key]
+                swap.set_view(self.volume.kd_path(), camera.lens.viewpoint)
             self.sampler.flush_parallel(swap, broadcast=True)
         elif self.batched:
             bricks = self.volume.device_bricks(self.sampler._ctx, self.sampler._storage)
