@@ -286,58 +286,68 @@ struct FastSampler {
     // 445 instructions per cell were not samples, and 20 % of the stall cycles waited for corner loads):
     //   * one PTX block per cell does the axis choice, exit_t, the sample spacing and the step with
     //     PREDICATED adds (nvcc turns `if (is0) t0 += d0` into an add plus two selects);
-    //   * the cell-local coordinate of the first sample needs no running origin: along a stepping axis
-    //     it is base + (t_mid - tmax_axis) * dc with base = 1 (stepping up) or 0 (stepping down), because
-    //     the ray leaves the cell at t = tmax_axis through that face; the cancellation t_mid - tmax is
-    //     done in fp64 (H13), the rest in fp32;
-    //   * the 8 corners of the NEXT cell are requested before the current cell is sampled, so their
+    //   * CORNER REUSE: consecutive cells of a ray share a face, so a step needs 4 new corner loads, not 8 (the
+    //     cast sits on the L1 LSU data pipe and the 8 corner LDG were a third of its wavefronts).  The cell is kept
+    //     in RAY-ORIENTED corner order -- corner (i,j,k) is the vertex at origin + i*S0 + j*S1 + k*S2 with
+    //     S_a = step_a * stride_a (entry side 0, exit side 1 on every axis) -- so a step along axis a is always
+    //     "exit face becomes entry face, load the new exit face" whatever the sign of the direction: 12 selects;
+    //   * the cell coordinates are mirrored with the corners (x' = 1 - x on an axis the ray descends), and need no
+    //     running origin: the ray leaves the cell through the exit face of a stepping axis at t = tmax_axis, so
+    //     the first sample sits at 1 + (t_mid - tmax_axis) * |dc|; the cancellation t_mid - tmax is done in fp64
+    //     (H13), the rest in fp32;
+    //   * the 4 corners of the NEXT cell's exit face are requested before the current cell is sampled, so their
     //     latency hides behind ~300 sample instructions.
+    // r01zi: 44.6 -> 43.8 ms on the north-star frame against the walk that loaded all 8 corners of every cell.
     // ------------------------------------------------------------------------------------------------
     template <bool MASKED>
     __device__ __forceinline__ void walk_colour(const WalkState &w)
     {
         const int ny = br->dims[1], nz = br->dims[2];
-        // (plane pitch = rows per plane * row pitch by construction; written this way the compiler keeps the relation
-        // between the two strides -- loading both cost 3 % of the north-star frame)
         const int vsy = br->pitch_y, vsx = (ny + 1) * vsy;
         float dcx[3], bse[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const double idds = br->idds[i];
             const double vdi = ray[(3 + i) * CTA_THREADS + threadIdx.x];
-            dcx[i] = (float)(vdi * idds);
-            if (w.step[i] > 0) bse[i] = 1.f;
-            else if (w.step[i] < 0) bse[i] = 0.f;
+            dcx[i] = fabsf((float)(vdi * idds));
+            if (w.step[i] != 0) bse[i] = 1.f;
             else bse[i] = (float)((ray[i * CTA_THREADS + threadIdx.x] - br->le[i]) * idds - (double)w.cur[i]);
         }
-        unsigned o = (unsigned)w.cur[0] * (unsigned)vsx + (unsigned)w.cur[1] * (unsigned)vsy + (unsigned)w.cur[2];
-        const int st0 = w.step[0] * vsx, st1 = w.step[1] * vsy, st2 = w.step[2];
+        // ray-oriented origin of the start cell and signed strides (an axis the ray does not move along keeps +stride)
+        const int S0 = w.step[0] < 0 ? -vsx : vsx, S1 = w.step[1] < 0 ? -vsy : vsy, S2 = w.step[2] < 0 ? -1 : 1;
+        unsigned o = (unsigned)(w.cur[0] + (w.step[0] < 0)) * (unsigned)vsx + (unsigned)(w.cur[1] + (w.step[1] < 0)) * (unsigned)vsy +
+                     (unsigned)(w.cur[2] + (w.step[2] < 0));
         unsigned mo = 0;
         int ms0 = 0, ms1 = 0;
         if (MASKED) {
             mo = ((unsigned)w.cur[0] * (unsigned)ny + (unsigned)w.cur[1]) * (unsigned)nz + (unsigned)w.cur[2];
             ms0 = w.step[0] * ny * nz; ms1 = w.step[1] * nz;
         }
-        // an axis the ray does not move along keeps tmax = 1e60 in the reference; 1e30 is as unreachable and
-        // keeps (float)(t_mid - tmax) finite (times dc = 0 it contributes nothing)
         double t0 = w.step[0] == 0 ? 1e30 : w.t0, t1 = w.step[1] == 0 ? 1e30 : w.t1, t2 = w.step[2] == 0 ? 1e30 : w.t2;
         const double d0 = w.d0, d1 = w.d1, d2 = w.d2, max_t = w.max_t, inv_ns = prm->inv_ns;
         int rem0 = w.rem0, rem1 = w.rem1, rem2 = w.rem2;
         double enter_t = w.enter_t;
         const T *data = (const T *)br->data[0];
-        RawCorners cur_c;
-        load_raw_corners(cur_c, data + o, vsx, vsy);
+        // c[i][j][k] in ray-oriented order, named as RawCorners names them: a=c00k, b=c01k, e=c10k, f=c11k
+        float a0, a1, b0, b1, e0, e1, f0, f1;
+        {
+            const T *d = data + o;
+            a0 = (float)__ldg(d); a1 = (float)__ldg(d + S2);
+            b0 = (float)__ldg(d + S1); b1 = (float)__ldg(d + S1 + S2);
+            e0 = (float)__ldg(d + S0); e1 = (float)__ldg(d + S0 + S2);
+            f0 = (float)__ldg(d + S0 + S1); f1 = (float)__ldg(d + S0 + S1 + S2);
+        }
         unsigned cont;
         do {
             const unsigned mo_cur = mo;
             float dt, q0, q1, q2;
-            unsigned axis;
+            unsigned axis, fo;
+            int U, V;
             asm volatile(
                 "{\n\t"
                 ".reg .pred a01, a02, a12, n01, p0, p1, p2, pc, pm;\n\t"
                 ".reg .f64 tm, ex, dl, dt, tmid, q;\n\t"
                 ".reg .s32 ds, rr;\n\t"
-                // axis of the smallest tmax, reference tie rule (grid_traversal.pyx:122-131)
                 "setp.lt.f64 a01, %0, %1;\n\t"
                 "setp.lt.f64 a02, %0, %2;\n\t"
                 "setp.lt.f64 a12, %1, %2;\n\t"
@@ -347,11 +357,10 @@ struct FastSampler {
                 "or.pred p2, p0, p1;\n\t"            // p2 == NOT (axis 2)
                 "selp.f64 tm, %1, %2, p1;\n\t"
                 "selp.f64 tm, %0, tm, p0;\n\t"
-                "setp.lt.f64 pm, tm, %17;\n\t"
-                "selp.f64 ex, tm, %17, pm;\n\t"       // exit_t = tm < max_t ? tm : max_t
-                // sample spacing and the first sample's distance to each exit face (fp64 cancellation)
+                "setp.lt.f64 pm, tm, %20;\n\t"
+                "selp.f64 ex, tm, %20, pm;\n\t"
                 "sub.rn.f64 dl, ex, %7;\n\t"
-                "mul.rn.f64 dt, dl, %18;\n\t"
+                "mul.rn.f64 dt, dl, %21;\n\t"
                 "fma.rn.f64 tmid, dt, 0d3FE0000000000000, %7;\n\t"
                 "cvt.rn.f32.f64 %8, dt;\n\t"
                 "sub.rn.f64 q, tmid, %0;\n\t"
@@ -360,47 +369,50 @@ struct FastSampler {
                 "cvt.rn.f32.f64 %10, q;\n\t"
                 "sub.rn.f64 q, tmid, %2;\n\t"
                 "cvt.rn.f32.f64 %11, q;\n\t"
-                // the step: cur[i] += step[i]; enter_t = tmax[i]; tmax[i] += tdelta[i]
-                "@p0 add.rn.f64 %0, %0, %14;\n\t"
-                "@p1 add.rn.f64 %1, %1, %15;\n\t"
-                "@!p2 add.rn.f64 %2, %2, %16;\n\t"
+                "@p0 add.rn.f64 %0, %0, %17;\n\t"
+                "@p1 add.rn.f64 %1, %1, %18;\n\t"
+                "@!p2 add.rn.f64 %2, %2, %19;\n\t"
                 "@p0 add.s32 %3, %3, -1;\n\t"
                 "@p1 add.s32 %4, %4, -1;\n\t"
                 "@!p2 add.s32 %5, %5, -1;\n\t"
-                "selp.b32 ds, %20, %21, p1;\n\t"
-                "selp.b32 ds, %19, ds, p0;\n\t"
+                "selp.b32 ds, %23, %24, p1;\n\t"
+                "selp.b32 ds, %22, ds, p0;\n\t"
                 "add.s32 %6, %6, ds;\n\t"
+                "add.s32 %14, %6, ds;\n\t"          // origin of the new cell's exit face
+                "selp.b32 %15, %24, %23, p2;\n\t"   // in-face strides: (S2,S1) axis 0, (S2,S0) axis 1, (S1,S0) axis 2
+                "selp.b32 %16, %23, %22, p0;\n\t"
                 "selp.u32 %13, 1, 2, p1;\n\t"
                 "selp.u32 %13, 0, %13, p0;\n\t"
-                // go on while the stepped index is inside the brick and enter_t < max_t (NaN goes on, like the reference)
                 "or.b32 rr, %3, %4;\n\t"
                 "or.b32 rr, rr, %5;\n\t"
                 "setp.ge.s32 pc, rr, 0;\n\t"
-                "setp.ge.f64 pm, tm, %17;\n\t"
+                "setp.ge.f64 pm, tm, %20;\n\t"
                 "not.pred pm, pm;\n\t"
                 "and.pred pc, pc, pm;\n\t"
                 "selp.u32 %12, 1, 0, pc;\n\t"
                 "mov.f64 %7, tm;\n\t"
                 "}"
                 : "+d"(t0), "+d"(t1), "+d"(t2), "+r"(rem0), "+r"(rem1), "+r"(rem2), "+r"(o), "+d"(enter_t),
-                  "=f"(dt), "=f"(q0), "=f"(q1), "=f"(q2), "=r"(cont), "=r"(axis)
-                : "d"(d0), "d"(d1), "d"(d2), "d"(max_t), "d"(inv_ns), "r"(st0), "r"(st1), "r"(st2));
-            if (MASKED) mo += (unsigned)(axis == 0 ? ms0 : (axis == 1 ? ms1 : st2));
-            // request the next cell's corners now; they are consumed one iteration later
-            RawCorners nxt_c;
-            if (cont) load_raw_corners(nxt_c, data + o, vsx, vsy);
+                  "=f"(dt), "=f"(q0), "=f"(q1), "=f"(q2), "=r"(cont), "=r"(axis), "=r"(fo), "=r"(U), "=r"(V)
+                : "d"(d0), "d"(d1), "d"(d2), "d"(max_t), "d"(inv_ns), "r"(S0), "r"(S1), "r"(S2));
+            if (MASKED) mo += (unsigned)(axis == 0 ? ms0 : (axis == 1 ? ms1 : w.step[2]));
+            // request the 4 corners of the next cell's exit face now; they are consumed one iteration later
+            float L0, L1, L2, L3;
+            if (cont) {
+                L0 = (float)__ldg(data + fo); L1 = (float)__ldg(data + (fo + (unsigned)U));
+                L2 = (float)__ldg(data + (fo + (unsigned)V)); L3 = (float)__ldg(data + (fo + (unsigned)U + (unsigned)V));
+            }
             bool sample = true;
             if (MASKED) sample = mask[mo_cur] == 1;
             if (sample) {
+                RawCorners cur_c;
+                cur_c.a0 = a0; cur_c.a1 = a1; cur_c.b0 = b0; cur_c.b1 = b1; cur_c.e0 = e0; cur_c.e1 = e1; cur_c.f0 = f0; cur_c.f1 = f1;
                 CornersP cp;
                 const bool all_zero = rows_from_raw(cp, cur_c, ct);
-                // exact zeros are rejected by FIT_get_value (isnormal); a sample is exactly 0 essentially only
-                // where the data are (zero padding), i.e. where all 8 corners are: test the cell, not every sample
                 if (!(tfm_zero_inside(TFM) && all_zero)) {
                     const float x = fmaf(q0, dcx[0], bse[0]), y = fmaf(q1, dcx[1], bse[1]), z = fmaf(q2, dcx[2], bse[2]);
                     const float sxs = dcx[0] * dt, sys = dcx[1] * dt, szs = dcx[2] * dt;
                     float m;
-                    // dt * (largest table product) <= 1: the max(1 - dt*T, 0) clamps cannot fire in this cell
                     const bool clamp = !(dt * tf->colour_clamp_bound <= 1.f);
                     if (tf->colour_delta) {
                         if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM), true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
@@ -409,11 +421,19 @@ struct FastSampler {
                         if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM), false>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
                         else m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM), false>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
                     }
-                    // some sample sat within fp32 rounding of a table bound (see CarefulSampler)
                     if (tfm_edge(TFM)) doubt = doubt || (m < tf->colour_band);
                 }
             }
-            cur_c = nxt_c;
+            // the exit face of the step axis becomes the entry face; the loaded face is the new exit face
+            const bool x0 = axis == 0, x1 = axis == 1, x2 = axis == 2;
+            const float n_a0 = x0 ? e0 : (x1 ? b0 : a1);
+            const float n_e0 = x0 ? L0 : (x1 ? f0 : e1);
+            const float n_b0 = x0 ? f0 : (x1 ? L0 : b1);
+            const float n_a1 = x0 ? e1 : (x1 ? b1 : L0);
+            const float n_f0 = x2 ? f1 : L2;
+            const float n_e1 = x0 ? L1 : (x1 ? f1 : L2);
+            const float n_b1 = x0 ? f1 : L1;
+            a0 = n_a0; e0 = n_e0; b0 = n_b0; a1 = n_a1; f0 = n_f0; e1 = n_e1; b1 = n_b1; f1 = L3;
         } while (cont);
     }
 

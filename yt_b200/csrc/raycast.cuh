@@ -528,15 +528,6 @@ struct RawCorners {
     float a0, e0, a1, e1, b0, f0, b1, f1;
 };
 
-template <typename T>
-__device__ __forceinline__ void load_raw_corners(RawCorners &r, const T *d, int sx, int sy)
-{
-    r.a0 = (float)__ldg(d); r.a1 = (float)__ldg(d + 1);
-    r.b0 = (float)__ldg(d + sy); r.b1 = (float)__ldg(d + sy + 1);
-    r.e0 = (float)__ldg(d + sx); r.e1 = (float)__ldg(d + sx + 1);
-    r.f0 = (float)__ldg(d + sx + sy); r.f1 = (float)__ldg(d + sx + sy + 1);
-}
-
 // Returns whether all 8 corners are exactly (+-)0.
 __device__ __forceinline__ bool rows_from_raw(CornersP &c, const RawCorners &r, const ColourTable &ct)
 {
