@@ -236,6 +236,27 @@ int ytb200_render(ytb200_frame *f, int kind, const ytb200_brickset *set, const i
                   const ytb200_tf *tf, int n_samples, int precision, const double *zbuffer_host,
                   double *image_host_inout, ytb200_stats *stats);
 
+/* ---- octree path (OctreeVolumeSource) ---------------------------------------------------------
+ * Replaces yt/utilities/lib/_octree_raytracing.pyx:15-34 (_OctreeRayTracing: Octree<int> of
+ * _octree_raytracing.hpp, built with insert_node per cell) and ImageSampler.cast_through_octree,
+ * image_samplers.pyx:202-299: every pixel's ray (per-pixel vp_pos / vp_dir) walks the tree front to back
+ * (cast_ray / proc_subtree, hpp:199-343) and the sampler's per-cell body runs on each terminal cell met, over
+ * the cell's 14 doubles -- 8 vertex values, left edge, right edge (render_source.py:669-680).  The z-buffer is
+ * not consulted (as in the reference).  All arithmetic fp64 in the reference's order. */
+typedef struct ytb200_octree ytb200_octree;
+/* _OctreeRayTracing.__init__(LE, RE, depth) */
+int ytb200_octree_create(ytb200_ctx *ctx, int max_depth, const double left_edge[3], const double right_edge[3],
+                         ytb200_octree **out);
+int ytb200_octree_destroy(ytb200_octree *oct);
+/* _OctreeRayTracing.add_nodes(ipos (n,3) int32, lvl (n) int32, key (n) int32) */
+int ytb200_octree_add_nodes(ytb200_octree *oct, int64_t n, const int32_t *ipos, const int32_t *lvl, const int32_t *key);
+int64_t ytb200_octree_node_count(const ytb200_octree *oct);
+/* the PartitionedGrid payload of OctreeVolumeSource.render: HOST (n_cells, 14) fp64, uploaded once */
+int ytb200_octree_set_cells(ytb200_octree *oct, int64_t n_cells, const double *cells_host);
+/* sampler(pg, oct=octree) with volume_method == "Octree": casts into the frame's device image.  Asynchronous. */
+int ytb200_frame_cast_octree(ytb200_frame *f, int kind, ytb200_octree *oct, const ytb200_tf *tf, int n_samples,
+                             ytb200_stats *stats);
+
 /* ---- AMR kd-tree: brick decomposition + view-order traversal, host side -----------------------
  * Replaces yt/utilities/lib/amr_kdtools.pyx (Node.add_grids/insert_grids/split_grids/
  * kdtree_get_choices 136-458,756-823; kd_traverse/viewpoint_traverse 102-111,612-622,708-755) and

@@ -62,6 +62,20 @@ def lib():
         i64p = C.POINTER(C.c_int64)
         _lib.orc_ghost_zone_interpolate.restype = None
         _lib.orc_ghost_zone_interpolate.argtypes = [C.c_int, dp, i64p, dp, dp, i64p, dp]
+        i32p = C.POINTER(C.c_int32)
+        _lib.orc_octree_create.restype = C.c_void_p
+        _lib.orc_octree_create.argtypes = [C.c_int, dp, dp]
+        _lib.orc_octree_destroy.restype = None
+        _lib.orc_octree_destroy.argtypes = [C.c_void_p]
+        _lib.orc_octree_add_nodes.restype = C.c_int
+        _lib.orc_octree_add_nodes.argtypes = [C.c_void_p, C.c_int64, i32p, i32p, i32p]
+        _lib.orc_octree_node_count.restype = C.c_int64
+        _lib.orc_octree_node_count.argtypes = [C.c_void_p]
+        _lib.orc_octree_cast_ray.restype = C.c_int64
+        _lib.orc_octree_cast_ray.argtypes = [C.c_void_p, dp, dp, C.c_int64, i32p, dp]
+        _lib.orc_cast_octree.restype = C.c_int64
+        _lib.orc_cast_octree.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_void_p,
+                                         C.POINTER(_TFDesc), C.c_int, C.c_int]
     return _lib
 
 
@@ -119,7 +133,24 @@ class ImageSampler:
         self._tf = None
         self.cells = 0
 
-    def __call__(self, pg, num_threads=0):
+    def cast_through_octree(self, pg, oct, num_threads=0):
+        """image_samplers.pyx:202-299.  `pg` holds one field of shape (n_cells, 14, 1): 8 vertex values, left edge,
+        right edge per cell (render_source.py:669-680); the rays are the per-pixel (nx, ny, 3) arrays."""
+        nx, ny = self.aimage.shape[:2]
+        if self.vp_pos.shape != (nx, ny, 3) or self.vp_dir.shape != (nx, ny, 3):
+            raise ValueError("cast_through_octree reads per-pixel vp_pos / vp_dir of shape (nx, ny, 3)")
+        cells = np.ascontiguousarray(pg.my_data[0], dtype="float64").reshape(-1, 14)
+        n = lib().orc_cast_octree(self.kind, nx, ny, _dptr(self.vp_pos), _dptr(self.vp_dir), _dptr(self.aimage),
+                                  _dptr(cells), oct._h, C.byref(self._tf) if self._tf is not None else None,
+                                  int(self.n_samples), int(num_threads))
+        if n < 0:
+            raise RuntimeError("oracle error %d" % n)
+        self.cells += n
+        return None
+
+    def __call__(self, pg, num_threads=0, oct=None):
+        if self.volume_method == "Octree":
+            return self.cast_through_octree(pg, oct, num_threads=num_threads)
         if self.volume_method != "KDTree":
             raise NotImplementedError(
                 'Volume rendering has not been implemented for method: "%s"' % self.volume_method)
@@ -191,6 +222,40 @@ class LightSourceRenderSampler(VolumeRenderSampler):
         ld /= np.sqrt(ld[0] * ld[0] + ld[1] * ld[1] + ld[2] * ld[2])     # image_samplers.pyx:526-528
         self.light_dir = np.ascontiguousarray(ld)
         self.light_rgba = np.ascontiguousarray(np.array(light_rgba, dtype="float64"))
+
+
+class _OctreeRayTracing:
+    """_octree_raytracing.pyx:15-34 over the restated Octree<int> (_octree_raytracing.hpp)."""
+
+    def __init__(self, LE, RE, depth):
+        self._LE = np.ascontiguousarray(LE, dtype="float64")
+        self._RE = np.ascontiguousarray(RE, dtype="float64")
+        self.depth = int(depth)
+        self._h = C.c_void_p(lib().orc_octree_create(self.depth, _dptr(self._LE), _dptr(self._RE)))
+
+    def add_nodes(self, ipos, lvl, key):
+        ipos = np.ascontiguousarray(ipos, dtype="int32")
+        lvl = np.ascontiguousarray(lvl, dtype="int32")
+        key = np.ascontiguousarray(key, dtype="int32")
+        i32p = C.POINTER(C.c_int32)
+        rc = lib().orc_octree_add_nodes(self._h, len(key), ipos.ctypes.data_as(i32p), lvl.ctypes.data_as(i32p),
+                                        key.ctypes.data_as(i32p))
+        if rc:
+            raise ValueError("level beyond the octree depth")
+
+    def cast_ray(self, o, d, cap=4096):
+        """(keys, t[:, 2]) of one ray: Octree::cast_ray(double*, double*, keyList, tList)."""
+        o = np.ascontiguousarray(o, dtype="float64"); d = np.ascontiguousarray(d, dtype="float64")
+        keys = np.empty(cap, "int32"); t = np.empty(2 * cap, "float64")
+        n = lib().orc_octree_cast_ray(self._h, _dptr(o), _dptr(d), cap, keys.ctypes.data_as(C.POINTER(C.c_int32)), _dptr(t))
+        assert n <= cap
+        return keys[:n].copy(), t[:2 * n].reshape(n, 2).copy()
+
+    def __del__(self):
+        try:
+            lib().orc_octree_destroy(self._h)
+        except Exception:
+            pass
 
 
 def vertex_centre(cells):

@@ -271,3 +271,105 @@ def scenarios(small=True):
     out.append(Scenario("tiny", "vr", cam, [([np.arange(8, dtype="float64").reshape(2, 2, 2) / 8.0], np.ones((1, 1, 1), "uint8"),
                                             *unit, [1, 1, 1])], [0], tf=colour_tf(height=50.0)))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# octree scenarios (cast_through_octree, image_samplers.pyx:202-299)
+# ---------------------------------------------------------------------------------------------------
+class OctreeScenario:
+    def __init__(self, name, kind, cam, depth, ipos, lvl, cells, tf=None, n_samples=10, image0=None, grey=False):
+        self.name, self.kind, self.cam, self.depth = name, kind, cam, depth
+        self.ipos, self.lvl, self.cells = ipos, lvl, cells      # int32 (n,3), int32 (n), float64 (n,14)
+        self.tf, self.n_samples, self.image0, self.grey = tf, n_samples, image0, grey
+
+
+def random_octree(depth, max_level, p_refine, seed, holes=0.0):
+    """Leaves of a randomly refined octree over the unit cube: (ipos int32 (n,3) as octree_raytracing.py:35 builds
+    them -- floor(centre * 2**depth) --, level int32 (n), centre (n,3), dx (n)).  `holes`: fraction of leaves dropped,
+    so some children are never added to the tree (absent nodes, _octree_raytracing.hpp:273-274)."""
+    rng = np.random.RandomState(seed)
+    leaves = []
+
+    def refine(i, j, k, level):
+        if level < max_level and (level < 1 or rng.uniform() < p_refine):
+            for di in range(2):
+                for dj in range(2):
+                    for dk in range(2):
+                        refine(2 * i + di, 2 * j + dj, 2 * k + dk, level + 1)
+        elif rng.uniform() >= holes:
+            leaves.append((i, j, k, level))
+
+    refine(0, 0, 0, 0)
+    ijk = np.array([l[:3] for l in leaves], dtype="float64")
+    lvl = np.array([l[3] for l in leaves], dtype="int32")
+    dx = 1.0 / (1 << lvl).astype("float64")
+    centre = (ijk + 0.5) * dx[:, None]
+    ipos = np.floor(centre * (1 << depth)).astype("int64").astype("int32")
+    return ipos, lvl, centre, dx
+
+
+def octree_cells(centre, dx, seed, lo=0.05, hi=0.95):
+    """The (n, 14) payload of OctreeVolumeSource.render (render_source.py:669-680): 8 vertex values of a smooth field
+    plus noise (x-major within the cell, as set_fields leaves them), then left and right edge."""
+    rng = np.random.RandomState(seed)
+    n = len(dx)
+    out = np.empty((n, 14), "float64")
+    c = 0
+    for a in range(2):
+        for b in range(2):
+            for k in range(2):
+                v = centre + (np.array([a, b, k]) - 0.5)[None, :] * dx[:, None]
+                f = 0.5 + 0.3 * np.sin(5.0 * v[:, 0]) * np.cos(4.0 * v[:, 1]) + 0.15 * np.sin(7.0 * v[:, 2])
+                out[:, c] = np.clip(f + rng.uniform(-0.03, 0.03, n), lo, hi)
+                c += 1
+    out[:, 8:11] = centre - dx[:, None] / 2
+    out[:, 11:14] = centre + dx[:, None] / 2
+    return out
+
+
+def octree_scenarios():
+    out = []
+    R = (40, 36)
+    ipos, lvl, centre, dx = random_octree(depth=5, max_level=4, p_refine=0.45, seed=3)
+    cells = octree_cells(centre, dx, 5)
+    cam_a = make_camera("perspective", R, position=[1.7, 1.5, 1.3], width=[0.8, 0.8, 1.0])     # all directions negative
+    cam_b = make_camera("perspective", R, position=[-0.6, 1.4, -0.9], width=[0.9, 0.9, 1.0])   # mixed signs
+    cam_c = make_camera("perspective", R, position=[0.52, 0.47, 0.55], focus=[0.9, 0.1, 0.2], width=[1.2, 1.2, 1.0])  # inside
+    rng = np.random.RandomState(9)
+    out.append(OctreeScenario("oct_vr_colour", "vr", cam_a, 5, ipos, lvl, cells, tf=colour_tf(n_gauss=4)))
+    out.append(OctreeScenario("oct_vr_grey_image0", "vr", cam_b, 5, ipos, lvl, cells, tf=colour_tf(grey=True, n_gauss=3, seed=2),
+                              n_samples=7, image0=rng.uniform(0, 0.2, R + (4,)), grey=True))
+    out.append(OctreeScenario("oct_vr_inside", "vr", cam_c, 5, ipos, lvl, cells, tf=colour_tf(n_gauss=5, seed=4), n_samples=4))
+    out.append(OctreeScenario("oct_iproj", "iproj", cam_b, 5, ipos, lvl, cells, n_samples=5))
+    out.append(OctreeScenario("oct_proj", "proj", cam_a, 5, ipos, lvl, cells))
+    # a tree with absent children and a deeper maximum depth than any cell uses
+    ipos2, lvl2, centre2, dx2 = random_octree(depth=7, max_level=5, p_refine=0.35, seed=8, holes=0.2)
+    cells2 = octree_cells(centre2, dx2, 6)
+    out.append(OctreeScenario("oct_vr_holes", "vr", cam_b, 7, ipos2, lvl2, cells2, tf=colour_tf(n_gauss=4, seed=7)))
+    return out
+
+
+def run_octree_scenario(sc, sampler_mod, grid_mod, octree_cls, num_threads=1):
+    """Drive one implementation as OctreeVolumeSource.render does (render_source.py:667-686)."""
+    nx, ny = sc.cam.resolution
+    img = np.zeros((nx, ny, 4), "float64") if sc.image0 is None else sc.image0.copy()
+    args, kwargs = sampler_args(sc.cam, image=img)
+    args[8] = "Octree"
+    if sc.kind != "vr":
+        kwargs.pop("camera_data")
+    if sc.kind == "vr":
+        s = sampler_mod.VolumeRenderSampler(*args, sc.tf, sc.n_samples, **kwargs)
+    elif sc.kind == "iproj":
+        s = sampler_mod.InterpolatedProjectionSampler(*args, sc.n_samples, **kwargs)
+    else:
+        s = sampler_mod.ProjectionSampler(*args, sc.n_samples, **kwargs)
+    tree = octree_cls(np.zeros(3), np.ones(3), sc.depth)
+    tree.add_nodes(sc.ipos, sc.lvl, np.arange(len(sc.lvl), dtype=np.int32))
+    n = len(sc.lvl)
+    dt = np.ascontiguousarray(sc.cells).reshape(1, n, 14, 1)
+    mask = np.full(dt.shape[1:], 1, dtype=np.uint8)
+    dims = np.array([1, 1, 1], dtype="int64")
+    pg = grid_mod.PartitionedGrid(0, dt, mask, np.ascontiguousarray(sc.cells[:, 8:11]).ravel(),
+                                  np.ascontiguousarray(sc.cells[:, 11:14]).ravel(), dims, n_fields=1)
+    s(pg, oct=tree, num_threads=num_threads)
+    return np.array(s.aimage, copy=True)

@@ -106,6 +106,12 @@ SIGNATURES = {
                                 C.c_int, C.c_int]),
     "ytb200_zpoints": (C.c_int, [dp, dp, C.c_int64, C.c_int64, i64p, i64p, dp, C.c_int64, i64p, dp, C.c_int64, i64p,
                                  C.c_int, C.c_int]),
+    "ytb200_octree_create": (C.c_int, [C.c_void_p, C.c_int, dp, dp, C.POINTER(C.c_void_p)]),
+    "ytb200_octree_destroy": (C.c_int, [C.c_void_p]),
+    "ytb200_octree_add_nodes": (C.c_int, [C.c_void_p, C.c_int64, i32p, i32p, i32p]),
+    "ytb200_octree_node_count": (C.c_int64, [C.c_void_p]),
+    "ytb200_octree_set_cells": (C.c_int, [C.c_void_p, C.c_int64, dp]),
+    "ytb200_frame_cast_octree": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Stats)]),
     "ytb200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "ytb200_host_free": (C.c_int, [C.c_void_p]),
 }

@@ -1,0 +1,153 @@
+// The octree cast: ImageSampler.cast_through_octree, image_samplers.pyx:202-299, over the
+// parametric octree traversal of _octree_raytracing.hpp:199-371 (Revelles, Urena & Lastra).
+//
+// One thread owns one pixel: it walks the tree front to back and samples every terminal cell it meets with the
+// sampler's per-cell body, so the reference's compositing order along a ray is kept by construction.  The
+// reference recurses (proc_subtree); here the recursion is an explicit per-thread stack of (t0, t1, node, next
+// child) frames -- the same arithmetic in the same order (tm = (t0 + t1) * 0.5 per level, std::max / std::min
+// written with the comparison libstdc++ uses), all fp64 without contraction: every operation is the reference's,
+// so the image equals the reference's bit for bit (up to libm's sqrt, which is correctly rounded on both sides).
+// General kernel, not a tuned path (the reference reaches it from OctreeVolumeSource only).
+#pragma once
+#include "raycast.cuh"
+
+namespace ytb {
+
+constexpr int OCT_MAX_LEVELS = 32;   // frames of the traversal stack: root + max_depth (<= 30) levels
+constexpr int OCT_THREADS = 128;
+
+struct OctParams {
+    int nx, ny;
+    const double *pos_px, *dir_px;   // (nx,ny,3) rays
+    double *image;                   // (nx,ny,4) fp64, in/out
+    const int *child;                // [n_nodes][8] child node index, -1 = absent (node 0 is the root)
+    const int *leaf;                 // [n_nodes][2]: (terminal, key)
+    double dle[3], dre[3], size[3];
+    const double *cells;             // [n_cells][14]: 8 vertex values (x-major), left edge, right edge
+    int n_samples;
+    DevTF tf;
+};
+
+__device__ __forceinline__ double std_max(double a, double b) { return a < b ? b : a; }
+__device__ __forceinline__ double std_min(double a, double b) { return b < a ? b : a; }
+
+// first_node / next_node, _octree_raytracing.hpp:346-371
+__device__ __forceinline__ int oct_first_node(double tx0, double ty0, double tz0, double txm, double tym, double tzm)
+{
+    int index = 0;
+    if (tx0 >= std_max(ty0, tz0)) { if (tym < tx0) index |= 2; if (tzm < tx0) index |= 1; }
+    else if (ty0 >= std_max(tx0, tz0)) { if (txm < ty0) index |= 4; if (tzm < ty0) index |= 1; }
+    else { if (txm < tz0) index |= 4; if (tym < tz0) index |= 2; }
+    return index;
+}
+__device__ __forceinline__ int oct_next_node(double tx, double ty, double tz, int ix, int iy, int iz)
+{
+    if (tx < std_min(ty, tz)) return ix;
+    else if (ty < std_min(tx, tz)) return iy;
+    return iz;
+}
+
+// The sampler body for one terminal cell: a 1x1x1 VolumeContainer over the cell's 14 doubles, index (0,0,0), mask
+// all ones (image_samplers.pyx:268-288 -> 327-343 / 372-402 / 453-487).
+template <int KIND>
+__device__ __forceinline__ void oct_sample_cell(const OctParams &p, const TFShared64 &t64, const double *cell,
+                                                const double (&vp)[3], const double (&vd)[3], double enter_t, double exit_t,
+                                                double (&acc)[4])
+{
+    if (KIND == KIND_PROJ) {
+        acc[0] = dadd(acc[0], dmul(cell[0], dsub(exit_t, enter_t)));
+        return;
+    }
+    double dp[3], ds[3], dvs[6], B64[4];
+    const double dt = ddiv(dsub(exit_t, enter_t), (double)p.n_samples);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double le = cell[8 + i], dds = dsub(cell[11 + i], le), idds = ddiv(1.0, dds);
+        dp[i] = dadd(dmul(dadd(enter_t, dmul(0.5, dt)), vd[i]), vp[i]);
+        dp[i] = dsub(dp[i], dadd(dmul(0.0, dds), le));
+        dp[i] = dmul(dp[i], idds);
+        ds[i] = dmul(dmul(vd[i], idds), dt);
+    }
+#pragma unroll
+    for (int j = 1; j < 6; j++) dvs[j] = 0.0;
+    for (int s = 0; s < p.n_samples; s++) {
+        dvs[0] = offset_interpolate64(cell, 4, 2, dp);
+        if (KIND == KIND_VR) eval_transfer64<false>(p.tf, t64, dt, dvs, acc, B64);
+        else acc[0] = dadd(acc[0], dmul(dvs[0], dt));
+#pragma unroll
+        for (int i = 0; i < 3; i++) dp[i] = dadd(dp[i], ds[i]);
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(OCT_THREADS) octree_cast_kernel(const __grid_constant__ OctParams p)
+{
+    const long long px = (long long)blockIdx.x * OCT_THREADS + threadIdx.x;
+    if (px >= (long long)p.nx * p.ny) return;
+    double vp[3], vd[3], o[3], d[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { vp[i] = p.pos_px[px * 3 + i]; vd[i] = p.dir_px[px * 3 + i]; }
+    // Ray(o, d): the direction normalised (hpp:53-65); vp_dir_len of cast_through_octree (image_samplers.pyx:246-249)
+    const double len = __dsqrt_rn(dadd(dadd(dmul(vd[0], vd[0]), dmul(vd[1], vd[1])), dmul(vd[2], vd[2])));
+    // cast_ray (hpp:199-226): mirror the ray into the positive octant, remember the flips in `a`
+    int a = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        o[i] = vp[i];
+        d[i] = ddiv(vd[i], len);
+        if (d[i] < 0.0) { o[i] = dsub(p.size[i], o[i]); d[i] = -d[i]; a |= 4 >> i; }
+    }
+    double st0[OCT_MAX_LEVELS][3], st1[OCT_MAX_LEVELS][3];
+    int snode[OCT_MAX_LEVELS], snext[OCT_MAX_LEVELS];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { st0[0][i] = ddiv(dsub(p.dle[i], o[i]), d[i]); st1[0][i] = ddiv(dsub(p.dre[i], o[i]), d[i]); }
+    double mx = st0[0][0], mn = st1[0][0];
+#pragma unroll
+    for (int i = 1; i < 3; i++) { if (mx < st0[0][i]) mx = st0[0][i]; if (st1[0][i] < mn) mn = st1[0][i]; }
+    if (!(mx < mn)) return;
+    TFShared64 t64;
+    t64.values = p.tf.values; t64.d0 = p.tf.d0; t64.dy = p.tf.dy;
+    double acc[4];
+    double *out = p.image + px * 4;
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[c] = out[c];
+    int sp = 0;
+    snode[0] = 0;
+    bool entering = true;
+    while (sp >= 0) {
+        const double tx0 = st0[sp][0], ty0 = st0[sp][1], tz0 = st0[sp][2];
+        const double tx1 = st1[sp][0], ty1 = st1[sp][1], tz1 = st1[sp][2];
+        const double txm = dmul(dadd(tx0, tx1), 0.5), tym = dmul(dadd(ty0, ty1), 0.5), tzm = dmul(dadd(tz0, tz1), 0.5);
+        const int n = snode[sp];
+        int i;
+        if (entering) {
+            // proc_subtree prologue (hpp:270-289)
+            if (tx1 < 0 || ty1 < 0 || tz1 < 0 || n < 0) { sp--; entering = false; continue; }
+            if (p.leaf[2 * n]) {
+                const double t_in = std_max(std_max(tx0, ty0), tz0), t_out = std_min(std_min(tx1, ty1), tz1);
+                oct_sample_cell<KIND>(p, t64, p.cells + 14ll * p.leaf[2 * n + 1], vp, vd, ddiv(t_in, len), ddiv(t_out, len), acc);
+                sp--; entering = false; continue;
+            }
+            i = oct_first_node(tx0, ty0, tz0, txm, tym, tzm);
+        } else {
+            i = snext[sp];
+            if (i >= 8) { sp--; continue; }
+        }
+        if (sp + 1 >= OCT_MAX_LEVELS) { sp--; entering = false; continue; }   // deeper than any tree the host accepts
+        // child i: lower half of an axis when its bit is clear, upper half when set; its successor along an axis is
+        // i with that bit set, or 8 (leave the node) -- the eight cases of the switch at hpp:301-341
+        const double c0x = (i & 4) ? txm : tx0, c1x = (i & 4) ? tx1 : txm;
+        const double c0y = (i & 2) ? tym : ty0, c1y = (i & 2) ? ty1 : tym;
+        const double c0z = (i & 1) ? tzm : tz0, c1z = (i & 1) ? tz1 : tzm;
+        snext[sp] = oct_next_node(c1x, c1y, c1z, (i & 4) ? 8 : (i | 4), (i & 2) ? 8 : (i | 2), (i & 1) ? 8 : (i | 1));
+        sp++;
+        st0[sp][0] = c0x; st0[sp][1] = c0y; st0[sp][2] = c0z;
+        st1[sp][0] = c1x; st1[sp][1] = c1y; st1[sp][2] = c1z;
+        snode[sp] = p.child[8 * n + (i ^ a)];
+        entering = true;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) out[c] = acc[c];
+}
+
+}  // namespace ytb

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "cast_kernels.cuh"
+#include "octree_cast.cuh"
 
 using namespace ytb;
 
@@ -952,6 +953,146 @@ extern "C" int ytb200_partial_apply(ytb200_ctx *ctx, const double *partial, doub
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// octree path: Octree<int> (_octree_raytracing.hpp) built on the host, flattened for the device
+// ------------------------------------------------------------------------------------------------
+struct ytb200_octree {
+    ytb200_ctx *ctx = nullptr;
+    int max_depth = 0;
+    double dle[3], dre[3], size[3];
+    std::vector<int> child;   // [n_nodes][8]
+    std::vector<int> leaf;    // [n_nodes][2] (terminal, key)
+    int max_key = -1;
+    bool dirty = true;
+    int *child_dev = nullptr, *leaf_dev = nullptr;
+    double *cells_dev = nullptr;
+    int64_t n_cells = 0;
+};
+
+static int oct_new_node(ytb200_octree *o)
+{
+    const int n = (int)(o->leaf.size() / 2);
+    o->child.insert(o->child.end(), 8, -1);
+    o->leaf.push_back(0); o->leaf.push_back(0);
+    return n;
+}
+
+extern "C" int ytb200_octree_create(ytb200_ctx *ctx, int max_depth, const double dle[3], const double dre[3], ytb200_octree **out)
+{
+    if (!ctx || !dle || !dre || !out) return fail(E_ARG, "NULL argument");
+    if (max_depth < 1 || max_depth > 30) return fail(E_ARG, "octree depth %d outside [1, 30]", max_depth);
+    auto *o = new ytb200_octree;
+    o->ctx = ctx; o->max_depth = max_depth;
+    for (int i = 0; i < 3; i++) { o->dle[i] = dle[i]; o->dre[i] = dre[i]; o->size[i] = dre[i] - dle[i]; }
+    oct_new_node(o);
+    *out = o;
+    return 0;
+}
+
+extern "C" int ytb200_octree_destroy(ytb200_octree *o)
+{
+    if (!o) return 0;
+    DeviceGuard g(o->ctx->device);
+    cudaFree(o->child_dev); cudaFree(o->leaf_dev); cudaFree(o->cells_dev);
+    delete o;
+    return 0;
+}
+
+// insert_node (hpp:137-170): one level per bit of ipos, from bit max_depth-1 down to bit max_depth-lvl
+extern "C" int ytb200_octree_add_nodes(ytb200_octree *o, int64_t n, const int32_t *ipos, const int32_t *lvl, const int32_t *key)
+{
+    if (!o || (n > 0 && (!ipos || !lvl || !key))) return fail(E_ARG, "NULL argument");
+    for (int64_t c = 0; c < n; c++) {
+        if (lvl[c] < 0 || lvl[c] > o->max_depth) return fail(E_ARG, "cell %lld: level %d beyond the octree depth %d", (long long)c, lvl[c], o->max_depth);
+        if (key[c] < 0) return fail(E_ARG, "cell %lld: negative key", (long long)c);
+        uint64_t mask = (uint64_t)1 << (o->max_depth - 1);
+        int node = 0;
+        for (int ibit = o->max_depth - 1; ibit >= o->max_depth - lvl[c]; --ibit) {
+            int iflat = 0;
+            for (int d = 0; d < 3; d++) iflat = (iflat << 1) | (((uint64_t)(int64_t)ipos[3 * c + d] & mask) ? 1 : 0);
+            mask >>= 1;
+            if (o->child[8 * (size_t)node + iflat] < 0) {
+                const int nn = oct_new_node(o);
+                o->child[8 * (size_t)node + iflat] = nn;
+            }
+            node = o->child[8 * (size_t)node + iflat];
+        }
+        o->leaf[2 * (size_t)node] = 1;
+        o->leaf[2 * (size_t)node + 1] = key[c];
+        if (key[c] > o->max_key) o->max_key = key[c];
+    }
+    o->dirty = true;
+    return 0;
+}
+
+extern "C" int64_t ytb200_octree_node_count(const ytb200_octree *o) { return o ? (int64_t)(o->leaf.size() / 2) : 0; }
+
+extern "C" int ytb200_octree_set_cells(ytb200_octree *o, int64_t n_cells, const double *cells_host)
+{
+    if (!o || n_cells < 1 || !cells_host) return fail(E_ARG, "bad cell array");
+    DeviceGuard g(o->ctx->device);
+    if (n_cells != o->n_cells) {
+        cudaFree(o->cells_dev); o->cells_dev = nullptr; o->n_cells = 0;
+        CK(cudaMalloc(&o->cells_dev, (size_t)n_cells * 14 * sizeof(double)));
+        o->n_cells = n_cells;
+    }
+    CK(cudaMemcpyAsync(o->cells_dev, cells_host, (size_t)n_cells * 14 * sizeof(double), cudaMemcpyHostToDevice, o->ctx->stream));
+    CK(cudaStreamSynchronize(o->ctx->stream));
+    return 0;
+}
+
+extern "C" int ytb200_frame_cast_octree(ytb200_frame *f, int kind, ytb200_octree *o, const ytb200_tf *tf, int n_samples,
+                                        ytb200_stats *stats)
+{
+    if (!f || !o) return fail(E_ARG, "NULL argument");
+    if (kind < 0 || kind > 2) return fail(E_ARG, "bad sampler kind %d", kind);
+    if (f->ctx != o->ctx) return fail(E_ARG, "frame and octree belong to different contexts");
+    if (!f->pos_px || !f->dir_px) return fail(E_ARG, "cast_through_octree reads per-pixel vp_pos / vp_dir: the frame has none (plane-parallel description)");
+    if (!o->cells_dev) return fail(E_STATE, "ytb200_octree_set_cells first");
+    if (o->max_key >= o->n_cells) return fail(E_ARG, "octree key %d beyond the %lld cells", o->max_key, (long long)o->n_cells);
+    if (kind == YTB200_VOLUME_RENDER) {
+        if (!tf) return fail(E_ARG, "VolumeRenderSampler needs a transfer function");
+        if (tf->d.light_on) return fail(E_UNSUPPORTED, "the lit sampler has no octree cast");
+        for (int i = 0; i < tf->d.n_fits; i++)
+            if (tf->d.field_id[i] >= 1 || tf->d.weight_field_id[i] >= 1)
+                return fail(E_ARG, "transfer function table %d refers to a field beyond the octree's single field", i);
+    }
+    if (kind != YTB200_PROJECTION && n_samples < 1) return fail(E_ARG, "n_samples must be >= 1");
+    DeviceGuard g(f->ctx->device);
+    cudaStream_t st = f->ctx->stream;
+    if (o->dirty) {
+        cudaFree(o->child_dev); cudaFree(o->leaf_dev); o->child_dev = o->leaf_dev = nullptr;
+        CK(cudaMalloc(&o->child_dev, o->child.size() * sizeof(int)));
+        CK(cudaMalloc(&o->leaf_dev, o->leaf.size() * sizeof(int)));
+        CK(cudaMemcpyAsync(o->child_dev, o->child.data(), o->child.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(o->leaf_dev, o->leaf.data(), o->leaf.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        o->dirty = false;
+    }
+    if (stats) CK(cudaEventRecord(f->ctx->ev0, st));
+    OctParams p{};
+    p.nx = f->cam.nx; p.ny = f->cam.ny;
+    p.pos_px = f->pos_px; p.dir_px = f->dir_px; p.image = f->image;
+    p.child = o->child_dev; p.leaf = o->leaf_dev; p.cells = o->cells_dev;
+    for (int i = 0; i < 3; i++) { p.dle[i] = o->dle[i]; p.dre[i] = o->dre[i]; p.size[i] = o->size[i]; }
+    p.n_samples = n_samples < 1 ? 1 : n_samples;
+    if (tf) p.tf = tf->d;
+    const long long npx = (long long)p.nx * p.ny;
+    const unsigned grid = (unsigned)((npx + OCT_THREADS - 1) / OCT_THREADS);
+    if (kind == YTB200_VOLUME_RENDER) octree_cast_kernel<KIND_VR><<<grid, OCT_THREADS, 0, st>>>(p);
+    else if (kind == YTB200_INTERPOLATED_PROJECTION) octree_cast_kernel<KIND_IPROJ><<<grid, OCT_THREADS, 0, st>>>(p);
+    else octree_cast_kernel<KIND_PROJ><<<grid, OCT_THREADS, 0, st>>>(p);
+    CK(cudaGetLastError());
+    if (stats) {
+        CK(cudaEventRecord(f->ctx->ev1, st));
+        CK(cudaEventSynchronize(f->ctx->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, f->ctx->ev0, f->ctx->ev1));
+        stats->kernel_ms = ms; stats->n_launches = 1; stats->n_cells = 0; stats->n_samples = 0;
+    }
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // binary swap over NVLink peer memory (replaces AMRKDTree.reduce_tree_images, amr_kdtree.py:297-323)

@@ -139,7 +139,7 @@ class ImageSampler:
         if self.volume_method == "KDTree":
             return self.cast_through_kdtree(pg, **kwa)
         elif self.volume_method == "Octree":
-            raise NotImplementedError("Octree traversal is outside the B200 hot path (SURVEY.md 2.1)")
+            return self.cast_through_octree(pg, **kwa)
         else:
             raise NotImplementedError(
                 'Volume rendering has not been implemented for method: "%s"' % self.volume_method)
@@ -151,6 +151,35 @@ class ImageSampler:
         self._pending.append(pg)
         self._dirty = True
         return 0
+
+    def cast_through_octree(self, pg, oct, num_threads=0):
+        """image_samplers.pyx:202-299: every pixel's ray walks the octree front to back and the sampler's per-cell body
+        runs on each terminal cell, over ``pg``'s single field of shape (n_cells, 14, 1) -- 8 vertex values, left
+        edge, right edge per cell (render_source.py:669-680).  The z-buffer is not consulted (as in the reference).
+        Runs at once (one launch) and leaves the result in the caller's image."""
+        from .octree_raytracing import _OctreeRayTracing
+        if not isinstance(pg, PartitionedGrid):
+            raise TypeError("Argument 'pg' has incorrect type (expected PartitionedGrid, got %s)" % type(pg).__name__)
+        if not isinstance(oct, _OctreeRayTracing):
+            raise TypeError("Argument 'oct' has incorrect type (expected _OctreeRayTracing, got %s)" % type(oct).__name__)
+        nx, ny = self.aimage_host.shape[:2]
+        if self.vp_pos.shape[:2] != (nx, ny) or self.vp_dir.shape[:2] != (nx, ny) or self.lens_type == "plane-parallel":
+            # the reference indexes vp_pos[vi, vj, :] unchecked: with the packed plane-parallel description
+            # (lens.py:89-94) it reads out of bounds; here that is an error
+            raise ValueError("cast_through_octree needs per-pixel vp_pos / vp_dir of shape (nx, ny, 3)")
+        if hasattr(self, "light_dir"):
+            raise NotImplementedError("LightSourceRenderSampler has no octree cast here")
+        cells = pg.my_data[0]
+        if cells.size % 14:
+            raise ValueError("octree cell data must hold 14 values per cell")
+        self.flush()
+        oct.set_cells(cells)
+        fr = self._frame
+        fr.upload(self.aimage_host, self.azbuffer)
+        L.check(L.load().ytb200_frame_cast_octree(fr.handle, int(self.kind), oct.handle,
+                                                  self._tables.handle if self._tables is not None else None,
+                                                  int(self.n_samples), None))
+        fr.download(self.aimage_host)
 
     # -- batched entry used by the scene mirror ---------------------------------------------------------
     def cast_bricks(self, brickset, order):
