@@ -106,3 +106,47 @@ def test_cuda_octree_errors(gpu):
     t2 = _OctreeRayTracing(np.zeros(3), np.ones(3), 5)
     t2.add_nodes(ipos, lvl, np.arange(len(lvl), dtype=np.int32))
     assert o.octree.depth == 5 and o.octree.node_count == t2.node_count
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grey", [False, True])
+def test_create_scene_octree_dataset(grey, gpu):
+    """yt.create_scene on an octree dataset -> OctreeVolumeSource.render (render_source.py:619-693), against the oracle
+    driven with the same sampler arguments."""
+    import yt_b200 as yt
+    from yt_b200.volume_rendering.render_source import OctreeVolumeSource
+    ipos, lvl, centre, dx = T.random_octree(depth=5, max_level=4, p_refine=0.45, seed=3)
+    cells = T.octree_cells(centre, dx, 5)
+    ds = yt.load_octree_cells(centre, lvl - 1, {"density": cells[:, :8].T.reshape(2, 2, 2, -1)})
+    with pytest.raises(ValueError):
+        yt.create_scene(ds).render()          # plane-parallel: no per-pixel rays (the reference reads out of bounds)
+    sc = yt.create_scene(ds, lens_type="perspective")
+    src = sc.get_source()
+    assert isinstance(src, OctreeVolumeSource) and src.use_ghost_zones and src.log_field
+    sc.camera.resolution = (48, 40)
+    sc.camera.position = [1.6, 1.4, 1.2]
+    sc.camera.width = [0.8, 0.8, 1.0]
+    src.tfh.grey_opacity = grey
+    im = np.array(sc.render())
+    # the oracle, with the arguments the scene built
+    params = sc.camera._get_sampler_params(src)
+    args = [np.atleast_3d(np.array(params["vp_pos"], dtype="float64")), np.atleast_3d(np.array(params["vp_dir"], dtype="float64")),
+            np.array(params["center"], dtype="float64"), params["bounds"], np.zeros(tuple(sc.camera.resolution) + (4,)),
+            np.array(params["x_vec"], dtype="float64"), np.array(params["y_vec"], dtype="float64"),
+            np.array(params["width"], dtype="float64"), "Octree"]
+    s = O.VolumeRenderSampler(*args, src.transfer_function, src.num_samples, camera_data=params["camera_data"],
+                              lens_type=params["lens_type"], zbuffer=np.ones(tuple(sc.camera.resolution)))
+    tree = O._OctreeRayTracing(np.zeros(3), np.ones(3), src.volume.octree.depth)
+    tree.add_nodes(ipos, lvl, np.arange(len(lvl), dtype=np.int32))
+    assert src.volume.octree.depth == 5
+    logc = cells.copy()
+    logc[:, :8] = np.log10(cells[:, :8])
+    pg = O.PartitionedGrid(0, logc.reshape(1, -1, 14, 1), np.ones((len(lvl), 14, 1), "uint8"), np.zeros(3), np.ones(3),
+                           np.ones(3, "int64"), n_fields=1)
+    s(pg, oct=tree)
+    want = np.array(s.aimage)
+    if not grey:
+        want[:, :, 3] = 1
+    want = np.rot90(want, k=2)
+    assert (want[:, :, :3] > 0).any(axis=2).mean() > 0.3
+    assert T.normalised_diff(im, want, grey) <= 1e-10

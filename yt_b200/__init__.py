@@ -11,7 +11,7 @@ Importing this package never touches CUDA; the first sampler / context construct
 __version__ = "0.1.0"
 
 from . import _lib  # noqa: F401
-from .loaders import load_amr_grids, load_uniform_grid  # noqa: F401
+from .loaders import load_amr_grids, load_octree_cells, load_uniform_grid  # noqa: F401
 from .parallel import enable_parallelism  # noqa: F401
 from .volume_rendering import (  # noqa: F401
     ColorTransferFunction,

@@ -293,3 +293,77 @@ def load_amr_grids(grid_data, domain_dimensions, bbox=None, sim_time=0.0, length
         spec["fields"] = {k: (v[0] if isinstance(v, tuple) else v) for k, v in g.items()}
         specs.append(spec)
     return StreamDataset(specs, dims, bbox, refine_by=refine_by, periodicity=periodicity, name="AMRGridData")
+
+
+# ---------------------------------------------------------------------------------------------------
+# octree cells (OctreeVolumeSource, render_source.py:619-693)
+# ---------------------------------------------------------------------------------------------------
+class OctreeIndex:
+    """Marker for ``create_volume_source`` (render_source.py:184-185): datasets whose index is an octree."""
+
+
+class OctreeAllData(AllData):
+    """The cells of an octree dataset as a data source: ``src["x"|"y"|"z"|"dx"|"grid_level"]`` in unitary
+    coordinates, the way OctreeRayTracing / OctreeVolumeSource.render read them (octree_raytracing.py:33-34,
+    render_source.py:669-672)."""
+
+    @property
+    def blocks(self):
+        return iter(())
+
+    def __getitem__(self, key):
+        return self.ds.cell_arrays[key[1] if isinstance(key, tuple) else key]
+
+    def _extrema(self, field, non_zero=False):
+        v = self.ds.vertex_data[self.ds._resolve(field)]
+        if non_zero:
+            v = v[v > 0]
+        return np.float64(v.min()), np.float64(v.max())
+
+    def vertex_centered_data(self, field):
+        """(2, 2, 2, n_cells) vertex values in the orientation OctreeRayTracing.vertex_centered_data returns them
+        (octree_raytracing.py:43-69): first index z, last index x -- ``set_fields`` swaps axes 0 and 2 back
+        (octree_raytracing.py:93-98) so that the sampler finds corner (x, y, z) at x*4 + y*2 + z."""
+        return self.ds.vertex_data[self.ds._resolve(field)].swapaxes(0, 2)
+
+
+class OctreeCellDataset(StreamDataset):
+    """Terminal cells of an octree over the unit cube with caller-supplied vertex-centred data.  (The reference
+    derives the vertex values from ghost zones of the oct handler -- yt machinery outside the ray-casting path.)"""
+
+    def __init__(self, centres, levels, vertex_data, name="octree_cells"):
+        centres = np.ascontiguousarray(centres, dtype="float64")
+        levels = np.ascontiguousarray(levels, dtype="int64")
+        n = len(levels)
+        if centres.shape != (n, 3):
+            raise RuntimeError("centres must have shape (n_cells, 3)")
+        self.domain_left_edge, self.domain_right_edge = np.zeros(3), np.ones(3)
+        self.domain_width, self.domain_center = np.ones(3), np.full(3, 0.5)
+        self.domain_dimensions = np.array([2, 2, 2], dtype="int64")
+        self.refine_by, self.periodicity, self.basename = 2, (True, True, True), name
+        self.min_level, self.max_level = 0, int(levels.max())
+        self.index = OctreeIndex()
+        dx = 1.0 / (2 << levels).astype("float64")    # level 0 cells are the 8 children of the root oct
+        self.cell_arrays = {"x": centres[:, 0], "y": centres[:, 1], "z": centres[:, 2], "dx": dx, "grid_level": levels}
+        self.field_info, self.field_list, self.vertex_data = {}, [], {}
+        for k, v in vertex_data.items():
+            key = k if isinstance(k, tuple) else ("stream", k)
+            arr = np.ascontiguousarray(v, dtype="float64")
+            if arr.shape != (2, 2, 2, n):
+                raise RuntimeError("vertex data of %s must have shape (2, 2, 2, n_cells)" % (k,))
+            self.vertex_data[key] = arr
+            self.field_info[key] = FieldInfo(key, key[1] in LOG_FIELDS)
+            self.field_list.append(key)
+        self.derived_field_list = list(self.field_list)
+        self.default_field = self._pick_default()
+        self.unit_registry = None
+
+    def all_data(self):
+        return OctreeAllData(self)
+
+
+def load_octree_cells(centres, levels, vertex_data):
+    """An in-memory octree dataset for ``create_scene`` / ``OctreeVolumeSource``: cell centres (n, 3) in the unit
+    cube, their levels (level L cells have dx = 2**-(L+1)) and, per field, the (2, 2, 2, n) vertex values indexed
+    (x, y, z) within a cell."""
+    return OctreeCellDataset(centres, levels, vertex_data)

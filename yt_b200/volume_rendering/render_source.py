@@ -1,6 +1,6 @@
 """Render sources -- yt/visualization/volume_rendering/render_source.py.
 
-``VolumeSource`` / ``KDTreeVolumeSource`` (209-616) with the reference's properties, setters and
+``VolumeSource`` / ``KDTreeVolumeSource`` / ``OctreeVolumeSource`` (209-693) with the reference's properties, setters and
 ``render``/``finalize_image`` contract.  The brick loop of ``render`` (594-597,
 ``for brick in volume.traverse(viewpoint): sampler(brick)``) is handed to the device as ONE launch:
 all kd-tree leaves are kept resident as a brick table and only the view order is recomputed per
@@ -13,6 +13,9 @@ import os
 import numpy as np
 
 from ..amr_kdtree import AMRKDTree
+from ..loaders import OctreeIndex
+from ..octree_raytracing import OctreeRayTracing
+from ..partitioned_grid import PartitionedGrid
 from .transfer_function_helper import TransferFunctionHelper
 from .transfer_functions import ColorTransferFunction, ProjectionTransferFunction, TransferFunction
 from .utils import data_source_or_all, new_interpolated_projection_sampler, new_projection_sampler, new_volume_render_sampler
@@ -48,9 +51,12 @@ class OpaqueSource(RenderSource):
 
 
 def create_volume_source(data_source, field):
+    """render_source.py:170-190: a kd-tree source for grid datasets, an octree source for octree datasets."""
     data_source = data_source_or_all(data_source)
+    if isinstance(data_source.ds.index, OctreeIndex):
+        return OctreeVolumeSource(data_source, field)
     if not hasattr(data_source.ds.index, "grids"):
-        raise NotImplementedError("only grid (kd-tree) datasets are on the B200 hot path")
+        raise NotImplementedError("Cannot render datasets that are neither grid-based nor octrees")
     return KDTreeVolumeSource(data_source, field)
 
 
@@ -290,6 +296,65 @@ class KDTreeVolumeSource(VolumeSource):
         if self._volume is not None:
             image = self.volume.reduce_tree_images(image, camera.lens.viewpoint, use_opacity=self.transfer_function.grey_opacity)
         return super().finalize_image(camera, image)
+
+
+class _OctreeVolume(OctreeRayTracing):
+    """octree_raytracing.py:9-98 over an ``OctreeAllData``: the tree from the cell centres / levels, and
+    ``set_fields`` leaving the vertex values in ``self.data`` as (8, n_cells), x-major within a cell."""
+
+    def __init__(self, data_source, context=None):
+        ds = data_source.ds
+        xyz = np.stack([data_source[k] for k in "xyz"], axis=-1)
+        super().__init__(xyz, data_source["grid_level"], ds.min_level, ds.max_level, context=context)
+        self.data_source = data_source
+
+    def set_fields(self, fields, log_fields, no_ghost, force=False):
+        if no_ghost:
+            raise NotImplementedError("Ghost zones are required with Octree datasets")
+        if len(fields) != 1:
+            raise ValueError("Can only set one fields at a time. This is likely a bug, and should be reported.")
+        field = self.data_source._determine_fields(fields)[0]
+        vertex_data = self.data_source.vertex_centered_data(field)
+        if log_fields[0]:
+            vertex_data = np.log10(vertex_data)
+        # "swap axis 0 and 2" then reshape is the reference's layout fix (octree_raytracing.py:93-98): the sampler
+        # reads corner (x, y, z) at x*4 + y*2 + z
+        self.data = vertex_data.swapaxes(0, 2).reshape(8, -1)
+
+
+class OctreeVolumeSource(VolumeSource):
+    """render_source.py:619-693: ghost zones always on, one PartitionedGrid holding 14 doubles per cell, one
+    ``sampler(pg, oct=tree)`` call."""
+    volume_method = "Octree"
+
+    def __init__(self, *args, **kwa):
+        super().__init__(*args, **kwa)
+        self.use_ghost_zones = True
+
+    def _get_volume(self):
+        if self._volume is None:
+            self._volume = _OctreeVolume(self.data_source)
+        return self._volume
+
+    def render(self, camera, zbuffer=None):
+        self._ensure_volume_fields()
+        self.zbuffer = zbuffer
+        self.set_sampler(camera)
+        if self.sampler is None:
+            raise RuntimeError("No sampler set. This is likely a bug as it should never happen.")
+        data = self.data_source
+        dx = data["dx"][:, None]
+        xyz = np.stack([data[k] for k in "xyz"], axis=-1)
+        LE, RE = xyz - dx / 2, xyz + dx / 2
+        dt = np.stack(list(self.volume.data) + [*LE.T, *RE.T], axis=-1).reshape(1, len(dx), 14, 1)
+        mask = np.full(dt.shape[1:], 1, dtype=np.uint8)
+        dims = np.array([1, 1, 1], dtype="int64")
+        pg = PartitionedGrid(0, dt, mask, LE.flatten(), RE.flatten(), dims, n_fields=1)
+        self.sampler(pg, oct=self.volume.octree)
+        self.current_image = self.finalize_image(camera, self.sampler.aimage)
+        if zbuffer is None:
+            self.zbuffer = ZBuffer(self.current_image, np.full(self.current_image.shape[:2], np.inf))
+        return self.current_image
 
 
 # ---------------------------------------------------------------------------------------------------------
