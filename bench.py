@@ -169,15 +169,16 @@ def measured_peak():
 def lsu_pipe_estimate(kind, samples, kernel_ms, sm_mhz, sm_count):
     """Busy fraction of the L1/shared LSU data pipe (one wavefront per cycle per SM).  Shared-memory wavefronts are
     exact by construction (two LDS.128 per sample, 4 wavefronts each, zero bank conflicts); wavefronts per global
-    load are the ncu averages of profiles/r01zd (VR: 8 corner loads per cell x 5.0; PROJ: 8.4 per load)."""
+    load are the ncu averages (VR, profiles/r01zn: 4 corner loads per cell x 6.0 -- the walk reuses the face two
+    consecutive cells share; PROJ, profiles/r01zd: 8.4 per load)."""
     if kind == "vr":
         cells = samples / N_SAMPLES
-        wf = samples / 32.0 * 8.0 + cells / 32.0 * 8 * 5.0
+        wf = samples / 32.0 * 8.0 + cells / 32.0 * 4 * 6.0
     else:
         wf = samples / 32.0 * 8.4
     cycles = kernel_ms * 1e-3 * sm_mhz * 1e6
     return {"wavefronts": wf, "frac": wf / sm_count / cycles,
-            "source": "LDS wavefronts counted, LDG wavefronts per request from ncu (profiles/r01zd_*); ncu measured 0.960 (VR) / 0.570 (PROJ)"}
+            "source": "LDS wavefronts counted, LDG wavefronts per request from ncu (profiles/r01zn_vr_*, r01zd_proj_*); ncu measured 0.849 (VR) / 0.570 (PROJ)"}
 
 
 def recorded_traffic(workload):
@@ -497,8 +498,8 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": recorded_traffic(args.workload), "peak_source": peak_src, "kernel": "cast_kernel",
                      "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
-                     "note": ("volume-render cast: 7.7 samples per HBM byte, so the HBM fraction is structurally ~1-2 %; the unit that is "
-                              "full is the L1/shared LSU data pipe, see `lsu_pipe` and `issue`") if kind == "vr" else
+                     "note": ("volume-render cast: 7.7 samples per HBM byte, so the HBM fraction is structurally ~1-2 %; the units that are "
+                              "busy are the L1/shared LSU data pipe (85 %) and instruction issue (71 %, ncu r01zn), see `lsu_pipe` and `issue`") if kind == "vr" else
                              "single-field projection walk: instruction issue 67 %, L1 LSU data pipe 57 % busy (ncu r01zd), DRAM traffic 2.4x algorithmic"},
         "lsu_pipe": lsu_pipe_estimate(kind, my_samples, kernel_ms, (clk or {}).get("sm_mhz") or sm_max, ctx.sm_count),
         "issue": {"samples_per_s_per_sm": total_samples / world / (kernel_ms * 1e-3) / ctx.sm_count,

@@ -58,7 +58,7 @@ def report(path):
     print("# ncu --set full --clock-control none, raw page of", path)
     for r in rows[2:]:
         print("kernel:", r[hdr.index("Kernel Name")])
-        for k in KEYS:
+        for k in KEYS + [h for h in hdr if "data_pipe_lsu_wavefronts" in h and h not in KEYS]:
             if k in hdr:
                 i = hdr.index(k)
                 print("  %-92s %-16s %s" % (k, units[i], r[i]))
