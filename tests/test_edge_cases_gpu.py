@@ -121,3 +121,29 @@ def test_two_casts_accumulate_like_two_sampler_calls(gpu):
     both = np.array(s.aimage, copy=True)
     assert not np.array_equal(first, both)
     assert T.normalised_diff(both, want, False) <= 1e-4
+
+
+@pytest.mark.parametrize("position", [[0.5, 0.5, 2.0], [0.5, 0.5, -1.0], [2.0, 0.5, 0.5], [-1.0, 0.5, 0.5], [0.5, 2.0, 0.5],
+                                      [0.5, -1.0, 0.5], [1.7, 0.5, 1.9], [0.5, -0.8, -0.9]])
+@pytest.mark.parametrize("masked", [False, True])
+def test_colour_walk_axis_aligned_and_planar_views(position, masked, gpu):
+    """The fused colour walk keeps a cell in ray-oriented corner order and mirrors the cell coordinates on descending
+    axes; an axis the ray does not move along keeps its memory orientation and a fixed in-cell coordinate.  Views along
+    +-x, +-y, +-z (two idle axes) and in a coordinate plane (one idle axis), with and without a cell mask."""
+    S, G = _mods()
+    n = 12
+    north = [0.0, 1.0, 0.0] if abs(position[1] - 0.5) < 1e-12 else [0.0, 0.0, 1.0]
+    cam = T.make_camera(resolution=(29, 31), position=position, focus=[0.5, 0.5, 0.5], width=[0.9, 0.9, 3.5], north=north)
+    b = list(_unit_brick(n, 7))
+    if masked:
+        m = np.ones((n, n, n), "uint8")
+        m[3:6, 2:9, 4:7] = 0
+        m[::5, ::3, 1] = 0
+        b[1] = m
+    sc = T.Scenario("axis", "vr", cam, [tuple(b)], [0], tf=T.colour_tf(height=40.0))
+    want = T.run_scenario(sc, O, O, num_threads=0)
+    got = T.run_scenario(sc, S, G)
+    assert want[..., :3].max() > 0
+    assert T.normalised_diff(got, want, False) <= 1e-4
+    got64 = T.run_scenario(sc, S, G, sampler_kwargs={"storage": "f64"})
+    assert T.normalised_diff(got64, want, False) <= 1e-4
