@@ -10,7 +10,12 @@
 
 namespace ytb {
 
-constexpr int TILE_I = 16, TILE_J = 16, CTA_THREADS = 256;
+#ifndef YTB_CTA_THREADS
+#define YTB_CTA_THREADS 256
+#endif
+// a CTA's warps are 4 x 8 pixel patches laid two abreast (see cast_kernel): 16 columns, CTA_THREADS / 16 rows
+constexpr int CTA_THREADS = YTB_CTA_THREADS, TILE_I = CTA_THREADS / 16, TILE_J = 16;
+static_assert(CTA_THREADS % 64 == 0, "warps pair up across the tile");
 #ifndef YTB_MIN_BLOCKS
 #define YTB_MIN_BLOCKS 2
 #endif

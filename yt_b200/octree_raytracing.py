@@ -29,7 +29,6 @@ class _OctreeRayTracing:
                                          C.byref(h)))
         self.handle = h
         self.depth = int(depth)
-        self._cells_id = None
         self._fin = weakref.finalize(self, lib.ytb200_octree_destroy, h)
 
     def add_nodes(self, ipos, lvl, key):
@@ -50,12 +49,10 @@ class _OctreeRayTracing:
         return int(L.load().ytb200_octree_node_count(self.handle))
 
     def set_cells(self, cells):
-        """Upload the (n_cells, 14) payload of OctreeVolumeSource.render's PartitionedGrid (once per array)."""
-        if self._cells_id is cells:
-            return
+        """Upload the (n_cells, 14) payload of OctreeVolumeSource.render's PartitionedGrid.  Every call uploads: the
+        reference reads the host array at each cast, so in-place edits between casts must be seen."""
         flat = np.ascontiguousarray(cells, dtype=np.float64).reshape(-1, 14)
         L.check(L.load().ytb200_octree_set_cells(self.handle, flat.shape[0], flat.ctypes.data_as(L.dp)))
-        self._cells_id = cells
 
 
 class OctreeRayTracing:
