@@ -169,6 +169,19 @@ def _rand_cells(n, seed, lo=0.0, hi=1.0):
     return np.random.RandomState(seed).uniform(lo, hi, size=tuple(n))
 
 
+def zero_padded(d):
+    """The same array inside a larger zeroed buffer.  A ray that enters a brick exactly through an edge makes the
+    reference sample an out-of-range cell over a zero-length segment (grid_traversal.pyx:104-138): it reads past the
+    array.  The plain samplers are immune (dt = 0 times a finite table value), the lit one multiplies by a gradient of
+    whatever it read -- NaN or inf garbage turns the pixel NaN.  With zeros around the data the CPU implementations are
+    deterministic (and equal to any finite garbage); the CUDA cast never touches that memory."""
+    d = np.ascontiguousarray(d, dtype="float64")
+    buf = np.zeros(3 * d.size + 192)
+    view = buf[d.size + 64:2 * d.size + 64].reshape(d.shape)
+    view[...] = d
+    return view
+
+
 def run_scenario(sc, sampler_mod, grid_mod, num_threads=1, sampler_kwargs=None):
     """Drive one implementation exactly as render_source.py:594-599 drives the reference."""
     img = np.zeros((sc.cam.resolution[0], sc.cam.resolution[1], 4), "float64") if sc.image0 is None else sc.image0.copy()
@@ -184,7 +197,7 @@ def run_scenario(sc, sampler_mod, grid_mod, num_threads=1, sampler_kwargs=None):
         s = sampler_mod.InterpolatedProjectionSampler(*args, sc.n_samples, **kwargs)
     else:
         s = sampler_mod.ProjectionSampler(*args, sc.n_samples, **kwargs)
-    grids = [grid_mod.PartitionedGrid(i, list(b[0]), b[1], np.array(b[2], "float64"), np.array(b[3], "float64"),
+    grids = [grid_mod.PartitionedGrid(i, [zero_padded(d) for d in b[0]], b[1], np.array(b[2], "float64"), np.array(b[3], "float64"),
                                       np.array(b[4], "int64")) for i, b in enumerate(sc.bricks)]
     for i in sc.order:
         s(grids[i], num_threads=num_threads)

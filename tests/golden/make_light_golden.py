@@ -24,7 +24,7 @@ def run_light(sc, sampler_mod, grid_mod, num_threads=1, sampler_kwargs=None):
     kw.update(sampler_kwargs or {})
     s = sampler_mod.LightSourceRenderSampler(*args, sc.tf, sc.n_samples, light_dir=np.array(LIGHT_DIR, dtype="float64"),
                                              light_rgba=np.array(LIGHT_RGBA, dtype="float64"), **kw)
-    grids = [grid_mod.PartitionedGrid(i, list(b[0]), b[1], np.array(b[2], "float64"), np.array(b[3], "float64"),
+    grids = [grid_mod.PartitionedGrid(i, [T.zero_padded(d) for d in b[0]], b[1], np.array(b[2], "float64"), np.array(b[3], "float64"),
                                       np.array(b[4], "int64")) for i, b in enumerate(sc.bricks)]
     for i in sc.order:
         s(grids[i], num_threads=num_threads)
