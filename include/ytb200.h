@@ -242,7 +242,7 @@ int ytb200_render(ytb200_frame *f, int kind, const ytb200_brickset *set, const i
  * image_samplers.pyx:202-299: every pixel's ray (per-pixel vp_pos / vp_dir) walks the tree front to back
  * (cast_ray / proc_subtree, hpp:199-343) and the sampler's per-cell body runs on each terminal cell met, over
  * the cell's 14 doubles -- 8 vertex values, left edge, right edge (render_source.py:669-680).  The z-buffer is
- * not consulted (as in the reference).  All arithmetic fp64 in the reference's order. */
+ * not consulted (as in the reference). */
 typedef struct ytb200_octree ytb200_octree;
 /* _OctreeRayTracing.__init__(LE, RE, depth) */
 int ytb200_octree_create(ytb200_ctx *ctx, int max_depth, const double left_edge[3], const double right_edge[3],
@@ -253,9 +253,11 @@ int ytb200_octree_add_nodes(ytb200_octree *oct, int64_t n, const int32_t *ipos, 
 int64_t ytb200_octree_node_count(const ytb200_octree *oct);
 /* the PartitionedGrid payload of OctreeVolumeSource.render: HOST (n_cells, 14) fp64, uploaded once */
 int ytb200_octree_set_cells(ytb200_octree *oct, int64_t n_cells, const double *cells_host);
-/* sampler(pg, oct=octree) with volume_method == "Octree": casts into the frame's device image.  Asynchronous. */
+/* sampler(pg, oct=octree) with volume_method == "Octree": casts into the frame's device image.  Asynchronous.
+ * precision: YTB200_PREC_EXACT = everything fp64 in the reference's order; YTB200_PREC_FAST = the volume render samples in
+ * fp32 (traversal and first-sample position stay fp64); the projection kinds are fp64 either way. */
 int ytb200_frame_cast_octree(ytb200_frame *f, int kind, ytb200_octree *oct, const ytb200_tf *tf, int n_samples,
-                             ytb200_stats *stats);
+                             int precision, ytb200_stats *stats);
 
 /* ---- AMR kd-tree: brick decomposition + view-order traversal, host side -----------------------
  * Replaces yt/utilities/lib/amr_kdtools.pyx (Node.add_grids/insert_grids/split_grids/

@@ -362,7 +362,7 @@ def octree_scenarios():
     return out
 
 
-def run_octree_scenario(sc, sampler_mod, grid_mod, octree_cls, num_threads=1):
+def run_octree_scenario(sc, sampler_mod, grid_mod, octree_cls, num_threads=1, sampler_kwargs=None):
     """Drive one implementation as OctreeVolumeSource.render does (render_source.py:667-686)."""
     nx, ny = sc.cam.resolution
     img = np.zeros((nx, ny, 4), "float64") if sc.image0 is None else sc.image0.copy()
@@ -370,6 +370,7 @@ def run_octree_scenario(sc, sampler_mod, grid_mod, octree_cls, num_threads=1):
     args[8] = "Octree"
     if sc.kind != "vr":
         kwargs.pop("camera_data")
+    kwargs.update(sampler_kwargs or {})
     if sc.kind == "vr":
         s = sampler_mod.VolumeRenderSampler(*args, sc.tf, sc.n_samples, **kwargs)
     elif sc.kind == "iproj":

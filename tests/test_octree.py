@@ -60,17 +60,23 @@ def test_oracle_ray_list_uniform_tree():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("sc", SCENARIOS, ids=lambda s: s.name)
-def test_cuda_matches_oracle_and_golden(sc, gpu):
+@pytest.mark.parametrize("precision", ["fast", "exact"])
+def test_cuda_matches_oracle_and_golden(sc, precision, gpu):
+    """EXACT: everything fp64 in the reference's order, agreement to rounding.  FAST (the default): the volume render
+    samples in fp32 and must meet the 1e-4 bar on the normalised RGBA; the projection kinds are fp64 either way."""
     from yt_b200 import image_samplers as S
     from yt_b200 import partitioned_grid as G
     from yt_b200.octree_raytracing import _OctreeRayTracing
     want = T.run_octree_scenario(sc, O, O, O._OctreeRayTracing, num_threads=0)
-    got = T.run_octree_scenario(sc, S, G, _OctreeRayTracing)
+    kw = {"precision": "exact", "storage": "f64"} if precision == "exact" else {}
+    got = T.run_octree_scenario(sc, S, G, _OctreeRayTracing, sampler_kwargs=kw)
     gold = np.load(GOLDEN)[sc.name]
     for ref in (want, gold):
         assert np.array_equal(np.isnan(ref), np.isnan(got))
         if sc.kind == "vr":
-            assert T.normalised_diff(got, ref, sc.grey) <= 1e-10
+            assert T.normalised_diff(got, ref, sc.grey) <= (1e-10 if precision == "exact" else 1e-4)
+            if not sc.grey:
+                assert np.array_equal(got[..., 3], ref[..., 3])      # alpha untouched, bit for bit
         else:
             scale = np.nanmax(np.abs(ref))
             assert np.nanmax(np.abs(got - ref)) <= 1e-12 * scale
@@ -149,4 +155,4 @@ def test_create_scene_octree_dataset(grey, gpu):
         want[:, :, 3] = 1
     want = np.rot90(want, k=2)
     assert (want[:, :, :3] > 0).any(axis=2).mean() > 0.3
-    assert T.normalised_diff(im, want, grey) <= 1e-10
+    assert T.normalised_diff(im, want, grey) <= 1e-4       # FAST precision, the scene default

@@ -111,7 +111,7 @@ SIGNATURES = {
     "ytb200_octree_add_nodes": (C.c_int, [C.c_void_p, C.c_int64, i32p, i32p, i32p]),
     "ytb200_octree_node_count": (C.c_int64, [C.c_void_p]),
     "ytb200_octree_set_cells": (C.c_int, [C.c_void_p, C.c_int64, dp]),
-    "ytb200_frame_cast_octree": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(Stats)]),
+    "ytb200_frame_cast_octree": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Stats)]),
     "ytb200_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "ytb200_host_free": (C.c_int, [C.c_void_p]),
 }

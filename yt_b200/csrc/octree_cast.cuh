@@ -7,7 +7,9 @@
 // child) frames -- the same arithmetic in the same order (tm = (t0 + t1) * 0.5 per level, std::max / std::min
 // written with the comparison libstdc++ uses), all fp64 without contraction: every operation is the reference's,
 // so the image equals the reference's bit for bit (up to libm's sqrt, which is correctly rounded on both sides).
-// General kernel, not a tuned path (the reference reaches it from OctreeVolumeSource only).
+// That is the EXACT precision and what the projection kinds always use (they carry the 1e-6 bar); the volume render's
+// FAST precision (the default) keeps the traversal in fp64 and samples in fp32 (oct_sample_cell_fast).
+// General kernels, not a tuned path (the reference reaches it from OctreeVolumeSource only).
 #pragma once
 #include "raycast.cuh"
 
@@ -25,6 +27,7 @@ struct OctParams {
     double dle[3], dre[3], size[3];
     const double *cells;             // [n_cells][14]: 8 vertex values (x-major), left edge, right edge
     int n_samples;
+    double inv_ns;                   // 1 / n_samples
     DevTF tf;
 };
 
@@ -79,9 +82,46 @@ __device__ __forceinline__ void oct_sample_cell(const OctParams &p, const TFShar
     }
 }
 
-template <int KIND>
+// FAST precision of the volume render (the product default, as for the kd path): the position of a cell's first
+// sample is formed in fp64 (the cancellation pos - left_edge, H13) and rounded once; trilinear interpolation, the
+// table lookups (fp32 (value, slope) pairs staged in shared memory, bounds split hi/lo) and the composite are fp32.
+__device__ __forceinline__ void oct_sample_cell_fast(const OctParams &p, const float2 *pairs, const double *cell,
+                                                     const double (&vp)[3], const double (&vd)[3], double enter_t, double exit_t,
+                                                     float (&rgba)[4])
+{
+    const double dt64 = (exit_t - enter_t) * p.inv_ns;
+    const double tmid = fma(0.5, dt64, enter_t);
+    float x[3], st[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double le = cell[8 + i], idds = 1.0 / (cell[11 + i] - le);
+        x[i] = (float)((fma(tmid, vd[i], vp[i]) - le) * idds);
+        st[i] = (float)(vd[i] * idds * dt64);
+    }
+    Corners c;
+    {
+        const float a0 = (float)cell[0], a1 = (float)cell[1], b0 = (float)cell[2], b1 = (float)cell[3];
+        const float e0 = (float)cell[4], e1 = (float)cell[5], f0 = (float)cell[6], f1 = (float)cell[7];
+        c.c000 = a0; c.dz00 = a1 - a0; c.c010 = b0; c.dz01 = b1 - b0;
+        c.c100 = e0; c.dz10 = e1 - e0; c.c110 = f0; c.dz11 = f1 - f0;
+    }
+    const float dt = (float)dt64;
+    float dvs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, B[4];
+    for (int s = 0; s < p.n_samples; s++) {
+        dvs[0] = trilinear(c, x[0], x[1], x[2]);
+        eval_transfer32<false>(p.tf, pairs, dt, dvs, rgba, B);
+        x[0] += st[0]; x[1] += st[1]; x[2] += st[2];
+    }
+}
+
+template <int KIND, bool FAST>
 __global__ void __launch_bounds__(OCT_THREADS) octree_cast_kernel(const __grid_constant__ OctParams p)
 {
+    extern __shared__ float2 s_oct_pairs[];
+    if (FAST) {
+        for (int i = threadIdx.x; i < p.tf.total_bins; i += OCT_THREADS) s_oct_pairs[i] = p.tf.pairs[i];
+        __syncthreads();
+    }
     const long long px = (long long)blockIdx.x * OCT_THREADS + threadIdx.x;
     if (px >= (long long)p.nx * p.ny) return;
     double vp[3], vd[3], o[3], d[3];
@@ -108,9 +148,11 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_cast_kernel(const __grid_c
     TFShared64 t64;
     t64.values = p.tf.values; t64.d0 = p.tf.d0; t64.dy = p.tf.dy;
     double acc[4];
+    float acc32[4];
+    bool touched = false;
     double *out = p.image + px * 4;
 #pragma unroll
-    for (int c = 0; c < 4; c++) acc[c] = out[c];
+    for (int c = 0; c < 4; c++) { acc[c] = out[c]; acc32[c] = (float)acc[c]; }
     int sp = 0;
     snode[0] = 0;
     bool entering = true;
@@ -125,7 +167,9 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_cast_kernel(const __grid_c
             if (tx1 < 0 || ty1 < 0 || tz1 < 0 || n < 0) { sp--; entering = false; continue; }
             if (p.leaf[2 * n]) {
                 const double t_in = std_max(std_max(tx0, ty0), tz0), t_out = std_min(std_min(tx1, ty1), tz1);
-                oct_sample_cell<KIND>(p, t64, p.cells + 14ll * p.leaf[2 * n + 1], vp, vd, ddiv(t_in, len), ddiv(t_out, len), acc);
+                const double *cell = p.cells + 14ll * p.leaf[2 * n + 1];
+                if (FAST) { oct_sample_cell_fast(p, s_oct_pairs, cell, vp, vd, ddiv(t_in, len), ddiv(t_out, len), acc32); touched = true; }
+                else oct_sample_cell<KIND>(p, t64, cell, vp, vd, ddiv(t_in, len), ddiv(t_out, len), acc);
                 sp--; entering = false; continue;
             }
             i = oct_first_node(tx0, ty0, tz0, txm, tym, tzm);
@@ -146,8 +190,18 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_cast_kernel(const __grid_c
         snode[sp] = p.child[8 * n + (i ^ a)];
         entering = true;
     }
+    if (FAST) {
+        // channels the sampler never writes (alpha of a non-grey render, pixels whose ray met no cell) keep their fp64
+        // initial value bit for bit
+        if (touched) {
 #pragma unroll
-    for (int c = 0; c < 4; c++) out[c] = acc[c];
+            for (int c = 0; c < 4; c++)
+                if (c < 3 || p.tf.grey) out[c] = (double)acc32[c];
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) out[c] = acc[c];
+    }
 }
 
 }  // namespace ytb

@@ -1043,10 +1043,11 @@ extern "C" int ytb200_octree_set_cells(ytb200_octree *o, int64_t n_cells, const 
 }
 
 extern "C" int ytb200_frame_cast_octree(ytb200_frame *f, int kind, ytb200_octree *o, const ytb200_tf *tf, int n_samples,
-                                        ytb200_stats *stats)
+                                        int precision, ytb200_stats *stats)
 {
     if (!f || !o) return fail(E_ARG, "NULL argument");
     if (kind < 0 || kind > 2) return fail(E_ARG, "bad sampler kind %d", kind);
+    if (precision != YTB200_PREC_FAST && precision != YTB200_PREC_EXACT) return fail(E_ARG, "bad precision %d", precision);
     if (f->ctx != o->ctx) return fail(E_ARG, "frame and octree belong to different contexts");
     if (!f->pos_px || !f->dir_px) return fail(E_ARG, "cast_through_octree reads per-pixel vp_pos / vp_dir: the frame has none (plane-parallel description)");
     if (!o->cells_dev) return fail(E_STATE, "ytb200_octree_set_cells first");
@@ -1077,12 +1078,19 @@ extern "C" int ytb200_frame_cast_octree(ytb200_frame *f, int kind, ytb200_octree
     p.child = o->child_dev; p.leaf = o->leaf_dev; p.cells = o->cells_dev;
     for (int i = 0; i < 3; i++) { p.dle[i] = o->dle[i]; p.dre[i] = o->dre[i]; p.size[i] = o->size[i]; }
     p.n_samples = n_samples < 1 ? 1 : n_samples;
+    p.inv_ns = 1.0 / (double)p.n_samples;
     if (tf) p.tf = tf->d;
     const long long npx = (long long)p.nx * p.ny;
     const unsigned grid = (unsigned)((npx + OCT_THREADS - 1) / OCT_THREADS);
-    if (kind == YTB200_VOLUME_RENDER) octree_cast_kernel<KIND_VR><<<grid, OCT_THREADS, 0, st>>>(p);
-    else if (kind == YTB200_INTERPOLATED_PROJECTION) octree_cast_kernel<KIND_IPROJ><<<grid, OCT_THREADS, 0, st>>>(p);
-    else octree_cast_kernel<KIND_PROJ><<<grid, OCT_THREADS, 0, st>>>(p);
+    if (kind == YTB200_VOLUME_RENDER && precision == YTB200_PREC_FAST) {
+        const size_t smem = (size_t)tf->d.total_bins * sizeof(float2);
+        if (smem > 200 * 1024) return fail(E_UNSUPPORTED, "transfer function tables (%zu B) exceed shared memory", smem);
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(octree_cast_kernel<KIND_VR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        octree_cast_kernel<KIND_VR, true><<<grid, OCT_THREADS, smem, st>>>(p);
+    } else if (kind == YTB200_VOLUME_RENDER) octree_cast_kernel<KIND_VR, false><<<grid, OCT_THREADS, 0, st>>>(p);
+    else if (kind == YTB200_INTERPOLATED_PROJECTION) octree_cast_kernel<KIND_IPROJ, false><<<grid, OCT_THREADS, 0, st>>>(p);
+    else octree_cast_kernel<KIND_PROJ, false><<<grid, OCT_THREADS, 0, st>>>(p);
     CK(cudaGetLastError());
     if (stats) {
         CK(cudaEventRecord(f->ctx->ev1, st));

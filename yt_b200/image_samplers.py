@@ -156,7 +156,9 @@ class ImageSampler:
         """image_samplers.pyx:202-299: every pixel's ray walks the octree front to back and the sampler's per-cell body
         runs on each terminal cell, over ``pg``'s single field of shape (n_cells, 14, 1) -- 8 vertex values, left
         edge, right edge per cell (render_source.py:669-680).  The z-buffer is not consulted (as in the reference).
-        Runs at once (one launch) and leaves the result in the caller's image."""
+        Runs at once (one launch) and leaves the result in the caller's image.  ``precision="fast"`` (default) samples
+        the volume render in fp32, ``"exact"`` does everything in fp64 in the reference's order; the projection kinds
+        are fp64 either way."""
         from .octree_raytracing import _OctreeRayTracing
         if not isinstance(pg, PartitionedGrid):
             raise TypeError("Argument 'pg' has incorrect type (expected PartitionedGrid, got %s)" % type(pg).__name__)
@@ -178,7 +180,7 @@ class ImageSampler:
         fr.upload(self.aimage_host, self.azbuffer)
         L.check(L.load().ytb200_frame_cast_octree(fr.handle, int(self.kind), oct.handle,
                                                   self._tables.handle if self._tables is not None else None,
-                                                  int(self.n_samples), None))
+                                                  int(self.n_samples), int(self._precision), None))
         fr.download(self.aimage_host)
 
     # -- batched entry used by the scene mirror ---------------------------------------------------------
