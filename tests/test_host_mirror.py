@@ -8,6 +8,7 @@ import pytest
 
 import yt_b200 as yt
 from oracle import oracle as O
+from tests import common as T
 from yt_b200 import loaders
 from yt_b200.volume_rendering import ColorTransferFunction, ProjectionTransferFunction, Scene, ZBuffer
 from yt_b200.volume_rendering.image_array import ImageArray
@@ -110,3 +111,34 @@ def test_scene_bookkeeping():
     assert sc.camera.lens.lens_type == "perspective"
     with pytest.raises(RuntimeError):
         sc.add_camera(ds, lens_type="no-such-lens")
+
+
+def test_octree_cell_dataset_feeds_the_octree_source_like_the_reference():
+    """load_octree_cells: the arrays OctreeRayTracing / OctreeVolumeSource.render read from the data source
+    (octree_raytracing.py:19-41, render_source.py:667-680) -- unitary centres, dx = 2**-(level + 1), levels shifted by
+    lvl_min = min_level + 1, and vertex data whose axes 0 and 2 set_fields swaps back to x-major."""
+    import yt_b200 as yt
+    from yt_b200.loaders import OctreeIndex
+    ipos, lvl, centre, dx = T.random_octree(depth=5, max_level=4, p_refine=0.45, seed=3)
+    cells = T.octree_cells(centre, dx, 5)
+    vd = cells[:, :8].T.reshape(2, 2, 2, -1)                  # indexed (x, y, z, cell)
+    ds = yt.load_octree_cells(centre, lvl - 1, {"density": vd})
+    src = ds.all_data()
+    assert isinstance(ds.index, OctreeIndex) and list(src.blocks) == []
+    assert np.array_equal(src["dx"], dx) and np.array_equal(src["grid_level"], lvl - 1)
+    assert np.array_equal(np.stack([src[k] for k in "xyz"], -1), centre)
+    assert ds.min_level == 0 and ds.max_level == int(lvl.max()) - 1
+    # what OctreeRayTracing.__init__ computes from them equals the tree inputs of the scenario
+    lvl_min = ds.min_level + 1
+    depth = lvl_min + ds.max_level + 1
+    assert depth == 5
+    assert np.array_equal(np.floor(centre * (1 << depth)).astype("int64"), ipos)
+    assert np.array_equal(src["grid_level"] + lvl_min, lvl)
+    # set_fields' layout fix (octree_raytracing.py:93-98) on the source's vertex data gives corner x*4 + y*2 + z
+    data = src.vertex_centered_data("density").swapaxes(0, 2).reshape(8, -1)
+    assert np.array_equal(data.T, cells[:, :8])
+    lo, hi = src.quantities["Extrema"]("density", non_zero=True)
+    assert lo == cells[:, :8].min() and hi == cells[:, :8].max()
+    assert ds.field_info[("stream", "density")].take_log
+    with pytest.raises(RuntimeError):
+        yt.load_octree_cells(centre, lvl - 1, {"density": vd[:, :, :, :-1]})
