@@ -16,7 +16,7 @@
 namespace ytb {
 
 constexpr int OCT_MAX_LEVELS = 32;   // frames of the traversal stack: root + max_depth (<= 30) levels
-constexpr int OCT_THREADS = 128;
+constexpr int OCT_THREADS = 128, OCT_TILE_I = 8, OCT_TILE_J = 16;
 
 struct OctParams {
     int nx, ny;
@@ -94,7 +94,8 @@ __device__ __forceinline__ void oct_sample_cell_fast(const OctParams &p, const f
     float x[3], st[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-        const double le = cell[8 + i], idds = 1.0 / (cell[11 + i] - le);
+        // 1 / dds to fp32 accuracy is enough here: it scales the already-formed difference pos - left_edge
+        const double le = cell[8 + i], idds = (double)__frcp_rn((float)(cell[11 + i] - le));
         x[i] = (float)((fma(tmid, vd[i], vp[i]) - le) * idds);
         st[i] = (float)(vd[i] * idds * dt64);
     }
@@ -122,8 +123,13 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_cast_kernel(const __grid_c
         for (int i = threadIdx.x; i < p.tf.total_bins; i += OCT_THREADS) s_oct_pairs[i] = p.tf.pairs[i];
         __syncthreads();
     }
-    const long long px = (long long)blockIdx.x * OCT_THREADS + threadIdx.x;
-    if (px >= (long long)p.nx * p.ny) return;
+    // a CTA is an 8 x 16 pixel tile, its warps 4 x 8 patches: neighbouring rays take nearly the same path through the tree
+    const int tiles_j = (p.ny + OCT_TILE_J - 1) / OCT_TILE_J;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int vi = (blockIdx.x / tiles_j) * OCT_TILE_I + (warp >> 1) * 4 + (lane >> 3);
+    const int vj = (blockIdx.x % tiles_j) * OCT_TILE_J + (warp & 1) * 8 + (lane & 7);
+    if (vi >= p.nx || vj >= p.ny) return;
+    const long long px = (long long)vi * p.ny + vj;
     double vp[3], vd[3], o[3], d[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) { vp[i] = p.pos_px[px * 3 + i]; vd[i] = p.dir_px[px * 3 + i]; }
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_cast_kernel(const __grid_c
         d[i] = ddiv(vd[i], len);
         if (d[i] < 0.0) { o[i] = dsub(p.size[i], o[i]); d[i] = -d[i]; a |= 4 >> i; }
     }
+    const double inv_len = 1.0 / len;   // FAST only: t / |v_dir| as a product
     double st0[OCT_MAX_LEVELS][3], st1[OCT_MAX_LEVELS][3];
     int snode[OCT_MAX_LEVELS], snext[OCT_MAX_LEVELS];
 #pragma unroll
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_cast_kernel(const __grid_c
             if (p.leaf[2 * n]) {
                 const double t_in = std_max(std_max(tx0, ty0), tz0), t_out = std_min(std_min(tx1, ty1), tz1);
                 const double *cell = p.cells + 14ll * p.leaf[2 * n + 1];
-                if (FAST) { oct_sample_cell_fast(p, s_oct_pairs, cell, vp, vd, ddiv(t_in, len), ddiv(t_out, len), acc32); touched = true; }
+                if (FAST) { oct_sample_cell_fast(p, s_oct_pairs, cell, vp, vd, t_in * inv_len, t_out * inv_len, acc32); touched = true; }
                 else oct_sample_cell<KIND>(p, t64, cell, vp, vd, ddiv(t_in, len), ddiv(t_out, len), acc);
                 sp--; entering = false; continue;
             }

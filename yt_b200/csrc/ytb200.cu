@@ -1080,8 +1080,7 @@ extern "C" int ytb200_frame_cast_octree(ytb200_frame *f, int kind, ytb200_octree
     p.n_samples = n_samples < 1 ? 1 : n_samples;
     p.inv_ns = 1.0 / (double)p.n_samples;
     if (tf) p.tf = tf->d;
-    const long long npx = (long long)p.nx * p.ny;
-    const unsigned grid = (unsigned)((npx + OCT_THREADS - 1) / OCT_THREADS);
+    const unsigned grid = (unsigned)(((p.nx + OCT_TILE_I - 1) / OCT_TILE_I) * ((p.ny + OCT_TILE_J - 1) / OCT_TILE_J));
     if (kind == YTB200_VOLUME_RENDER && precision == YTB200_PREC_FAST) {
         const size_t smem = (size_t)tf->d.total_bins * sizeof(float2);
         if (smem > 200 * 1024) return fail(E_UNSUPPORTED, "transfer function tables (%zu B) exceed shared memory", smem);
