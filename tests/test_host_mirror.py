@@ -142,3 +142,24 @@ def test_octree_cell_dataset_feeds_the_octree_source_like_the_reference():
     assert ds.field_info[("stream", "density")].take_log
     with pytest.raises(RuntimeError):
         yt.load_octree_cells(centre, lvl - 1, {"density": vd[:, :, :, :-1]})
+
+
+def test_fake_random_ds_draws_like_the_reference_fixture():
+    """yt/testing.py:345-436: one RandomState(0x4D3D3D3) stream, density drawn first, then the velocities."""
+    from yt_b200.testing import fake_random_ds
+    ds = fake_random_ds(16, nprocs=8)
+    prng = np.random.RandomState(0x4D3D3D3)
+    want = {f: prng.random_sample((16, 16, 16)) for f in ("density", "velocity_x", "velocity_y", "velocity_z")}
+    assert len(ds.index.grids) == 8 and [k[1] for k in ds.field_list] == list(want)
+    for g in ds.index.grids:
+        lo = np.rint((g.LeftEdge - ds.domain_left_edge) * 16).astype(int)
+        hi = lo + g.ActiveDimensions
+        for f, v in want.items():
+            assert np.array_equal(g[("stream", f)], v[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]])
+    neg = fake_random_ds([4, 5, 6], peak_value=3.0, fields=("density", "velocity_x"), negative=[False, True])
+    prng = np.random.RandomState(0x4D3D3D3)
+    d0 = prng.random_sample((4, 5, 6)) * 3.0
+    d1 = (prng.random_sample((4, 5, 6)) - 0.5) * 3.0
+    g = neg.index.grids[0]
+    assert np.array_equal(g[("stream", "density")], d0) and np.array_equal(g[("stream", "velocity_x")], d1)
+    assert ds.default_field == ("stream", "density") and ds.field_info[("stream", "density")].take_log

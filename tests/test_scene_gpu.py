@@ -190,3 +190,22 @@ def test_oversized_leaves_are_cut_into_pieces(lens, grey, gpu, monkeypatch):
             want, _ = oracle_render(sc)
     assert T.normalised_diff(images[1500], images[2 ** 31], grey) <= 2e-5
     assert T.normalised_diff(images[1500], want, grey) <= 1e-4
+
+
+def test_baseline_config0_fake_random_ds_scene(gpu):
+    """BASELINE.json configs[0]: fake_random_ds(64), Scene + VolumeSource with the default transfer function (512 bins,
+    10 layers, log10 density), default corner camera, PlaneParallelLens, 512 x 512 -- the reference's own CPU-runnable
+    case (~1.3e7 cells, ~1.3e8 samples), against the oracle."""
+    from yt_b200.testing import fake_random_ds
+    ds = fake_random_ds(64)
+    sc = yt.create_scene(ds)
+    src = sc.get_source()
+    assert tuple(sc.camera.resolution) == (512, 512) and sc.camera.lens.lens_type == "plane-parallel"
+    assert src.log_field and src.num_samples == 10
+    im = np.asarray(sc.render())
+    assert src.transfer_function.nbins == 512
+    want, nbricks = oracle_render(sc)
+    assert nbricks == 1
+    assert im.shape == (512, 512, 4) and want[:, :, :3].max() > 0
+    assert T.normalised_diff(im, want, False) <= 1e-4
+    assert np.all(im[:, :, 3] == 1.0)
