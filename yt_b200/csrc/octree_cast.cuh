@@ -4,7 +4,7 @@
 // One thread owns one pixel: it walks the tree front to back and samples every terminal cell it meets with the
 // sampler's per-cell body, so the reference's compositing order along a ray is kept by construction.  The
 // reference recurses (proc_subtree); here the recursion is an explicit per-thread stack of (t0, t1, node, next
-// child) frames -- the same arithmetic in the same order (tm = (t0 + t1) * 0.5 per level, std::max / std::min
+// child) frames for the ancestors that still have children to visit, the current node being kept in registers -- the same arithmetic in the same order (tm = (t0 + t1) * 0.5 per level, std::max / std::min
 // written with the comparison libstdc++ uses), all fp64 without contraction: every operation is the reference's,
 // so the image equals the reference's bit for bit (up to libm's sqrt, which is correctly rounded on both sides).
 // That is the EXACT precision and what the projection kinds always use (they carry the 1e-6 bar); the volume render's
@@ -160,42 +160,53 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_cast_kernel(const __grid_c
     double *out = p.image + px * 4;
 #pragma unroll
     for (int c = 0; c < 4; c++) { acc[c] = out[c]; acc32[c] = (float)acc[c]; }
-    int sp = 0;
-    snode[0] = 0;
-    bool entering = true;
-    while (sp >= 0) {
-        const double tx0 = st0[sp][0], ty0 = st0[sp][1], tz0 = st0[sp][2];
-        const double tx1 = st1[sp][0], ty1 = st1[sp][1], tz1 = st1[sp][2];
-        const double txm = dmul(dadd(tx0, tx1), 0.5), tym = dmul(dadd(ty0, ty1), 0.5), tzm = dmul(dadd(tz0, tz1), 0.5);
-        const int n = snode[sp];
-        int i;
-        if (entering) {
+    // The current node's frame lives in registers; the stack holds only those ancestors that still have a child to
+    // visit (a node whose last child is being entered is not stacked: the recursion's tail call), so terminal cells --
+    // most of the nodes a ray meets -- never touch local memory.
+    double tx0 = st0[0][0], ty0 = st0[0][1], tz0 = st0[0][2], tx1 = st1[0][0], ty1 = st1[0][1], tz1 = st1[0][2];
+    int n = 0, sp = 0, i = 0;
+    for (;;) {
+        bool restacked = false;
+        {
             // proc_subtree prologue (hpp:270-289)
-            if (tx1 < 0 || ty1 < 0 || tz1 < 0 || n < 0) { sp--; entering = false; continue; }
-            if (p.leaf[2 * n]) {
+            bool done = tx1 < 0 || ty1 < 0 || tz1 < 0 || n < 0;
+            if (!done && p.leaf[2 * n]) {
                 const double t_in = std_max(std_max(tx0, ty0), tz0), t_out = std_min(std_min(tx1, ty1), tz1);
                 const double *cell = p.cells + 14ll * p.leaf[2 * n + 1];
                 if (FAST) { oct_sample_cell_fast(p, s_oct_pairs, cell, vp, vd, t_in * inv_len, t_out * inv_len, acc32); touched = true; }
                 else oct_sample_cell<KIND>(p, t64, cell, vp, vd, ddiv(t_in, len), ddiv(t_out, len), acc);
-                sp--; entering = false; continue;
+                done = true;
             }
-            i = oct_first_node(tx0, ty0, tz0, txm, tym, tzm);
-        } else {
-            i = snext[sp];
-            if (i >= 8) { sp--; continue; }
+            if (done) {
+                // return to the nearest ancestor with a child left
+                if (sp == 0) break;
+                sp--;
+                tx0 = st0[sp][0]; ty0 = st0[sp][1]; tz0 = st0[sp][2];
+                tx1 = st1[sp][0]; ty1 = st1[sp][1]; tz1 = st1[sp][2];
+                n = snode[sp]; i = snext[sp];
+                restacked = true;   // slot sp still holds this frame's t0 / t1 / node
+            }
         }
-        if (sp + 1 >= OCT_MAX_LEVELS) { sp--; entering = false; continue; }   // deeper than any tree the host accepts
+        const double txm = dmul(dadd(tx0, tx1), 0.5), tym = dmul(dadd(ty0, ty1), 0.5), tzm = dmul(dadd(tz0, tz1), 0.5);
+        if (!restacked) i = oct_first_node(tx0, ty0, tz0, txm, tym, tzm);
         // child i: lower half of an axis when its bit is clear, upper half when set; its successor along an axis is
         // i with that bit set, or 8 (leave the node) -- the eight cases of the switch at hpp:301-341
         const double c0x = (i & 4) ? txm : tx0, c1x = (i & 4) ? tx1 : txm;
         const double c0y = (i & 2) ? tym : ty0, c1y = (i & 2) ? ty1 : tym;
         const double c0z = (i & 1) ? tzm : tz0, c1z = (i & 1) ? tz1 : tzm;
-        snext[sp] = oct_next_node(c1x, c1y, c1z, (i & 4) ? 8 : (i | 4), (i & 2) ? 8 : (i | 2), (i & 1) ? 8 : (i | 1));
-        sp++;
-        st0[sp][0] = c0x; st0[sp][1] = c0y; st0[sp][2] = c0z;
-        st1[sp][0] = c1x; st1[sp][1] = c1y; st1[sp][2] = c1z;
-        snode[sp] = p.child[8 * n + (i ^ a)];
-        entering = true;
+        const int nxt = oct_next_node(c1x, c1y, c1z, (i & 4) ? 8 : (i | 4), (i & 2) ? 8 : (i | 2), (i & 1) ? 8 : (i | 1));
+        if (nxt < 8) {
+            if (sp >= OCT_MAX_LEVELS) break;   // deeper than any tree the host accepts
+            if (!restacked) {
+                st0[sp][0] = tx0; st0[sp][1] = ty0; st0[sp][2] = tz0;
+                st1[sp][0] = tx1; st1[sp][1] = ty1; st1[sp][2] = tz1;
+                snode[sp] = n;
+            }
+            snext[sp] = nxt;
+            sp++;
+        }
+        n = p.child[8 * n + (i ^ a)];
+        tx0 = c0x; ty0 = c0y; tz0 = c0z; tx1 = c1x; ty1 = c1y; tz1 = c1z;
     }
     if (FAST) {
         // channels the sampler never writes (alpha of a non-grey render, pixels whose ray met no cell) keep their fp64
