@@ -163,3 +163,36 @@ def test_fake_random_ds_draws_like_the_reference_fixture():
     g = neg.index.grids[0]
     assert np.array_equal(g[("stream", "density")], d0) and np.array_equal(g[("stream", "velocity_x")], d1)
     assert ds.default_field == ("stream", "density") and ds.field_info[("stream", "density")].take_log
+
+
+def test_camera_view_sequences_and_auto_defaults():
+    """camera.py:310-346, 598-760: iter_rotate / iter_move / iter_zoom step the camera like n calls of rotate /
+    set_position / zoom; auto=True frames the box of the cell centres."""
+    arr = np.random.default_rng(3).random((8, 8, 8)) + 0.1
+    ds = yt.load_uniform_grid({"density": arr}, arr.shape, nprocs=8)
+    sc = Scene()
+    cam = sc.add_camera(ds)
+    ref = sc.add_camera(ds)
+    assert sc.get_camera() is ref
+    sc.set_camera(cam)
+    assert sc.camera is cam
+    steps = list(cam.iter_rotate(0.6, 3))
+    for _ in range(3):
+        ref.rotate(0.2)
+    assert steps == [0, 1, 2]
+    assert np.allclose(cam.unit_vectors, ref.unit_vectors) and np.allclose(cam.position, ref.position)
+    p0 = cam.position.copy()
+    for _ in cam.iter_move([2.0, 3.0, 4.0], 4):
+        pass
+    assert np.allclose(cam.position, [2.0, 3.0, 4.0])
+    for _ in cam.iter_move([4.0, 1.5, 8.0], 5, exponential=True):
+        pass
+    assert np.allclose(cam.position, [4.0, 1.5, 8.0]) and not np.allclose(p0, cam.position)
+    assert np.allclose(cam.normal_vector, (cam.focus - cam.position) / np.linalg.norm(cam.focus - cam.position))
+    w0 = cam.width.copy()
+    assert len(list(cam.iter_zoom(8.0, 3))) == 3
+    assert np.allclose(cam.width[:2], w0[:2] / 8.0) and cam.width[2] == w0[2]
+    auto = sc.add_camera(ds, auto=True)
+    # cell centres span [1/16, 15/16] on every axis: the diagonal of that box is the width
+    assert np.allclose(auto.width, np.sqrt(3.0) * 14.0 / 16.0)
+    assert np.allclose(auto.position, ds.domain_right_edge) and np.allclose(auto.focus, ds.domain_center)

@@ -55,6 +55,10 @@ class Camera(Orientation):
             self._domain_width = np.ones(3)
         super().__init__(self._focus - self._position, self.north_vector, steady_north=False)
         self.set_lens(lens_type)
+        if auto:
+            if self.data_source is None:
+                raise RuntimeError("auto=True needs a data source")
+            self.set_defaults_from_data_source(self.data_source)
 
     # -- properties with the reference's side effects -------------------------------------------------
     @property
@@ -195,6 +199,48 @@ class Camera(Orientation):
     def zoom(self, factor):
         self._width[:2] = self._width[:2] / factor
         self.switch_orientation()
+
+    # -- sequences of views (camera.py:598-760): generators that move the camera one step per iteration ---
+    def iter_rotate(self, theta, n_steps, rot_vector=None, rot_center=None):
+        dtheta = (1.0 * theta) / n_steps
+        for i in range(n_steps):
+            self.rotate(dtheta, rot_vector=rot_vector, rot_center=rot_center)
+            yield i
+
+    def iter_move(self, final, n_steps, exponential=False):
+        """Towards ``final`` in ``n_steps`` equal displacements, or equal ratios per component if ``exponential``."""
+        final = _vec3(final)
+        if exponential:
+            dx = ((final / self._position) * 1.0) ** (1.0 / n_steps)
+        else:
+            dx = (final - self._position) * 1.0 / n_steps
+        for i in range(n_steps):
+            self.set_position(self._position * dx if exponential else self._position + dx)
+            yield i
+
+    def iter_zoom(self, final, n_steps):
+        f = final ** (1.0 / n_steps)
+        for i in range(n_steps):
+            self.zoom(f)
+            yield i
+
+    def set_defaults_from_data_source(self, data_source):
+        """camera.py:310-346 (what ``auto=True`` does): look at the data source's centre from the domain's right edge,
+        with a field of view as wide as the diagonal of the box of its cell centres."""
+        ds = data_source.ds
+        grids = [g for g, _ in data_source.blocks]
+        lo = np.min([g.LeftEdge + 0.5 * g.dds for g in grids], axis=0)
+        hi = np.max([g.RightEdge - 0.5 * g.dds for g in grids], axis=0)
+        width = np.sqrt(((hi - lo) ** 2).sum())
+        self._width = np.array([width] * 3, dtype="float64")
+        self._focus = np.array(ds.domain_center, dtype="float64")
+        self._position = np.array(ds.domain_right_edge, dtype="float64")
+        self._domain_center = np.array(ds.domain_center, dtype="float64")
+        self._domain_width = np.array(ds.domain_width, dtype="float64")
+        Orientation.__init__(self, self._focus - self._position, self.north_vector, steady_north=False)
+        if self.lens is not None:
+            self.lens.setup_box_properties(self)
+        self._moved = True
 
     def __repr__(self):
         return ("<Camera Object>:\n\tposition:%s\n\tfocus:%s\n\tnorth_vector:%s\n\twidth:%s\n\tresolution:%s\n"

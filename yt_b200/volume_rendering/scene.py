@@ -64,6 +64,12 @@ class Scene:
     def camera(self):
         self._camera = None
 
+    def set_camera(self, camera):
+        self.camera = camera
+
+    def get_camera(self):
+        return self.camera
+
     # -- rendering --------------------------------------------------------------------------------------
     def _validate(self):
         for source in self.sources.values():
