@@ -196,3 +196,21 @@ def test_camera_view_sequences_and_auto_defaults():
     # cell centres span [1/16, 15/16] on every axis: the diagonal of that box is the width
     assert np.allclose(auto.width, np.sqrt(3.0) * 14.0 / 16.0)
     assert np.allclose(auto.position, ds.domain_right_edge) and np.allclose(auto.focus, ds.domain_center)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/yt/testing.py"), reason="needs the reference checkout")
+def test_orientation_fixture_equals_the_reference_construction():
+    """yt_b200.testing.fake_vr_orientation_test_ds against yt/testing.py:653-738 evaluated as written (the function body
+    only needs numpy; `import yt` itself does not work here)."""
+    from yt_b200.testing import fake_vr_orientation_test_ds
+    src = open("/root/reference/yt/testing.py").read()
+    a = src.index("def fake_vr_orientation_test_ds")
+    body = src[a:src.index("\ndef ", a + 10)].replace(
+        "from yt.loaders import load_uniform_grid", "load_uniform_grid = lambda data, shape, bbox=None: (data['density'][0], bbox)")
+    ns = {"np": np}
+    exec(body, ns)
+    for kw in ({}, {"N": 40, "scale": 3.0}):
+        want, bbox = ns["fake_vr_orientation_test_ds"](**kw)
+        ds = fake_vr_orientation_test_ds(**kw)
+        assert np.array_equal(ds.index.grids[0][("stream", "density")], want)
+        assert np.array_equal(ds.domain_left_edge, bbox[:, 0]) and np.array_equal(ds.domain_right_edge, bbox[:, 1])
