@@ -61,13 +61,13 @@ def bench_tf():
 
 def bench_camera(res):
     """Default camera of yt.create_scene on a unit-cube dataset (camera.py:127-137): corner view."""
-    from tests.common import make_camera
+    from yt_b200.synthetic import make_camera
     return make_camera("plane-parallel", resolution=(res, res))
 
 
 def sampler_call_args(cam, image, zbuffer):
-    from tests.common import sampler_args
-    args, kwargs = sampler_args(cam, zbuffer=zbuffer, image=image)
+    from yt_b200.volume_rendering.utils import sampler_arguments
+    args, kwargs = sampler_arguments(cam, zbuffer=zbuffer, image=image)
     kwargs.pop("camera_data")
     return args, kwargs
 
@@ -154,7 +154,7 @@ def split_slab(lo, hi, vd, centred):
 
 def amr_camera(res):
     """PerspectiveLens outside the domain corner looking at the centre (BASELINE configs[3])."""
-    from tests.common import make_camera
+    from yt_b200.synthetic import make_camera
     return make_camera("perspective", resolution=(res, res), position=[1.6, 1.4, 1.2], width=[0.9, 0.9, 1.0])
 
 
@@ -182,11 +182,39 @@ def lsu_pipe_estimate(kind, samples, kernel_ms, sm_mhz, sm_count):
 
 
 def recorded_traffic(workload):
-    """DRAM bytes per launch of the cast kernel from the committed ncu --set full capture, if any."""
+    """DRAM bytes per launch of the cast kernel from the committed ncu --set full capture of this workload at N=1."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         return json.load(open(p)).get(workload)
     return None
+
+
+def roofline_block(workload, kind, world, my_samples, kernel_ms, alg_bytes, clk, sm_count):
+    """The dominant kernel against the roof that bounds it.  The volume-render and interpolated-projection casts do
+    7.7 samples per HBM byte: their roof is the L1/shared LSU data pipe (one wavefront per cycle per SM; ncu
+    `l1tex__data_pipe_lsu_wavefronts`), so `bound`/`achieved`/`peak`/`frac` describe THAT pipe and the HBM figure
+    sits beside it as `hbm_frac`.  The ProjectionSampler cast reads every cell once and does ~10 instructions per
+    cell: its roof is HBM.  `traffic` is the recorded N=1 ncu figure of this workload (null at N > 1: not measured)."""
+    peak, peak_src, sm_max = measured_peak()
+    sm_mhz = (clk or {}).get("sm_mhz") or sm_max
+    hbm = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    lsu = lsu_pipe_estimate(kind, my_samples, kernel_ms, sm_mhz, sm_count)
+    issue = {"samples_per_s_per_sm": my_samples / (kernel_ms * 1e-3) / sm_count,
+             "lane_slots_per_sample_at_sm_clock": (sm_count * 128 * sm_mhz * 1e6) / (my_samples / (kernel_ms * 1e-3))}
+    traffic = recorded_traffic(workload) if world == 1 else None
+    common = {"kernel": "proj_kernel" if kind == "proj" else "cast_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
+              "traffic": traffic, "traffic_source": "recorded: ncu --set full of this workload at N=1 (profiles/traffic.json), not this run" if traffic else None,
+              "hbm_achieved_gbs": hbm, "hbm_peak_gbs": peak, "hbm_frac": hbm / peak, "peak_source": peak_src,
+              "lsu_pipe": lsu, "issue": issue}
+    if kind == "proj":
+        common.update({"bound": "hbm", "achieved": hbm, "peak": peak, "unit": "GB/s", "frac": hbm / peak})
+    else:
+        gw = lsu["wavefronts"] / (kernel_ms * 1e-3) / 1e9
+        common.update({"bound": "l1_lsu_pipe", "achieved": gw, "peak": sm_count * sm_mhz * 1e-3, "unit": "Gwavefronts/s",
+                       "frac": lsu["frac"],
+                       "note": "7.7 samples per HBM byte: the HBM fraction is structurally 1-2 % (hbm_frac); the unit that is full is the "
+                               "L1/shared LSU data pipe (two LDS.128 table rows per sample + 4 corner loads per cell), then instruction issue"})
+    return common
 
 
 # ------------------------------------------------------------------------------------------------
@@ -194,7 +222,7 @@ def recorded_traffic(workload):
 # ------------------------------------------------------------------------------------------------
 def cpu_render_sample(kind, n=256, res=512, threads=0, repeats=1):
     from oracle import oracle as O
-    from tests.common import vertex_centre
+    from yt_b200.loaders import vertex_centre_no_ghost as vertex_centre
     from yt_b200.synthetic import host_cells
     if O.ref_available():
         S, G = O.load_ref()
@@ -259,13 +287,50 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def single_rank_image(workload, ctx, frame, cam, sargs, tf, kcode, kind, dev):
+    """The workload's frame cast by THIS rank alone over the whole volume (world == 1 code path: one launch, no
+    compositing), on the caller's frame; returns the host image.  Reference for `parity_vs_n1`."""
+    from yt_b200 import _lib as L
+    from yt_b200 import device as D
+    from yt_b200 import synthetic
+    n, res, _ = WORKLOADS[workload]
+    if workload in AMR_WORKLOADS:
+        from yt_b200 import loaders
+        from yt_b200.amr_kdtree import AMRKDTree
+        base, tile, levels = AMR_WORKLOADS[workload]
+        grids, dd = synthetic.nested_amr_grids(base_cells=base, tile=tile, levels=levels, seed=SEED)
+        ds = loaders.load_amr_grids(grids, dd)
+        kd = AMRKDTree(ds, comm_rank=0, comm_size=1)
+        kd.set_fields([ds.default_field], [False], True)
+        bricks = kd.device_bricks(ctx, L.STORE_F32)
+        order = np.ascontiguousarray(kd.view_order(cam.lens.viewpoint), dtype=np.int64)
+    else:
+        centred = 0 if kind == "proj" else 1
+        vd = np.asarray(sargs[1], dtype=np.float64).ravel()[:3]
+        pieces = split_slab([0, 0, 0], [n, n, n], vd, centred)
+        bricks = D.BrickSet(ctx, len(pieces), 1, L.CELL_CENTRED if kind == "proj" else L.VERTEX_CENTRED, L.STORE_F32)
+        for i, (plo, phi) in enumerate(pieces):
+            if kind != "proj":
+                vol, pitch = synthetic.vertex_slab(n, plo, phi, SEED, dev), None
+            else:
+                vol, pitch = synthetic.cell_slab(n, plo, phi, SEED, dev)
+            bricks.attach(i, [vol.data_ptr()], 0, [plo[a] / n for a in range(3)], [phi[a] / n for a in range(3)],
+                          [phi[a] - plo[a] for a in range(3)], keep=vol, row_pitch=pitch)
+        bricks.commit()
+        order = np.arange(len(pieces), dtype=np.int64)
+    frame.clear()
+    frame.cast(kcode, bricks, order, tf=tf, n_samples=N_SAMPLES)
+    out = frame.download(np.empty((res, res, 4)))
+    del bricks
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from yt_b200 import _lib as L
     from yt_b200 import device as D
     from yt_b200 import synthetic
-    from yt_b200.parallel import BinarySwap
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -292,8 +357,8 @@ def run_ours(args):
         img_host[:] = 0.0
         zb_host[:] = 1.0
         from yt_b200 import image_samplers as S
-        from tests.common import sampler_args
-        sargs, skw = sampler_args(cam, zbuffer=zb_host, image=img_host)
+        from yt_b200.volume_rendering.utils import sampler_arguments
+        sargs, skw = sampler_arguments(cam, zbuffer=zb_host, image=img_host)
         if not amr:
             skw.pop("camera_data")
         skw["context"] = ctx
@@ -336,25 +401,15 @@ def run_ours(args):
             order = np.arange(len(pieces), dtype=np.int64)
             n_bricks = len(pieces)
             cells_desc = [n, n, n]
-        # multi-GPU compositing: binary swap over NVLink peer memory (YTB200_SWAP=nccl: the NCCL send/recv baseline)
-        peer = world > 1 and os.environ.get("YTB200_SWAP", "peer") != "nccl"
+        # multi-GPU compositing: binary swap over NVLink peer memory when every rank can map its peers, else the NCCL
+        # send/recv compositor (still entirely on the GPUs); YTB200_SWAP=nccl forces the baseline
         swap = partial = None
-        if peer:
-            # CUDA IPC needs every rank to see its peers' devices; if any rank cannot map a peer, ALL ranks take the
-            # NCCL send/recv compositor instead (still entirely on the GPUs)
-            from yt_b200.parallel import PeerSwap
-            ok = 1
-            try:
-                swap = PeerSwap(ctx, frame, path, cam.lens.viewpoint, rank, world, f32=(kind == "vr"))
-            except Exception as exc:  # noqa: BLE001
-                sys.stderr.write("rank %d: peer-memory swap unavailable (%s); using the NCCL compositor\n" % (rank, exc))
-                ok, swap = 0, None
-            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            peer = bool(flag.item())
-        if world > 1 and not peer:
-            swap = BinarySwap(ctx, res, res, path, cam.lens.viewpoint, rank, world)
-            partial = torch.empty((res, res, 8), dtype=torch.float64, device=dev)
+        peer = False
+        if world > 1:
+            from yt_b200.parallel import make_compositor
+            swap, peer = make_compositor(ctx, frame, path, cam.lens.viewpoint, rank, world, f32=(kind == "vr"))
+            if not peer:
+                partial = torch.empty((res, res, 8), dtype=torch.float64, device=dev)
 
         def cast_partial(timed=False):
             if peer:
@@ -449,11 +504,24 @@ def run_ours(args):
             kt.append(s.kernel_ms)
         kernel_ms = float(np.mean(kt))
 
+        # ---- the N-rank frame against the SAME frame cast by rank 0 alone (SCALE lines carry multi-GPU parity) ----
+        parity_vs_n1 = None
+        dev_img = None
+        if world > 1:
+            frame_device()
+            ctx.synchronize()
+            if rank == 0:
+                dev_img = frame.download(np.empty((res, res, 4)))
+            if not args.no_parity and (amr or n <= 1024):
+                if rank == 0:
+                    solo = single_rank_image(args.workload, ctx, frame, cam, sargs, tf, kcode, kind, dev)
+                    from yt_b200.metrics import normalised_diff, projection_diff
+                    parity_vs_n1 = normalised_diff(dev_img, solo, False) if kind == "vr" else projection_diff(dev_img[:, :, 0], solo[:, :, 0])
+                    del solo
+                    torch.cuda.empty_cache()
+                dist.barrier()
         e2e_out = None
         if peer:
-            # reference image of the device-timed route, for the check below
-            frame_device()
-            dev_img = frame.download(np.empty((res, res, 4)))
             e2e_out = D.pinned_empty((res, res, 4))
             frame.bind_host(img_host, zb_host)
         for _ in range(2):
@@ -470,10 +538,8 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    peak, peak_src, sm_max = measured_peak()
     elem = 4
     alg_bytes = my_elems * elem + 2.0 * res * res * 32 + res * res * 8 + (2.0 * res * res * 24 if amr else 0.0)
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     gs = total_samples / (ms_step * 1e-3) / 1e9
     gs_e2e = total_samples / (ms_e2e * 1e-3) / 1e9
     launches_per_step = 2 if world == 1 else 2 + swap.launches_per_composite
@@ -495,17 +561,12 @@ def run_ours(args):
                 "note": ("host (page-locked) image+zbuffer in, host image out through ytb200_render: the cast kernel reads/writes the host arrays in place over PCIe; bricks device-resident across frames" if world == 1 else "host (page-locked) image+zbuffer read in place by every rank (z-buffer by the cast, its strip of the initial colours by the swap), composited image copied out of rank 0's frame; checked equal to the device-route image")},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(args.workload), "peak_source": peak_src, "kernel": "cast_kernel",
-                     "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
-                     "note": ("volume-render cast: 7.7 samples per HBM byte, so the HBM fraction is structurally ~1-2 %; the units that are "
-                              "busy are the L1/shared LSU data pipe (85 %) and instruction issue (71 %, ncu r01zn), see `lsu_pipe` and `issue`") if kind == "vr" else
-                             "single-field projection walk: instruction issue 67 %, L1 LSU data pipe 57 % busy (ncu r01zd), DRAM traffic 2.4x algorithmic"},
-        "lsu_pipe": lsu_pipe_estimate(kind, my_samples, kernel_ms, (clk or {}).get("sm_mhz") or sm_max, ctx.sm_count),
-        "issue": {"samples_per_s_per_sm": total_samples / world / (kernel_ms * 1e-3) / ctx.sm_count,
-                  "lane_slots_per_sample_at_sm_clock": (ctx.sm_count * 128 * (clk["sm_mhz"] or sm_max) * 1e6) / (my_samples / (kernel_ms * 1e-3))
-                  if clk else None},
+        "roofline": roofline_block(args.workload, kind, world, my_samples, kernel_ms, alg_bytes, clk, ctx.sm_count),
     }
+    if parity_vs_n1 is not None:
+        line["parity_vs_n1"] = {"value": parity_vs_n1, "bar": 1e-4 if kind == "vr" else 1e-6,
+                                "what": ("normalised max |RGBA difference| (SURVEY.md A.5)" if kind == "vr" else "max |difference| / max |reference|")
+                                + " between this N-rank composited frame and the same frame cast by rank 0 alone in one launch"}
     if world == 1 and not args.no_cpu and not amr and n <= 1024:
         info = cpu_render_sample(kind, args.cpu_size, args.cpu_res, threads=0, repeats=2)
         v = info["samples"] / info["seconds"] / 1e9
@@ -525,6 +586,7 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=256)
     ap.add_argument("--cpu-res", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip rank 0's single-GPU render of the same frame (parity_vs_n1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

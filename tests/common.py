@@ -18,45 +18,8 @@ from yt_b200.volume_rendering.camera import Camera  # noqa: E402
 from yt_b200.volume_rendering.transfer_functions import ColorTransferFunction, MultiVariateTransferFunction, TransferFunction  # noqa: E402
 
 
-class FakeDS:
-    def __init__(self, le=(0, 0, 0), re=(1, 1, 1)):
-        self.domain_left_edge = np.array(le, dtype="float64")
-        self.domain_right_edge = np.array(re, dtype="float64")
-        self.domain_width = self.domain_right_edge - self.domain_left_edge
-        self.domain_center = 0.5 * (self.domain_left_edge + self.domain_right_edge)
-        self.ds = self
-
-    def all_data(self):
-        return self
-
-
-def make_camera(lens_type="plane-parallel", resolution=(64, 64), position=None, focus=None, width=None,
-                north=None, ds=None):
-    cam = Camera(None, ds or FakeDS(), lens_type=lens_type)
-    cam.resolution = resolution
-    if north is not None:
-        cam.north_vector = np.array(north, dtype="float64")
-    if position is not None:
-        cam.position = position
-    if focus is not None:
-        cam.focus = focus
-    if width is not None:
-        cam.width = width
-    return cam
-
-
-def sampler_args(cam, zbuffer=None, image=None):
-    """(args, kwargs) of the reference's ImageSampler.__init__, as utils.py:55-139 builds them."""
-    src = types.SimpleNamespace(zbuffer=None)
-    p = cam._get_sampler_params(src)
-    nx, ny = cam.resolution
-    img = np.zeros((nx, ny, 4), dtype="float64") if image is None else image
-    args = [np.atleast_3d(np.array(p["vp_pos"], dtype="float64")), np.atleast_3d(np.array(p["vp_dir"], dtype="float64")),
-            np.array(p["center"], dtype="float64"), p["bounds"], img, np.array(p["x_vec"], dtype="float64"),
-            np.array(p["y_vec"], dtype="float64"), np.array(p["width"], dtype="float64"), "KDTree"]
-    kwargs = {"lens_type": p["lens_type"], "camera_data": np.array(p["camera_data"], dtype="float64")}
-    kwargs["zbuffer"] = np.ones((nx, ny), "float64") if zbuffer is None else zbuffer
-    return args, kwargs
+from yt_b200.synthetic import BoxDomain as FakeDS, make_camera  # noqa: E402,F401
+from yt_b200.volume_rendering.utils import sampler_arguments as sampler_args  # noqa: E402,F401
 
 
 def vertex_centre(cells):
@@ -139,17 +102,7 @@ def multivariate_tf(bounds0=(0.0, 1.0), bounds1=(0.0, 2.0), grey=False):
     return mv
 
 
-def normalised_diff(img, ref, grey):
-    """rescale both with the reference's maxima, return max |difference|."""
-    cmax = ref[:, :, :3].sum(axis=2).max()
-    out = 0.0
-    if cmax > 0:
-        out = np.abs(np.clip(img[:, :, :3] / cmax, 0, 1) - np.clip(ref[:, :, :3] / cmax, 0, 1)).max()
-    if grey:
-        amax = ref[:, :, 3].max()
-        if amax > 0:
-            out = max(out, np.abs(np.clip(img[:, :, 3] / amax, 0, 1) - np.clip(ref[:, :, 3] / amax, 0, 1)).max())
-    return out
+from yt_b200.metrics import normalised_diff  # noqa: E402,F401
 
 
 # ---------------------------------------------------------------------------------------------------

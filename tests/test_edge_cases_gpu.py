@@ -147,3 +147,42 @@ def test_colour_walk_axis_aligned_and_planar_views(position, masked, gpu):
     assert T.normalised_diff(got, want, False) <= 1e-4
     got64 = T.run_scenario(sc, S, G, sampler_kwargs={"storage": "f64"})
     assert T.normalised_diff(got64, want, False) <= 1e-4
+
+
+def test_two_brick_sets_through_one_sampler_do_not_share_cached_footprints(gpu):
+    """the frame caches the per-brick pixel footprints of the last (set, order).  Two different single-brick
+    sets flushed through one sampler both have order [0], and the second temporary set may be allocated at the first
+    one's address -- the cache must be keyed on the set's generation, not its pointer."""
+    S, G = _mods()
+    cam = T.make_camera(resolution=(64, 64), width=[1.5, 1.5, 1.5])
+    img = np.zeros((64, 64, 4))
+    args, kw = T.sampler_args(cam, image=img)
+    kw.pop("camera_data")
+    tf = T.colour_tf(height=60.0)
+    s = S.VolumeRenderSampler(*args, tf, 10, **kw)
+    want = np.zeros((64, 64, 4))
+    a2, k2 = T.sampler_args(cam, image=want)
+    k2.pop("camera_data")
+    o = O.VolumeRenderSampler(*a2, tf, 10, **k2)
+    # a small brick in one corner of the view, then a large one covering the whole view
+    small = _unit_brick(4, 7)
+    geoms = [(np.array([0.0, 0.0, 0.0]), np.array([0.2, 0.2, 0.2])), (np.zeros(3), np.ones(3))]
+    for le, re in geoms:
+        s(G.PartitionedGrid(0, small[0], small[1], le, re, np.array(small[4], "int64")))
+        _ = s.aimage                                   # flush: a temporary brick set is built and freed
+        o(O.PartitionedGrid(0, small[0], small[1], le, re, np.array(small[4], "int64")), num_threads=0)
+    assert want[:, :, :3].max() > 0
+    assert T.normalised_diff(np.array(s.aimage), want, False) <= 1e-4
+    # the same set re-uploaded with another geometry and re-committed must not reuse the old footprints either
+    from yt_b200 import _lib as L
+    from yt_b200 import device as D
+    img[:] = 0.0
+    want[:] = 0.0
+    bs = D.BrickSet(s._ctx, 1, 1, L.VERTEX_CENTRED, s._storage)
+    for le, re in geoms:
+        bs.upload(0, small[0], small[1], le, re, small[4])
+        bs.commit()
+        s.cast_bricks(bs, np.zeros(1, dtype=np.int64))
+        _ = s.aimage
+        o(O.PartitionedGrid(0, small[0], small[1], le, re, np.array(small[4], "int64")), num_threads=0)
+    assert T.normalised_diff(np.array(s.aimage), want, False) <= 1e-4

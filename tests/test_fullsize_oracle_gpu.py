@@ -1,0 +1,184 @@
+"""Oracle differentials AT BASELINE.json's sizes: the frames the benchmark times, against the reference samplers.
+
+The CUDA cast renders the full frame; the compiled reference (``oracle/_ref``, the unmodified Cython samplers -- it
+travels to the GPU box; the C oracle, pinned bitwise to it, stands in if it is absent) casts a LATTICE of the very same
+rays through the very same fp32-rounded data widened to fp64:
+
+* the reference takes any ray set through its per-pixel ``vp_pos`` / ``vp_dir`` arrays (``generate_vector_info_null``,
+  lenses.pyx:196-207), so a (64, 64) sub-image holding every 32nd pixel's plane-parallel ray
+  (``generate_vector_info_plane_parallel``, lenses.pyx:179-192, same operation order) costs ~7e7 samples instead of 3e10;
+* the 1024^3 volume is handed to it as x-slabs in increasing ray parameter (what ``walk_volume`` does inside one brick,
+  SURVEY.md finding 6 / H14), downloaded one at a time, so the host never holds more than ~1.1 GB of fp64.
+
+Bars: volume render max-abs 1e-4 on the normalised RGBA, projection rtol 1e-6 of the largest integral.
+"""
+import numpy as np
+import pytest
+
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+SEED = 0          # bench.py's seed: these are the benchmark's volumes
+
+
+def _need_memory(gb):
+    import torch
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < gb * 2 ** 30:
+        pytest.skip("needs %d GB of free HBM" % gb)
+
+
+def _reference():
+    from oracle import oracle as O
+    if O.ref_available():
+        S, G = O.load_ref()
+        return S, G, "reference"
+    return O, O, "oracle"
+
+
+def lattice_rays(cam, args, ii, jj):
+    """vp_pos / vp_dir (len(ii), len(jj), 3) of the plane-parallel rays of pixels ii x jj, computed as
+    generate_vector_info_plane_parallel does (lenses.pyx:179-192)."""
+    nx, ny = cam.resolution
+    vp = np.asarray(args[0], "float64").ravel()
+    vd = np.asarray(args[1], "float64").ravel()[:3]
+    w = np.asarray(args[7], "float64")
+    px = w[0] * np.asarray(ii, "float64") / (nx - 1.0) - w[0] / 2.0
+    py = w[1] * np.asarray(jj, "float64") / (ny - 1.0) - w[1] / 2.0
+    pos = (vp[0:3][None, None, :] * px[:, None, None] + vp[3:6][None, None, :] * py[None, :, None]) + vp[9:12][None, None, :]
+    dirs = np.broadcast_to(vd, pos.shape)
+    return np.ascontiguousarray(pos), np.ascontiguousarray(dirs), vd
+
+
+def x_slabs(n, n_slabs, vd):
+    """Cell ranges [x0, x1) of `n_slabs` x-slabs in the order a ray of direction vd meets them."""
+    edges = np.linspace(0, n, n_slabs + 1).astype(int)
+    out = [(int(edges[k]), int(edges[k + 1])) for k in range(n_slabs)]
+    return out if vd[0] >= 0 else out[::-1]
+
+
+def reference_on_lattice(kind, cam, args, ii, jj, n, slab_of, centred, tf=None, n_samples=10, n_slabs=8, threads=0):
+    """The reference sampler of `kind` over the rays of pixels ii x jj through the n^3 volume, slab by slab.
+    `slab_of(x0, x1)` returns the host fp64 array of cells [x0, x1) (vertices [x0, x1] when `centred`)."""
+    S, G, label = _reference()
+    pos, dirs, vd = lattice_rays(cam, args, ii, jj)
+    img = np.zeros((len(ii), len(jj), 4))
+    a = list(args)
+    a[0], a[1], a[4] = pos, dirs, img
+    kw = {"lens_type": "lattice", "zbuffer": np.ones(img.shape[:2])}
+    if kind == "vr":
+        s = S.VolumeRenderSampler(*a, tf, n_samples, **kw)
+    elif kind == "iproj":
+        s = S.InterpolatedProjectionSampler(*a, n_samples, **kw)
+    else:
+        s = S.ProjectionSampler(*a, n_samples, **kw)
+    for x0, x1 in x_slabs(n, n_slabs, vd):
+        data = slab_of(x0, x1)
+        assert data.shape[0] == x1 - x0 + centred and data.dtype == np.float64
+        pg = G.PartitionedGrid(0, [data], np.ones((x1 - x0, n, n), "uint8"), np.array([x0 / n, 0.0, 0.0]), np.array([x1 / n, 1.0, 1.0]),
+                               np.array([x1 - x0, n, n], "int64"))
+        s(pg, num_threads=threads)
+        del pg, data
+    return np.array(s.aimage, copy=True), label
+
+
+def test_north_star_frame_matches_the_reference_on_a_ray_lattice(gpu):
+    """The 1024^3 @ 2048^2 frame bench.py times (same volume, camera, tables, n_samples), against the reference."""
+    import torch
+    from bench import N_SAMPLES, bench_camera, bench_tf
+    from yt_b200 import _lib as L
+    from yt_b200 import device as D
+    from yt_b200 import image_samplers as S
+    from yt_b200 import synthetic
+    N, R = 1024, 2048
+    _need_memory(12)
+    dev = torch.device("cuda", gpu.device)
+    cam, tf = bench_camera(R), bench_tf()
+    args, kw = T.sampler_args(cam)
+    kw.pop("camera_data")
+    s = S.VolumeRenderSampler(*args, tf, N_SAMPLES, **kw)
+    vol = synthetic.vertex_slab(N, [0, 0, 0], [N, N, N], SEED, dev)
+    bs = D.BrickSet(s._ctx, 1, 1, L.VERTEX_CENTRED, L.STORE_F32)
+    bs.attach(0, [vol.data_ptr()], 0, [0.0] * 3, [1.0] * 3, [N] * 3, keep=vol)
+    bs.commit()
+    s.cast_bricks(bs, np.arange(1, dtype=np.int64))
+    got = np.array(s.aimage)
+    ii = jj = np.arange(16, R, 32)
+    want, label = reference_on_lattice("vr", cam, args, ii, jj, N, lambda x0, x1: vol[x0:x1 + 1].cpu().numpy().astype("float64"), 1,
+                                       tf=tf, n_samples=N_SAMPLES)
+    sub = got[np.ix_(ii, jj)]
+    assert want[:, :, :3].max() > 0 and (want[:, :, :3].sum(axis=2) > 0).mean() > 0.3, label
+    err = T.normalised_diff(sub, want, False)
+    print("north star vs %s on a %dx%d ray lattice: normalised max diff %.3g" % (label, len(ii), len(jj), err))
+    assert err <= 1e-4
+    assert np.array_equal(sub[:, :, 3], want[:, :, 3])     # non-grey: alpha untouched (H9)
+
+
+def test_cfg3_random_field_projection_matches_the_reference_on_a_ray_lattice(gpu):
+    """BASELINE configs[2]: off-axis ProjectionSampler of the benchmark's random 1024^3 field at 2048^2."""
+    import torch
+    from bench import bench_camera
+    from yt_b200 import _lib as L
+    from yt_b200 import device as D
+    from yt_b200 import image_samplers as S
+    from yt_b200 import synthetic
+    N, R = 1024, 2048
+    _need_memory(8)
+    dev = torch.device("cuda", gpu.device)
+    cam = bench_camera(R)
+    args, kw = T.sampler_args(cam)
+    kw.pop("camera_data")
+    s = S.ProjectionSampler(*args, 10, **kw)
+    vol, pitch = synthetic.cell_slab(N, [0, 0, 0], [N, N, N], SEED, dev)
+    bs = D.BrickSet(s._ctx, 1, 1, L.CELL_CENTRED, L.STORE_F32)
+    bs.attach(0, [vol.data_ptr()], 0, [0.0] * 3, [1.0] * 3, [N] * 3, keep=vol, row_pitch=pitch)
+    bs.commit()
+    s.cast_bricks(bs, np.arange(1, dtype=np.int64))
+    got = np.array(s.aimage)
+    ii = jj = np.arange(16, R, 32)
+    want, label = reference_on_lattice("proj", cam, args, ii, jj, N, lambda x0, x1: vol[x0:x1].cpu().numpy().astype("float64"), 0)
+    sub = got[np.ix_(ii, jj)]
+    assert want[:, :, 0].max() > 0.5 and (want[:, :, 0] > 0).mean() > 0.3
+    err = np.abs(sub[:, :, 0] - want[:, :, 0]).max() / want[:, :, 0].max()
+    print("cfg3 vs %s on a %dx%d ray lattice: max diff / max %.3g" % (label, len(ii), len(jj), err))
+    assert err <= 1e-6
+    # per pixel too, wherever the integral is not a sliver of the volume's edge
+    big = want[:, :, 0] > 1e-3 * want[:, :, 0].max()
+    assert np.abs(sub[:, :, 0][big] / want[:, :, 0][big] - 1.0).max() <= 1e-6
+    assert np.all(got[:, :, 1:] == 0.0)
+
+
+def test_cfg2_full_frame_matches_the_reference(gpu):
+    """BASELINE configs[1] in full: 512^3 VolumeSource, ColorTransferFunction, off-axis 1024^2 -- every pixel."""
+    import torch
+    from bench import N_SAMPLES, bench_camera, bench_tf
+    from yt_b200 import _lib as L
+    from yt_b200 import device as D
+    from yt_b200 import image_samplers as S
+    from yt_b200 import synthetic
+    N, R = 512, 1024
+    _need_memory(4)
+    dev = torch.device("cuda", gpu.device)
+    cam, tf = bench_camera(R), bench_tf()
+    args, kw = T.sampler_args(cam)
+    kw.pop("camera_data")
+    s = S.VolumeRenderSampler(*args, tf, N_SAMPLES, **kw)
+    vol = synthetic.vertex_slab(N, [0, 0, 0], [N, N, N], SEED, dev)
+    bs = D.BrickSet(s._ctx, 1, 1, L.VERTEX_CENTRED, L.STORE_F32)
+    bs.attach(0, [vol.data_ptr()], 0, [0.0] * 3, [1.0] * 3, [N] * 3, keep=vol)
+    bs.commit()
+    s.cast_bricks(bs, np.arange(1, dtype=np.int64))
+    got = np.array(s.aimage)
+    Sr, Gr, label = _reference()
+    img = np.zeros((R, R, 4))
+    a2, kw2 = T.sampler_args(cam, image=img)
+    kw2.pop("camera_data")
+    ref = Sr.VolumeRenderSampler(*a2, tf, N_SAMPLES, **kw2)
+    data = vol.cpu().numpy().astype("float64")
+    pg = Gr.PartitionedGrid(0, [data], np.ones((N, N, N), "uint8"), np.zeros(3), np.ones(3), np.array([N] * 3, "int64"))
+    ref(pg, num_threads=0)
+    want = np.array(ref.aimage)
+    assert want[:, :, :3].max() > 0
+    err = T.normalised_diff(got, want, False)
+    print("cfg2 full frame vs %s: normalised max diff %.3g" % (label, err))
+    assert err <= 1e-4

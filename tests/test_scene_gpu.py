@@ -229,8 +229,6 @@ def _orientation_scene(lens_type, res=400):
     return sc, cam
 
 
-@pytest.mark.skipif(not os.environ.get("YTB200_RUN_UNVERIFIED"),
-                    reason="written at the end of round 1 when no GPU slot was left to run it once; enable with YTB200_RUN_UNVERIFIED=1")
 @pytest.mark.parametrize("view", ["perspective", "plane-parallel", "yaw", "pitch", "roll"])
 def test_vr_orientation_views_match_the_oracle(view, gpu):
     """test_vr_orientation.py:62-94 as parity tests: both lens types, then yaw / pitch / roll by pi about the origin.

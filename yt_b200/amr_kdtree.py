@@ -150,7 +150,9 @@ class AMRKDTree:
         self.tree = Tree(ds, comm_rank, comm_size, min_level=min_level, max_level=max_level, data_source=self.data_source)
         self._brick_of_node = {}     # native node index -> PartitionedGrid
         self._leaf_slot = None       # native node index -> position in the device brick table
-        self._device_sets = {}       # (device, storage) -> BrickSet over all leaves
+        self._device_sets = {}       # (device, storage, centred on device) -> BrickSet over all leaves
+        self._set_meta = {}          # id(BrickSet) -> (leaf slot table, piece plan) of that set
+        self._piece_plan = {}
 
     # -- data ------------------------------------------------------------------------------------------
     def set_fields(self, fields, log_fields, no_ghost, force=False):
@@ -164,6 +166,7 @@ class AMRKDTree:
         self.fields, self.log_fields, self.no_ghost = new_fields, new_log, no_ghost
         if regenerate:
             self._brick_of_node, self._device_sets, self._leaf_slot = {}, {}, None
+            self._set_meta, self._piece_plan = {}, {}
             self.current_vcds, self.current_saved_grids = [], []
         self.brick_dimensions = []
         self.bricks = np.array(list(self.traverse()), dtype=object)
@@ -227,13 +230,19 @@ class AMRKDTree:
         key = (ctx.device, storage, bool(centre_on_device))
         if key not in self._device_sets:
             leaves = [int(i) for i in self.tree.traverse()]
+            # slot table and piece plan belong to THIS set (another set of the same tree may cut its leaves differently)
             self._leaf_slot = np.full(len(self.tree.nodes["grid"]), -1, dtype="int64")
             self._leaf_slot[leaves] = np.arange(len(leaves))
+            self._piece_plan = {}
             if centre_on_device and leaves:
-                self._device_sets[key] = self._device_bricks_from_cells(leaves, ctx, storage)
+                bs = self._device_bricks_from_cells(leaves, ctx, storage)
             else:
-                self._device_sets[key] = build_brickset([self.get_brick_data(i) for i in leaves], ctx, storage)
-        return self._device_sets[key]
+                bs = build_brickset([self.get_brick_data(i) for i in leaves], ctx, storage)
+            self._device_sets[key] = bs
+            self._set_meta[id(bs)] = (self._leaf_slot, self._piece_plan)
+        bs = self._device_sets[key]
+        self._leaf_slot, self._piece_plan = self._set_meta[id(bs)]   # view_order() without `bricks` means this set
+        return bs
 
     def _device_bricks_from_cells(self, leaves, ctx, storage):
         from . import _lib as L
@@ -251,7 +260,7 @@ class AMRKDTree:
             pieces = _tree_leaves(tree)
             plans.append((node, grid, tree, pieces, n_slots))
             n_slots += len(pieces)
-        self._piece_plan = {}
+        self._piece_plan.clear()
         if n_slots != len(leaves):
             slot_of = {}
             for node, grid, tree, pieces, first in plans:
@@ -296,17 +305,18 @@ class AMRKDTree:
         ctx.synchronize()   # the cell arrays may be released once every leaf has been centred
         return out.commit()
 
-    def view_order(self, viewpoint, camera=None):
-        """Positions in the device brick table, in the order ``traverse(viewpoint)`` yields the leaves.  A leaf that
+    def view_order(self, viewpoint, camera=None, bricks=None):
+        """Positions in the device brick table `bricks` (default: the set ``device_bricks`` returned last), in the
+        order ``traverse(viewpoint)`` yields the leaves.  A leaf that
         was cut into pieces expands to its pieces in increasing ray parameter t (what walk_volume does inside ONE
         brick): along the ray direction for a plane-parallel lens, away from the common ray origin
         (the camera position) otherwise."""
         if self._leaf_slot is None:
             raise RuntimeError("device_bricks() must be called first")
+        leaf_slot, plan = (self._leaf_slot, self._piece_plan) if bricks is None else self._set_meta[id(bricks)]
         leaves = self.tree.traverse(viewpoint)
-        plan = getattr(self, "_piece_plan", None)
         if not plan:
-            return self._leaf_slot[leaves]
+            return leaf_slot[leaves]
         if camera is not None and camera.lens.lens_type == "plane-parallel":
             direction = np.asarray(camera.unit_vectors[2], dtype="float64") * float(camera.width[2])
             lower_first = lambda grid, ax, cut: direction[ax] >= 0          # noqa: E731
@@ -320,7 +330,7 @@ class AMRKDTree:
         for node in leaves:
             node = int(node)
             if node not in plan:
-                out.append(int(self._leaf_slot[node]))
+                out.append(int(leaf_slot[node]))
                 continue
             tree, grid, slot_of = plan[node]
 

@@ -4,6 +4,7 @@
 #include "../../include/ytb200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -65,7 +66,17 @@ struct ytb200_brickset {
     bool committed = false;
     bool any_mask = false;
     int64_t bytes = 0;
+    // process-unique id of this set's committed contents: a new value at creation and at every commit, so that a
+    // frame's cached footprints can never be taken for those of another set that reuses the address, nor for this
+    // set's bricks before a re-upload (see prepare_order)
+    uint64_t generation = 0;
 };
+
+static uint64_t next_generation()
+{
+    static std::atomic<uint64_t> g{0};
+    return ++g;
+}
 
 struct ytb200_tf {
     ytb200_ctx *ctx = nullptr;
@@ -85,7 +96,7 @@ struct ytb200_frame {
     int4 *extent_dev = nullptr;
     int64_t order_cap = 0;
     std::vector<int> order_host;
-    const ytb200_brickset *order_set = nullptr;
+    uint64_t order_generation = 0;   // ytb200_brickset::generation the cached order / footprints belong to (0: none)
 };
 
 struct DeviceGuard {
@@ -166,6 +177,7 @@ extern "C" int ytb200_bricks_create(ytb200_ctx *ctx, int64_t n_bricks, int n_fie
     s->ctx = ctx; s->n = n_bricks; s->n_fields = n_fields; s->centring = centring; s->storage = storage;
     s->host.resize((size_t)n_bricks);
     memset(s->host.data(), 0, sizeof(DevBrick) * (size_t)n_bricks);
+    s->generation = next_generation();
     *out = s;
     return 0;
 }
@@ -421,6 +433,7 @@ extern "C" int ytb200_bricks_commit(ytb200_brickset *s)
         CK(cudaStreamSynchronize(s->ctx->stream));
     }
     s->committed = true;
+    s->generation = next_generation();
     return 0;
 }
 
@@ -729,7 +742,7 @@ static int prepare_order(ytb200_frame *f, const ytb200_brickset *set, const int6
     if (!set->committed) return fail(E_STATE, "brick set not committed (call ytb200_bricks_commit)");
     if (set->ctx->device != f->ctx->device) return fail(E_ARG, "brick set and frame live on different devices");
     if (n_order < 0 || n_order > set->n * 64 + 1024) return fail(E_ARG, "bad n_order %lld", (long long)n_order);
-    bool same = f->order_set == set && (int64_t)f->order_host.size() == n_order;
+    bool same = f->order_generation != 0 && f->order_generation == set->generation && (int64_t)f->order_host.size() == n_order;
     if (same)
         for (int64_t i = 0; i < n_order; i++)
             if (f->order_host[(size_t)i] != (int)order[i]) { same = false; break; }
@@ -739,7 +752,7 @@ static int prepare_order(ytb200_frame *f, const ytb200_brickset *set, const int6
         if (order[i] < 0 || order[i] >= set->n) return fail(E_ARG, "order[%lld]=%lld out of range", (long long)i, (long long)order[i]);
         f->order_host[(size_t)i] = (int)order[i];
     }
-    f->order_set = nullptr;
+    f->order_generation = 0;
     if (n_order > f->order_cap) {
         CK(cudaStreamSynchronize(f->ctx->stream));
         cudaFree(f->order_dev); cudaFree(f->extent_dev);
@@ -754,7 +767,7 @@ static int prepare_order(ytb200_frame *f, const ytb200_brickset *set, const int6
         CK(cudaGetLastError());
         if (launches) (*launches)++;
     }
-    f->order_set = set;
+    f->order_generation = set->generation;
     return 0;
 }
 
@@ -1293,6 +1306,8 @@ extern "C" int ytb200_swap_error(ytb200_swap *s, int *error_out)
     DeviceGuard g(s->ctx->device);
     CK(cudaStreamSynchronize(s->ctx->stream));
     CK(cudaMemcpy(error_out, swap_flag(s->slab, 56), sizeof(int), cudaMemcpyDeviceToHost));
+    // reported once: a later frame that completes must not inherit this frame's failure
+    if (*error_out) CK(cudaMemset(swap_flag(s->slab, 56), 0, sizeof(unsigned long long)));
     return 0;
 }
 

@@ -21,22 +21,59 @@ class FieldInfo:
         return self.name[1]
 
 
-def vertex_centre_no_ghost(cells):
-    """ghost_zone_interpolate(rf=1, input_left=0.5, output_left=0) of interpolators.pyx:177-227:
-    trilinear interpolation of cell centres onto vertices, linearly extrapolated at the faces."""
-    out = np.asarray(cells, dtype="float64")
-    for ax in range(3):
-        n = out.shape[ax]
-        r = np.arange(n + 1, dtype="float64") - 0.5
-        i = np.clip(np.trunc(r).astype("int64"), 0, max(n - 2, 0))
-        xp = r - i
-        lo = np.take(out, i, axis=ax)
-        hi = np.take(out, np.minimum(i + 1, n - 1), axis=ax)
-        shape = [1, 1, 1]
-        shape[ax] = n + 1
-        xp = xp.reshape(shape)
-        out = lo * (1.0 - xp) + hi * xp
+def ghost_zone_interpolate(rf, input_field, input_left, out_shape, output_left):
+    """interpolators.pyx:177-227 on the host, term for term: every output point takes the 8-term weighted sum of the
+    input cells (ii, ij, ik)..(ii+1, ij+1, ik+1), ii = clip(int(pos), 0, n - 2), in the reference's term order and
+    with its weight products ((xm*ym)*zm ...), so the result is bit-identical to the Cython loop and to the device
+    kernel (``vertex_centre_kernel``).  Output positions accumulate ``opos += ods`` exactly as the reference does."""
+    f = np.ascontiguousarray(input_field, dtype="float64")
+    input_left = np.asarray(input_left, dtype="float64")
+    output_left = np.asarray(output_left, dtype="float64")
+    idx, wp = [], []
+    for a in range(3):
+        n_in, n_out = f.shape[a], int(out_shape[a])
+        if n_in < 2:
+            raise NotImplementedError("vertex centring needs >= 2 cells per axis (the reference divides by shape - 1)")
+        temp = input_left[a] + (rf * (n_in - 1))
+        ids = (temp - input_left[a]) / (n_in - 1)
+        iids = 1.0 / ids
+        if n_out > 1:
+            temp = output_left[a] + n_out - 1
+            ods = (temp - output_left[a]) / (n_out - 1)
+        else:
+            ods = 0.0
+        opos = np.empty(n_out, dtype="float64")
+        acc = np.float64(output_left[a])
+        for o in range(n_out):        # sequential accumulation, like the reference's `opos += ods`
+            opos[o] = acc
+            acc = acc + ods
+        ropos = (opos - input_left[a]) * iids
+        ii = np.clip(np.trunc(ropos).astype("int64"), 0, n_in - 2)   # C <int> truncates toward zero
+        idx.append(ii)
+        wp.append(ropos - ii)
+    (ii, ij, ik), (xp, yp, zp) = idx, wp
+    xm, ym, zm = 1.0 - xp, 1.0 - yp, 1.0 - zp
+    X = lambda v: v[:, None, None]   # noqa: E731
+    Y = lambda v: v[None, :, None]   # noqa: E731
+    Z = lambda v: v[None, None, :]   # noqa: E731
+    g = lambda a, b, c: f[np.ix_(ii + a, ij + b, ik + c)]   # noqa: E731
+    out = g(0, 0, 0) * ((X(xm) * Y(ym)) * Z(zm))
+    out = out + g(1, 0, 0) * ((X(xp) * Y(ym)) * Z(zm))
+    out = out + g(0, 1, 0) * ((X(xm) * Y(yp)) * Z(zm))
+    out = out + g(0, 0, 1) * ((X(xm) * Y(ym)) * Z(zp))
+    out = out + g(1, 0, 1) * ((X(xp) * Y(ym)) * Z(zp))
+    out = out + g(0, 1, 1) * ((X(xm) * Y(yp)) * Z(zp))
+    out = out + g(1, 1, 0) * ((X(xp) * Y(yp)) * Z(zm))
+    out = out + g(1, 1, 1) * ((X(xp) * Y(yp)) * Z(zp))
     return np.ascontiguousarray(out)
+
+
+def vertex_centre_no_ghost(cells):
+    """grid_patch.py:284-296: ghost_zone_interpolate(1, cells, [0.5]*3, out, [0]*3) -- trilinear interpolation of
+    the cell centres onto the vertices, linearly extrapolated at the faces.  Needs >= 2 cells per axis (a one-cell
+    axis is 0/0 in the reference), like the device path."""
+    c = np.asarray(cells, dtype="float64")
+    return ghost_zone_interpolate(1, c, [0.5] * 3, [n + 1 for n in c.shape], [0.0] * 3)
 
 
 class Grid:
@@ -223,23 +260,82 @@ class StreamDataset:
         return self.basename
 
 
-def _split_counts(shape, nprocs):
-    """Processor grid for ``nprocs`` pieces: repeatedly halve (or divide by the smallest prime factor) the
-    axis with the most cells per piece.  (The reference balances surface/volume in decompose.py:get_psize;
-    any cell-aligned split yields the same image -- SURVEY.md finding 6.)"""
-    psize = [1, 1, 1]
-    n = int(nprocs)
-    f = 2
-    factors = []
+def _prime_powers(n):
+    """[(prime, power)] of n, primes ascending."""
+    out, p = [], 2
     while n > 1:
-        while n % f == 0:
-            factors.append(f)
-            n //= f
-        f += 1
-    for f in sorted(factors, reverse=True):
-        ax = int(np.argmax([shape[a] / psize[a] for a in range(3)]))
-        psize[ax] *= f
-    return psize
+        m = 0
+        while n % p == 0:
+            n //= p
+            m += 1
+        if m:
+            out.append((p, m))
+        p += 1 if p == 2 else 2
+    return out
+
+
+def _decomposition_quality(n_d, pieces, ldom):
+    """Score of the processor grid `ldom` for an array of shape `n_d` (decompose.py:27-50: load balance over a
+    surface penalty, with the reference's constants; 0 when an axis would get more pieces than cells)."""
+    eff = int((n_d > 1).sum())
+    ideal = eff * pieces ** (1.0 / eff) * np.prod(n_d) ** (float(eff - 1) / float(eff))
+    m = np.where(n_d > 1)
+    nd = np.array(n_d, dtype=np.float64)[m]
+    bsize = int(np.sum(ldom[m] / nd * np.prod(nd)))
+    balance = float(np.prod(n_d)) / (float(pieces) * np.prod((n_d - 1) // ldom + 1))
+    q = balance / (1 + 0.25 * (bsize / ideal - 1.0))
+    q *= 1.0 - (0.001 * ldom[0] + 0.0001 * ldom[1]) / pieces
+    return 0 if np.any(ldom > n_d) else q
+
+
+def get_psize(n_d, pieces):
+    """Processor grid (px, py, pz) with px*py*pz == pieces that the reference picks for an array of shape `n_d`
+    (decompose.py:69-105).  Every way of dealing each prime power p^m over the three axes is scored and the FIRST
+    best one wins, so the candidates must come in the reference's order: per prime the exponent triples
+    (m - t, t - k, k) for t = m..0, k = t..0, the smallest prime's triple changing fastest.  The cut positions
+    decide the no-ghost vertex values on internal grid faces, hence the image (each grid extrapolates at its own
+    faces), so this has to be the reference's choice, not just any cell-aligned one."""
+    n_d = np.asarray(n_d, dtype=np.int64)
+    pieces = int(pieces)
+    if pieces == 1:
+        return np.ones(3, dtype=np.int64)
+    per_prime = []
+    for p, m in _prime_powers(pieces):
+        per_prime.append([(p, (m - t, t - k, k)) for t in range(m, -1, -1) for k in range(t, -1, -1)])
+    best, psize = 0.0, np.ones(3, dtype=np.int64)
+    pos = [0] * len(per_prime)
+    while True:
+        ldom = np.ones(3, dtype=np.int64)
+        for lst, i in zip(per_prime, pos):
+            p, e = lst[i]
+            ldom *= p ** np.array(e)
+        q = _decomposition_quality(n_d, pieces, ldom)
+        if q > best:
+            best, psize = q, ldom
+        # odometer, first prime fastest; the reference stops when the LAST prime runs out of triples
+        j = 0
+        while j < len(pos):
+            if pos[j] + 1 < len(per_prime[j]):
+                pos[j] += 1
+                break
+            pos[j] = 0
+            j += 1
+        if j == len(pos):
+            return psize
+
+
+def piece_edges(n_d, psize):
+    """Cell ranges [(lo, hi)] of the px*py*pz pieces in the reference's order (decompose.py:108-148, x slowest):
+    lo = n * i // p, hi = n * (i + 1) // p."""
+    n_d = np.asarray(n_d, dtype=np.int64)
+    psize = np.asarray(psize, dtype=np.int64)
+    out = []
+    for i in range(int(psize[0])):
+        for j in range(int(psize[1])):
+            for k in range(int(psize[2])):
+                pc = np.array((i, j, k), dtype=np.int64)
+                out.append((n_d * pc // psize, n_d * (pc + 1) // psize))
+    return out
 
 
 def load_uniform_grid(data, domain_dimensions, length_unit=None, bbox=None, nprocs=1, sim_time=0.0,
@@ -261,17 +357,13 @@ def load_uniform_grid(data, domain_dimensions, length_unit=None, bbox=None, npro
     if nprocs == 1:
         specs.append({"level": 0, "left_edge": le, "right_edge": re, "dimensions": dims, "fields": fields})
     else:
-        psize = _split_counts(dims, nprocs)
-        edges = [np.linspace(0, dims[a], psize[a] + 1).astype("int64") for a in range(3)]
+        # loaders.py:355-372: the processor grid comes from the FIRST field's array shape
+        psize = get_psize(dims, nprocs)
         dds = (re - le) / dims
-        for i in range(psize[0]):
-            for j in range(psize[1]):
-                for k in range(psize[2]):
-                    lo = np.array([edges[0][i], edges[1][j], edges[2][k]])
-                    hi = np.array([edges[0][i + 1], edges[1][j + 1], edges[2][k + 1]])
-                    sub = {f: v[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] for f, v in fields.items()}
-                    specs.append({"level": 0, "left_edge": le + lo * dds, "right_edge": le + hi * dds,
-                                  "dimensions": hi - lo, "fields": sub})
+        for lo, hi in piece_edges(dims, psize):
+            sub = {f: v[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] for f, v in fields.items()}
+            specs.append({"level": 0, "left_edge": le + lo * dds, "right_edge": le + hi * dds,
+                          "dimensions": hi - lo, "fields": sub})
     return StreamDataset(specs, dims, bbox, periodicity=periodicity, name="UniformGridData")
 
 

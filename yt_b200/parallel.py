@@ -287,3 +287,42 @@ class PeerSwap:
         L.check(L.load().ytb200_swap_error(self.handle, C.byref(e)))
         if e.value:
             raise RuntimeError("binary swap: a peer did not signal within 10 s")
+
+
+def make_compositor(ctx, frame, path, viewpoint, rank, world, f32=True, group=None, prefer=None):
+    """The compositor every rank of the job agrees on: :class:`PeerSwap` when ALL ranks can map each other's slabs
+    (one host, at most 8 GPUs, peer access between the devices, CUDA IPC working), :class:`BinarySwap` over NCCL
+    send/recv otherwise -- for more than 8 ranks, several nodes, or devices without peer access.  ``prefer``
+    ("peer" / "nccl"; default: ``YTB200_SWAP`` or "peer") only expresses a wish: a rank that cannot open a peer makes
+    the whole job fall back, it never raises.  Collective: every rank must call it.  Returns (swap, is_peer)."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    prefer = prefer or os.environ.get("YTB200_SWAP", "peer")
+    swap, ok = None, 0
+    if world > 1 and prefer != "nccl" and world <= 8:
+        hosts = [None] * world
+        dist.all_gather_object(hosts, (socket.gethostname(), int(ctx.device)), group=group)
+        same_host = len({h for h, _ in hosts}) == 1
+        can = same_host
+        if same_host:
+            for _, d in hosts:
+                if d != ctx.device and not torch.cuda.can_device_access_peer(ctx.device, d):
+                    can = False
+        # the IPC exchange inside PeerSwap is itself collective: enter it only if every rank will
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(can), group=group)
+        if all(flags):
+            try:
+                swap = PeerSwap(ctx, frame, path, viewpoint, rank, world, f32=f32, group=group)
+                ok = 1
+            except Exception as exc:  # noqa: BLE001  (cudaIpcOpenMemHandle refused, out of memory, ...)
+                import sys
+                sys.stderr.write("rank %d: peer-memory swap unavailable (%s); falling back to the NCCL compositor\n" % (rank, exc))
+                swap, ok = None, 0
+            flags = [None] * world
+            dist.all_gather_object(flags, bool(ok), group=group)
+            ok = int(all(flags))
+    if world > 1 and not ok:
+        swap = BinarySwap(ctx, frame.nx, frame.ny, path, viewpoint, rank, world, group=group)
+    return swap, bool(ok)

@@ -110,3 +110,34 @@ def nested_amr_grids(base_cells=32, tile=8, levels=4, seed=0, refine_by=2, field
         q = (hi - lo) / 4.0
         lo, hi = lo + q, hi - q
     return out, [base_cells] * 3
+
+
+class BoxDomain:
+    """The few dataset attributes a Camera reads (camera.py:127-137), for a bare box with no fields."""
+
+    def __init__(self, le=(0, 0, 0), re=(1, 1, 1)):
+        self.domain_left_edge = np.array(le, dtype="float64")
+        self.domain_right_edge = np.array(re, dtype="float64")
+        self.domain_width = self.domain_right_edge - self.domain_left_edge
+        self.domain_center = 0.5 * (self.domain_left_edge + self.domain_right_edge)
+        self.ds = self
+
+    def all_data(self):
+        return self
+
+
+def make_camera(lens_type="plane-parallel", resolution=(64, 64), position=None, focus=None, width=None, north=None, ds=None):
+    """A Camera over `ds` (default: the unit box) with the reference's defaults -- the corner view of
+    ``yt.create_scene`` -- unless position / focus / width / north are given."""
+    from .volume_rendering.camera import Camera
+    cam = Camera(None, ds or BoxDomain(), lens_type=lens_type)
+    cam.resolution = resolution
+    if north is not None:
+        cam.north_vector = np.array(north, dtype="float64")
+    if position is not None:
+        cam.position = position
+    if focus is not None:
+        cam.focus = focus
+    if width is not None:
+        cam.width = width
+    return cam

@@ -12,6 +12,7 @@ import os
 
 import numpy as np
 
+from .. import _lib as _L
 from ..amr_kdtree import AMRKDTree
 from ..loaders import OctreeIndex
 from ..octree_raytracing import OctreeRayTracing
@@ -268,18 +269,21 @@ class KDTreeVolumeSource(VolumeSource):
             if len(self.volume.tree.traverse()) > 0:
                 bricks = self.volume.device_bricks(self.sampler._ctx, self.sampler._storage)
                 self.sampler.cast_bricks(bricks, self.volume.view_order(camera.lens.viewpoint, camera))
-            if os.environ.get("YTB200_SWAP", "peer") == "nccl":
+            # one compositor per (image size, partial type): a PeerSwap's IPC-shared slab outlives the per-render
+            # samplers.  make_compositor falls back to the NCCL route for > 8 ranks, several hosts or no peer access.
+            from ..parallel import PeerSwap, make_compositor
+            key = (nx, ny, self.sampler.kind, self.sampler._precision, self.volume.comm_size)
+            cache = self.__dict__.setdefault("_swaps", {})
+            if key not in cache:
+                f32 = self.sampler.kind == _L.VOLUME_RENDER and self.sampler._precision == _L.PREC_FAST
+                cache[key] = make_compositor(self.sampler._ctx, self.sampler._frame, self.volume.kd_path(), camera.lens.viewpoint,
+                                             self.volume.comm_rank, self.volume.comm_size, f32=f32)[0]
+            swap = cache[key]
+            if isinstance(swap, PeerSwap):
+                swap.set_view(self.volume.kd_path(), camera.lens.viewpoint)
+            else:
                 swap = BinarySwap(self.sampler._ctx, nx, ny, self.volume.kd_path(), camera.lens.viewpoint,
                                   self.volume.comm_rank, self.volume.comm_size)
-            else:
-                # one compositor per (image size, partial type): its IPC-shared slab outlives the per-render samplers
-                key = (nx, ny, self.sampler.kind, self.sampler._precision, self.volume.comm_size)
-                cache = self.__dict__.setdefault("_peer_swaps", {})
-                if key not in cache:
-                    cache[key] = self.sampler.peer_swap(self.volume.kd_path(), camera.lens.viewpoint,
-                                                        self.volume.comm_rank, self.volume.comm_size)
-                swap = cache[key]
-                swap.set_view(self.volume.kd_path(), camera.lens.viewpoint)
             self.sampler.flush_parallel(swap, broadcast=True)
         elif self.batched:
             bricks = self.volume.device_bricks(self.sampler._ctx, self.sampler._storage)

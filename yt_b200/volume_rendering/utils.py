@@ -69,6 +69,24 @@ def new_projection_sampler(camera, render_source):
     return ProjectionSampler(*args, lens_type=params["lens_type"], zbuffer=_zbuffer_kwarg(params, render_source))
 
 
+def sampler_arguments(camera, zbuffer=None, image=None, volume_method="KDTree"):
+    """(args, kwargs) of ``ImageSampler.__init__`` for `camera` exactly as the factories above assemble them
+    (utils.py:55-139), without a render source: ``args`` stops at ``volume_method`` (append the transfer function /
+    ``num_samples`` the sampler class takes), ``kwargs`` holds ``lens_type``, ``camera_data`` (only
+    ``new_volume_render_sampler`` forwards it -- pop it for the projection samplers) and ``zbuffer``.
+    Used by the benchmark and the parity tests to drive the CUDA samplers and the CPU implementations they are checked against
+    with one argument tuple."""
+    import types
+    p = ensure_code_unit_params(camera._get_sampler_params(types.SimpleNamespace(zbuffer=None)))
+    nx, ny = camera.resolution
+    img = np.zeros((nx, ny, 4), dtype="float64") if image is None else image
+    p["image"] = img
+    args = _common_args(p, types.SimpleNamespace(volume_method=volume_method))
+    kwargs = {"lens_type": p["lens_type"], "camera_data": np.array(p["camera_data"], dtype="float64"),
+              "zbuffer": np.ones((nx, ny), "float64") if zbuffer is None else zbuffer}
+    return args, kwargs
+
+
 def get_corners(le, re):
     return np.array([[le[0], le[1], le[2]], [re[0], le[1], le[2]], [re[0], re[1], le[2]], [le[0], re[1], le[2]],
                      [le[0], le[1], re[2]], [re[0], le[1], re[2]], [re[0], re[1], re[2]], [le[0], re[1], re[2]]], dtype="float64")
