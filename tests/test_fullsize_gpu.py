@@ -52,6 +52,7 @@ def test_cfg3_constant_field_projects_to_the_chord_length(gpu):
     bs = D.BrickSet(s._ctx, 1, 1, L.CELL_CENTRED, L.STORE_F32)
     bs.attach(0, [buf.data_ptr()], 0, [0.0] * 3, [1.0] * 3, [N] * 3, keep=buf, row_pitch=pitch)
     bs.commit()
+    torch.cuda.synchronize()     # the volume was generated on torch's stream, the cast runs on the context's
     s.cast_bricks(bs, np.arange(1, dtype=np.int64))
     got = np.array(s.aimage)[:, :, 0]
     # closed form: slab intersection of p + t d with the unit cube, clipped to t in [0, 1]
@@ -94,6 +95,7 @@ def test_north_star_sub_bricks_reproduce_the_single_brick_frame(gpu):
         for b, (v, g) in enumerate(zip(vols, geoms)):
             bs.attach(b, [v.data_ptr()], 0, g[0], g[1], g[2], keep=v)
         bs.commit()
+        torch.cuda.synchronize()
         order = np.ascontiguousarray(T.view_order([(g[0], g[1]) for g in geoms], cam.lens.viewpoint), dtype=np.int64)
         counts.append(s.count_samples(bs, order))
         s.cast_bricks(bs, order)

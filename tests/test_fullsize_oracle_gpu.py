@@ -28,6 +28,20 @@ def _need_memory(gb):
         pytest.skip("needs %d GB of free HBM" % gb)
 
 
+def _lattice(R, n=64):
+    """n pixel indices spread over [0, R): one per R/n block, at a position inside the block that walks through every
+    residue modulo 16 and 32 (a regular stride would only ever test lane 0 of every CTA tile)."""
+    step = R // n
+    k = np.arange(n)
+    return k * step + (k * 5 + 3) % step
+
+
+def _torch_done():
+    """torch generated the volume on ITS stream; the samplers launch on the context's own non-blocking stream."""
+    import torch
+    torch.cuda.synchronize()
+
+
 def _reference():
     from oracle import oracle as O
     if O.ref_available():
@@ -101,9 +115,10 @@ def test_north_star_frame_matches_the_reference_on_a_ray_lattice(gpu):
     bs = D.BrickSet(s._ctx, 1, 1, L.VERTEX_CENTRED, L.STORE_F32)
     bs.attach(0, [vol.data_ptr()], 0, [0.0] * 3, [1.0] * 3, [N] * 3, keep=vol)
     bs.commit()
+    _torch_done()
     s.cast_bricks(bs, np.arange(1, dtype=np.int64))
     got = np.array(s.aimage)
-    ii = jj = np.arange(16, R, 32)
+    ii, jj = _lattice(R), _lattice(R)[::-1].copy()
     want, label = reference_on_lattice("vr", cam, args, ii, jj, N, lambda x0, x1: vol[x0:x1 + 1].cpu().numpy().astype("float64"), 1,
                                        tf=tf, n_samples=N_SAMPLES)
     sub = got[np.ix_(ii, jj)]
@@ -133,9 +148,10 @@ def test_cfg3_random_field_projection_matches_the_reference_on_a_ray_lattice(gpu
     bs = D.BrickSet(s._ctx, 1, 1, L.CELL_CENTRED, L.STORE_F32)
     bs.attach(0, [vol.data_ptr()], 0, [0.0] * 3, [1.0] * 3, [N] * 3, keep=vol, row_pitch=pitch)
     bs.commit()
+    _torch_done()
     s.cast_bricks(bs, np.arange(1, dtype=np.int64))
     got = np.array(s.aimage)
-    ii = jj = np.arange(16, R, 32)
+    ii, jj = _lattice(R), _lattice(R)[::-1].copy()
     want, label = reference_on_lattice("proj", cam, args, ii, jj, N, lambda x0, x1: vol[x0:x1].cpu().numpy().astype("float64"), 0)
     sub = got[np.ix_(ii, jj)]
     assert want[:, :, 0].max() > 0.5 and (want[:, :, 0] > 0).mean() > 0.3
@@ -167,6 +183,7 @@ def test_cfg2_full_frame_matches_the_reference(gpu):
     bs = D.BrickSet(s._ctx, 1, 1, L.VERTEX_CENTRED, L.STORE_F32)
     bs.attach(0, [vol.data_ptr()], 0, [0.0] * 3, [1.0] * 3, [N] * 3, keep=vol)
     bs.commit()
+    _torch_done()
     s.cast_bricks(bs, np.arange(1, dtype=np.int64))
     got = np.array(s.aimage)
     Sr, Gr, label = _reference()

@@ -10,12 +10,6 @@
 
 namespace ytb {
 
-#ifndef YTB_CTA_THREADS
-#define YTB_CTA_THREADS 256
-#endif
-// a CTA's warps are 4 x 8 pixel patches laid two abreast (see cast_kernel): 16 columns, CTA_THREADS / 16 rows
-constexpr int CTA_THREADS = YTB_CTA_THREADS, TILE_I = CTA_THREADS / 16, TILE_J = 16;
-static_assert(CTA_THREADS % 64 == 0, "warps pair up across the tile");
 #ifndef YTB_MIN_BLOCKS
 #define YTB_MIN_BLOCKS 2
 #endif
@@ -754,24 +748,6 @@ struct FastSampler {
         }
     }
 };
-
-// lenses.pyx:179-192 (plane-parallel, same operation order) / 196-207 (per-pixel arrays)
-__device__ __forceinline__ void make_ray(const DevCamera &cam, int vi, int vj, double (&vp)[3], double (&vd)[3])
-{
-    if (cam.lens == 0) {
-        const double px = dsub(ddiv(dmul(cam.width[0], (double)vi), dsub((double)cam.nx, 1.0)), ddiv(cam.width[0], 2.0));
-        const double py = dsub(ddiv(dmul(cam.width[1], (double)vj), dsub((double)cam.ny, 1.0)), ddiv(cam.width[1], 2.0));
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            vp[i] = dadd(dadd(dmul(cam.vp_pos[i], px), dmul(cam.vp_pos[3 + i], py)), cam.vp_pos[9 + i]);
-            vd[i] = cam.vp_dir[i];
-        }
-    } else {
-        const size_t o = ((size_t)vi * cam.ny + vj) * 3;
-#pragma unroll
-        for (int i = 0; i < 3; i++) { vp[i] = cam.pos_px[o + i]; vd[i] = cam.dir_px[o + i]; }
-    }
-}
 
 // walk_volume for the ColorTransferFunction fast path: reference entry logic, then the fused walk
 template <bool HAVE_IV = false, class S>

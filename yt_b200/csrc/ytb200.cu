@@ -16,6 +16,7 @@
 
 #include "cast_kernels.cuh"
 #include "octree_cast.cuh"
+#include "proj.h"
 
 using namespace ytb;
 
@@ -96,6 +97,7 @@ struct ytb200_frame {
     int4 *extent_dev = nullptr;
     int64_t order_cap = 0;
     std::vector<int> order_host;
+    bool image_is_host = false;      // f->image currently aliases a page-locked host array (ytb200_render, in place)
     uint64_t order_generation = 0;   // ytb200_brickset::generation the cached order / footprints belong to (0: none)
 };
 
@@ -872,6 +874,10 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
             } else e = launch_kind<KIND_VR, TFM_GENERAL>(p, grid, smem, st, exact, f64, partial != nullptr, nf1);
         } else if (kind == YTB200_INTERPOLATED_PROJECTION) {
             e = launch_kind<KIND_IPROJ, TFM_NONE>(p, grid, 0, st, exact, f64, partial != nullptr, nf1);
+        } else if (!exact && !f64 && !getenv("YTB200_PROJ_DDA")) {
+            // fp32 storage, FAST: the slab walk (proj_kernels.cuh); image_samplers.pyx:337-343 sums min(4, n_fields) fields
+            const ProjMap pm = make_proj_map(f->cam, n_order > 0 ? &set->host[(size_t)order[0]] : nullptr, f->image_is_host);
+            e = launch_proj(p, pm, std::min(4, set->n_fields), partial != nullptr, st);
         } else {
             e = launch_kind<KIND_PROJ, TFM_NONE>(p, grid, 0, st, exact, f64, partial != nullptr, nf1);
         }
@@ -1352,9 +1358,11 @@ extern "C" int ytb200_render(ytb200_frame *f, int kind, const ytb200_brickset *s
         double *keep_img = f->image, *keep_zb = f->zbuffer;
         f->image = img;
         f->zbuffer = zb;   // nullptr == ones
+        f->image_is_host = true;
         int rc = cast_common(f, kind, set, order, n_order, tf, n_samples, precision, nullptr, stats);
         f->image = keep_img;
         f->zbuffer = keep_zb;
+        f->image_is_host = false;
         if (rc) return rc;
         DeviceGuard g(f->ctx->device);
         CK(cudaStreamSynchronize(f->ctx->stream));
