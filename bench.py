@@ -406,14 +406,15 @@ def run_ours(args):
         swap = partial = None
         peer = False
         if world > 1:
-            from yt_b200.parallel import make_compositor
-            swap, peer = make_compositor(ctx, frame, path, cam.lens.viewpoint, rank, world, f32=(kind == "vr"))
+            from yt_b200.parallel import make_compositor, partial_format
+            fmt = partial_format(kcode, tf, bricks.n_fields)
+            swap, peer = make_compositor(ctx, frame, path, cam.lens.viewpoint, rank, world, fmt=fmt)
             if not peer:
                 partial = torch.empty((res, res, 8), dtype=torch.float64, device=dev)
 
         def cast_partial(timed=False):
             if peer:
-                return frame.cast_partial(kcode, bricks, order, swap.partial_ptr, tf=tf, n_samples=N_SAMPLES, timed=timed, f32=swap.f32)
+                return swap.cast(frame, kcode, bricks, order, tf=tf, n_samples=N_SAMPLES, timed=timed)
             return frame.cast_partial(kcode, bricks, order, partial.data_ptr(), tf=tf, n_samples=N_SAMPLES, timed=timed)
 
         def composite():
@@ -447,14 +448,12 @@ def run_ours(args):
             if world == 1:
                 frame.render(kcode, bricks, order, img_host, zbuffer=zb_host, tf=tf, n_samples=N_SAMPLES)
             elif peer:
-                # host arrays are read in place (z-buffer by the cast, the rank's strip of the initial colours by
-                # the swap's last kernel); the composited image lands in rank 0's frame and is copied out
+                # ONE page-locked image / z-buffer mapped into every rank's process: each rank reads max_t and its strip of
+                # the initial colours in place and its last swap kernel stores the finished strip back over its own PCIe
+                # link; rank 0's stream ends with a wait for every rank's strip
                 cast_partial()
-                composite()
-                if rank == 0:
-                    frame.download(e2e_out)
-                else:
-                    ctx.synchronize()
+                swap.composite_host(frame, img_shared)
+                ctx.synchronize()
             else:
                 frame.upload(img_host, zb_host)
                 cast_partial()
@@ -520,18 +519,32 @@ def run_ours(args):
                     del solo
                     torch.cuda.empty_cache()
                 dist.barrier()
-        e2e_out = None
+        img_shared = zb_shared = None
         if peer:
-            e2e_out = D.pinned_empty((res, res, 4))
-            frame.bind_host(img_host, zb_host)
+            from yt_b200.parallel import shared_pinned_empty
+            img_shared = shared_pinned_empty((res, res, 4), rank=rank, world=world, tag="img")
+            zb_shared = shared_pinned_empty((res, res), rank=rank, world=world, tag="zb")
+            if rank == 0:
+                img_shared[:] = 0.0
+                zb_shared[:] = 1.0
+            dist.barrier()
+            frame.bind_host(img_shared, zb_shared)
         for _ in range(2):
             frame_e2e()
         ms_e2e = timed(frame_e2e, args.steps) / args.steps
         if peer:
             swap.check()   # raises if a device-side wait of the swap timed out
+            # one more frame from zeroed initial colours: the host-route image must equal the device-route image
+            dist.barrier()
+            if rank == 0:
+                img_shared[:] = 0.0
+            dist.barrier()
+            frame_e2e()
+            swap.check()
+            dist.barrier()
             frame.bind_host(None)
-            if rank == 0 and not np.array_equal(e2e_out, dev_img):
-                raise SystemExit("e2e image differs from the device-route image")
+            if rank == 0 and not np.array_equal(img_shared, dev_img):
+                raise SystemExit("e2e image differs from the device-route image (max |diff| %g)" % np.abs(img_shared - dev_img).max())
 
     if rank != 0:
         if world > 1:
@@ -542,7 +555,7 @@ def run_ours(args):
     alg_bytes = my_elems * elem + 2.0 * res * res * 32 + res * res * 8 + (2.0 * res * res * 24 if amr else 0.0)
     gs = total_samples / (ms_step * 1e-3) / 1e9
     gs_e2e = total_samples / (ms_e2e * 1e-3) / 1e9
-    launches_per_step = 2 if world == 1 else 2 + swap.launches_per_composite
+    launches_per_step = 2 if world == 1 else 2 + swap.launches_per_composite   # clear + cast (+ rounds + apply)
     line = {
         "metric": "Gsamples/s", "value": gs, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -551,14 +564,14 @@ def run_ours(args):
                    "n_samples": 1 if kind == "proj" else N_SAMPLES, "lens": "perspective" if amr else "plane-parallel",
                    "view": "camera at (1.6,1.4,1.2) looking at the domain centre" if amr else "default corner camera, width 1.5",
                    "bricks_per_rank": n_bricks, "samples_per_frame": total_samples, "parallelism": "kd%d" % world,
-                   "composite": ("none" if world == 1 else ("binary swap over NVLink peer memory, fp32 (A,B)" if peer and kind == "vr" else
-                                 ("binary swap over NVLink peer memory, fp64 (A,B)" if peer else "binary swap, NCCL send/recv, fp64 (A,B)"))),
+                   "composite": ("none" if world == 1 else ("binary swap over NVLink peer memory, %d B per pixel (partial format %d)" % (swap.bytes_per_pixel, swap.fmt)
+                                 if peer else "binary swap, NCCL send/recv, fp64 (A,B)")),
                    "l2": "brick (%.2f GB per rank) larger than L2; no flush needed" % (my_elems * elem / 1e9)},
         "ms_per_frame": ms_step,
         "e2e": {"value": gs_e2e, "unit": "Gsamples/s", "ms_per_frame": ms_e2e,
                 "h2d_bytes_per_step": res * res * 40 if not peer else res * res * 8 * world + res * res * 32,
                 "d2h_bytes_per_step": res * res * 32,
-                "note": ("host (page-locked) image+zbuffer in, host image out through ytb200_render: the cast kernel reads/writes the host arrays in place over PCIe; bricks device-resident across frames" if world == 1 else "host (page-locked) image+zbuffer read in place by every rank (z-buffer by the cast, its strip of the initial colours by the swap), composited image copied out of rank 0's frame; checked equal to the device-route image")},
+                "note": ("host (page-locked) image+zbuffer in, host image out through ytb200_render: the cast kernel reads/writes the host arrays in place over PCIe; bricks device-resident across frames" if world == 1 else "one page-locked image + z-buffer mapped into every rank: each rank reads max_t and its strip of the initial colours in place and stores its finished strip over its own PCIe link (ytb200_swap_composite_host); checked equal to the device-route image")},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk,
         "roofline": roofline_block(args.workload, kind, world, my_samples, kernel_ms, alg_bytes, clk, ctx.sm_count),

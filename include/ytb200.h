@@ -186,32 +186,49 @@ int ytb200_frame_cast_partial_f32(ytb200_frame *f, int kind, const ytb200_bricks
 
 /* ---- binary swap over NVLink peer memory: AMRKDTree.reduce_tree_images (amr_kdtree.py:297-323) -------
  * One process per GPU.  Every rank creates a swap object (one cudaMalloc'd slab holding the partial-image buffers of
- * all rounds, the final image and the ordering flags), publishes its 64-byte CUDA IPC handle to the other ranks by
- * any host channel, and opens theirs.  A frame is then
- *   ytb200_frame_cast_partial[_f32](..., ytb200_swap_partial(swap), ...);  ytb200_swap_composite(swap, frame, broadcast);
- * Each swap round is ONE kernel that reads the partner's half straight out of its HBM through the peer mapping and
- * composes it with the local half (A = A2 + B2*A1, B = B2*B1); the final strips are applied to the
- * initial colours and stored directly into rank 0's (or, with `broadcast`, every rank's) slab, from where the
- * destination copies the finished image into the frame passed to ytb200_swap_composite.  No NCCL call,
- * no receive buffers; cross-GPU ordering is a sequence number per round pushed into the consumer's memory.
- * `bytes_per_pixel`: 32 (fp32 A,B -- cast with _f32) or 64 (fp64 A,B). */
+ * every round, a final region and the flag words), passes its CUDA IPC handle to the others ONCE, and then per frame
+ *   ytb200_swap_cast(swap, frame, ...);  ytb200_swap_composite(swap, frame, broadcast);
+ * The cast writes this rank's partial straight into the slab, in the smallest exact format of the affine map
+ * C -> A + B*C (ytb200_partial_format: 16 B per pixel for the ColorTransferFunction render, 8 B per summed field for
+ * the projections, the general (A,B) pair otherwise), and its last CTA tells the round-0 partner.  Each swap round is
+ * ONE kernel: it waits for the partner's flag, reads the partner's half straight out of its HBM through the peer
+ * mapping, composes and signals.  The last round stores every rank's composed strip into the destination ranks'
+ * slabs (rank 0, or every rank with `broadcast`), whose apply kernel writes A + B*C0 into the frame's image.  No
+ * NCCL call, no host round trip: a frame is log2(world) + 2 launches on a destination rank.
+ * ytb200_swap_composite_host instead lets every rank store the FINISHED pixels of its strip into one page-locked
+ * image mapped into every rank's process (ytb200_host_register of the same shared memory): the image leaves the box
+ * over all PCIe links at once.  Peers must be on one host, with peer access (<= 8 ranks, power of two);
+ * yt_b200.parallel.make_compositor falls back to NCCL send/recv (BinarySwap) otherwise.
+ * Host inputs: ytb200_frame_bind_host lets the partial casts read max_t, and the composite read its strip of the
+ * initial colours, in place from page-locked arrays. */
 /* Multi-GPU frames with host inputs: bind the caller's PAGE-LOCKED image (initial colours) and z-buffer (NULL = ones)
- * as inputs of the frame; the partial casts then read max_t, and ytb200_swap_composite the initial colours of the
- * rank's final strip, in place over PCIe instead of from uploaded copies (a rank reads 1/P of the image instead of
- * uploading all of it).  image_host = NULL unbinds.  The result still lands in the destination frames' device images. */
+ * as inputs of the frame; the partial casts then read max_t, and the composite the initial colours of the rank's final
+ * strip, in place over PCIe instead of from uploaded copies (a rank reads 1/P of the image instead of uploading all of
+ * it).  image_host = NULL unbinds. */
 int ytb200_frame_bind_host(ytb200_frame *f, const double *image_host, const double *zbuffer_host);
 typedef struct ytb200_swap ytb200_swap;
-int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, int world, int bytes_per_pixel, ytb200_swap **out);
+#define YTB200_PARTIAL_AB64 0   /* fp64 (A[4], B[4]): 64 B per pixel -- EXACT precision */
+#define YTB200_PARTIAL_AB32 1   /* fp32 (A[4], B[4]): 32 B -- FAST volume render, any transfer function */
+#define YTB200_PARTIAL_A32 2    /* fp32 A[4], B = 1 - A or 0 where flagged: 16 B -- FAST ColorTransferFunction render */
+#define YTB200_PARTIAL_A32G 3   /* the same with grey opacity (flag in the sign of alpha) */
+#define YTB200_PARTIAL_SUM1 4   /* fp64 sums, B == 1: 8 / 16 / 32 B -- the projection samplers */
+#define YTB200_PARTIAL_SUM2 5
+#define YTB200_PARTIAL_SUM4 6
+int ytb200_partial_format(int kind, const ytb200_tf *tf, int n_fields, int precision);   /* < 0: error */
+int ytb200_partial_bytes(int format);
+int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, int world, int format, ytb200_swap **out);
 int ytb200_swap_destroy(ytb200_swap *swap);
+int ytb200_swap_format(const ytb200_swap *swap);
 int ytb200_swap_handle(ytb200_swap *swap, void *handle64_out);
 int ytb200_swap_open(ytb200_swap *swap, int peer_rank, const void *slab_handle64);
 /* The schedule of this rank (yt_b200.parallel.plan_binary_swap): per round the partner, the pixel region [p0,p1) both
- * partners hold, the half [k0,k1) this rank keeps, and whether this rank's content is applied first (the far side
- * of the kd split seen from the viewpoint, amr_kdtools.pyx:708-755). */
+ * hold, the part [k0,k1) this rank keeps, and whether this rank's content is composited first. */
 int ytb200_swap_plan(ytb200_swap *swap, int n_rounds, const int32_t *partner, const int64_t *p0, const int64_t *p1,
                      const int64_t *k0, const int64_t *k1, const int32_t *mine_is_earlier);
-void *ytb200_swap_partial(ytb200_swap *swap);   /* where the NEXT frame's partial cast must write */
+int ytb200_swap_cast(ytb200_swap *swap, ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
+                     int64_t n_order, const ytb200_tf *tf, int n_samples, int precision, ytb200_stats *stats);
 int ytb200_swap_composite(ytb200_swap *swap, ytb200_frame *f, int broadcast);
+int ytb200_swap_composite_host(ytb200_swap *swap, ytb200_frame *f, double *image_host_inout);
 int ytb200_swap_error(ytb200_swap *swap, int *error_out);   /* synchronises; 1 = a peer did not arrive within 10 s */
 
 /* ---- opaque sources: zlines / zpoints (yt/utilities/lib/misc_utilities.pyx:244-404) -------------------
@@ -284,6 +301,11 @@ int64_t ytb200_kdtree_traverse(const ytb200_kdtree *t, const double *viewpoint, 
 /* Pinned host memory for the image / z-buffer (cudaHostAlloc). */
 int ytb200_host_alloc(int64_t bytes, void **out);
 int ytb200_host_free(void *p);
+/* Page-lock and map memory the caller owns (e.g. POSIX shared memory every rank of a multi-GPU render has mapped):
+ * afterwards it is accepted wherever a page-locked array is (ytb200_render, ytb200_frame_bind_host,
+ * ytb200_swap_composite_host). */
+int ytb200_host_register(void *p, int64_t bytes);
+int ytb200_host_unregister(void *p);
 
 #ifdef __cplusplus
 }

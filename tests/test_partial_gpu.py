@@ -85,19 +85,46 @@ def test_two_partials_composed_equal_the_plain_cast(sc, gpu):
 
 
 @pytest.mark.parametrize("sc", _cases(), ids=lambda s: s.name)
-def test_fp32_partial_through_the_swap_object(sc, gpu):
-    """world = 1: no rounds, the swap's last kernel applies the fp32 (A,B) map to the initial colours."""
-    from yt_b200.parallel import PeerSwap
-    if sc.kind != "vr":
-        pytest.skip("fp32 partials are used for the volume render only")
+@pytest.mark.parametrize("compact", [True, False])
+def test_partial_through_the_swap_object(sc, compact, gpu):
+    """world = 1: no rounds, the swap's apply kernel decodes the partial (compact: 16 B per pixel for the colour render,
+    8 B per summed field for the projection; else the general fp32 / fp64 (A, B) pair) and applies it to the initial
+    colours -- including pixels whose opacity clamps fired (their flag must survive the encoding)."""
+    from yt_b200 import _lib as L
+    from yt_b200.parallel import PeerSwap, partial_format
     want = T.run_scenario(sc, O, O, num_threads=0)
     s, bs, img = _setup(sc)
     fr = s._frame
-    swap = PeerSwap(s._ctx, fr, [], sc.cam.lens.viewpoint, 0, 1, f32=True)
+    fmt = partial_format(s.kind, s._tables, bs.n_fields)
+    if sc.kind == "vr":
+        assert fmt == (L.PARTIAL_A32G if sc.grey else L.PARTIAL_A32)
+    else:
+        assert fmt == L.PARTIAL_SUM2
+    if not compact:
+        fmt = L.PARTIAL_AB32 if sc.kind == "vr" else L.PARTIAL_SUM4
+    swap = PeerSwap(s._ctx, fr, [], sc.cam.lens.viewpoint, 0, 1, fmt=fmt)
     for _ in range(3):   # three frames: both buffer parities are used
         fr.upload(img, s.azbuffer)
-        fr.cast_partial(s.kind, bs, np.array(sc.order, dtype=np.int64), swap.partial_ptr, tf=s._tables, n_samples=s.n_samples, f32=True)
+        swap.cast(fr, s.kind, bs, np.array(sc.order, dtype=np.int64), tf=s._tables, n_samples=s.n_samples)
         swap.composite(fr)
         swap.check()
         got = fr.download(np.empty_like(img))
         _check(sc, got, want)
+
+
+def test_swap_composite_into_a_page_locked_host_image(gpu):
+    """composite_host: the finished pixels go straight into a registered host array holding the initial colours."""
+    from yt_b200.parallel import PeerSwap, partial_format, shared_pinned_empty
+    sc = _cases()[2]
+    want = T.run_scenario(sc, O, O, num_threads=0)
+    s, bs, img = _setup(sc)
+    fr = s._frame
+    host = shared_pinned_empty(img.shape)
+    swap = PeerSwap(s._ctx, fr, [], sc.cam.lens.viewpoint, 0, 1, fmt=partial_format(s.kind, s._tables, bs.n_fields))
+    for _ in range(2):
+        host[:] = img
+        fr.upload(img, s.azbuffer)
+        swap.cast(fr, s.kind, bs, np.array(sc.order, dtype=np.int64), tf=s._tables, n_samples=s.n_samples)
+        swap.composite_host(fr, host)
+        swap.check()
+        _check(sc, np.array(host), want)

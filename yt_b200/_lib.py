@@ -15,6 +15,8 @@ LENS_PLANE_PARALLEL, LENS_PERSPECTIVE, LENS_GENERIC = 0, 1, 2
 CELL_CENTRED, VERTEX_CENTRED = 0, 1
 STORE_F32, STORE_F64 = 0, 1
 PREC_FAST, PREC_EXACT = 0, 1
+# partial-image formats (include/ytb200.h: YTB200_PARTIAL_*)
+PARTIAL_AB64, PARTIAL_AB32, PARTIAL_A32, PARTIAL_A32G, PARTIAL_SUM1, PARTIAL_SUM2, PARTIAL_SUM4 = range(7)
 
 dp = C.POINTER(C.c_double)
 i64p = C.POINTER(C.c_int64)
@@ -88,8 +90,15 @@ SIGNATURES = {
     "ytb200_swap_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ytb200_swap_open": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "ytb200_swap_plan": (C.c_int, [C.c_void_p, C.c_int, i32p, i64p, i64p, i64p, i64p, i32p]),
-    "ytb200_swap_partial": (C.c_void_p, [C.c_void_p]),
+    "ytb200_swap_format": (C.c_int, [C.c_void_p]),
+    "ytb200_partial_format": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int]),
+    "ytb200_partial_bytes": (C.c_int, [C.c_int]),
+    "ytb200_swap_cast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, i64p, C.c_int64, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_void_p]),
     "ytb200_swap_composite": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "ytb200_swap_composite_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ytb200_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
+    "ytb200_host_unregister": (C.c_int, [C.c_void_p]),
     "ytb200_swap_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "ytb200_partial_compose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "ytb200_partial_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),

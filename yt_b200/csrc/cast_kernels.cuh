@@ -962,7 +962,7 @@ cast_kernel(const __grid_constant__ CastParams p)
     }
 
     // ---- write back ---------------------------------------------------------------------------------
-    if (!active) return;
+    if (active) {
     double out[4], Bout[4];
     if constexpr (EXACT) {
 #pragma unroll
@@ -1000,17 +1000,15 @@ cast_kernel(const __grid_constant__ CastParams p)
     }
     if (PARTIAL) {
         if (KIND == KIND_VR && !p.tf.grey) { out[3] = 0.0; Bout[3] = 1.0; }
-        if (p.partial_f32) {
-            float4 *dst = reinterpret_cast<float4 *>(p.partial) + pix * 2;
-            dst[0] = make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
-            dst[1] = make_float4((float)Bout[0], (float)Bout[1], (float)Bout[2], (float)Bout[3]);
-        } else {
-            double4 *dst = reinterpret_cast<double4 *>(p.partial + pix * 8);
-            dst[0] = make_double4(out[0], out[1], out[2], out[3]);
-            dst[1] = make_double4(Bout[0], Bout[1], Bout[2], Bout[3]);
-        }
+        store_partial(p.partial, p.partial_fmt, pix, out, Bout);
     } else {
         *reinterpret_cast<double4 *>(p.image + pix * 4) = make_double4(out[0], out[1], out[2], out[3]);
+    }
+    }
+    if (PARTIAL && p.tail_flag != nullptr) {
+        SwapSignal sg;
+        sg.n = 1; sg.flag[0] = p.tail_flag;
+        grid_tail_signal(p.tail_counter, sg, p.tail_seq);
     }
 }
 
@@ -1235,67 +1233,164 @@ __global__ void __launch_bounds__(VC_THREADS) vertex_centre_kernel(const TIN *__
 }
 
 // ---- binary-swap compositing over NVLink peer memory -----------------------------------
-// One swap round = ONE kernel: it composes this rank's kept half with the partner's copy of the same pixels, read
-// straight out of the partner's HBM through its NVLink peer mapping -- no send/recv, no receive buffer.
-// Ordering between GPUs is a sequence number per (rank, round) pushed into the CONSUMER's memory by a
-// stream-ordered `swap_signal_kernel` after the producer kernel, and awaited by `swap_wait_kernel` (local spin).
-template <typename V4>
-__global__ void compose_peer_kernel(const V4 *__restrict__ mine, const V4 *__restrict__ theirs, V4 *__restrict__ out,
-                                    long long n, int mine_is_earlier)
+// One swap round = ONE kernel: it waits (every CTA spins on a flag word in this rank's own memory) until the partner has
+// finished the buffer it is about to read, composes this rank's kept half with the partner's copy of the same pixels --
+// read straight out of the partner's HBM through its NVLink peer mapping: no send/recv, no receive buffer -- stores the
+// result (locally; in the LAST round into the destination ranks' slabs, or as finished fp64 pixels into the caller's
+// page-locked host image) and, when the whole grid has stored, pushes the frame's sequence number into the flag word
+// of whoever reads that result next.  A frame is k + 2 launches on the destination rank (cast, k rounds, apply) and
+// k + 1 elsewhere, whatever the image size.
+
+// the map of pixel i in compute precision CT (float for the fp32 formats, double otherwise)
+template <int FMT> struct pf_compute { using type = double; };
+template <> struct pf_compute<PF_AB32> { using type = float; };
+template <> struct pf_compute<PF_A32> { using type = float; };
+template <> struct pf_compute<PF_A32G> { using type = float; };
+
+template <int FMT, typename CT>
+__device__ __forceinline__ void pf_load(const void *__restrict__ buf, long long i, CT (&A)[4], CT (&B)[4])
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const V4 Am = mine[2 * i], Bm = mine[2 * i + 1];
-    const V4 At = theirs[2 * i], Bt = theirs[2 * i + 1];
-    const V4 A1 = mine_is_earlier ? Am : At, B1 = mine_is_earlier ? Bm : Bt;   // applied first
-    const V4 A2 = mine_is_earlier ? At : Am, B2 = mine_is_earlier ? Bt : Bm;   // applied second
-    V4 A, B;
-    A.x = B2.x * A1.x + A2.x; A.y = B2.y * A1.y + A2.y; A.z = B2.z * A1.z + A2.z; A.w = B2.w * A1.w + A2.w;
-    B.x = B2.x * B1.x; B.y = B2.y * B1.y; B.z = B2.z * B1.z; B.w = B2.w * B1.w;
-    out[2 * i] = A;
-    out[2 * i + 1] = B;
+    if constexpr (FMT == PF_AB64) {
+        const double4 a = reinterpret_cast<const double4 *>(buf)[2 * i], b = reinterpret_cast<const double4 *>(buf)[2 * i + 1];
+        A[0] = a.x; A[1] = a.y; A[2] = a.z; A[3] = a.w; B[0] = b.x; B[1] = b.y; B[2] = b.z; B[3] = b.w;
+    } else if constexpr (FMT == PF_AB32) {
+        const float4 a = reinterpret_cast<const float4 *>(buf)[2 * i], b = reinterpret_cast<const float4 *>(buf)[2 * i + 1];
+        A[0] = a.x; A[1] = a.y; A[2] = a.z; A[3] = a.w; B[0] = b.x; B[1] = b.y; B[2] = b.z; B[3] = b.w;
+    } else if constexpr (FMT == PF_A32) {
+        const float4 a = reinterpret_cast<const float4 *>(buf)[i];
+        const unsigned bits = (unsigned)a.w;
+        A[0] = a.x; A[1] = a.y; A[2] = a.z; A[3] = 0.f;
+        B[0] = (bits & 1u) ? 0.f : 1.f - a.x; B[1] = (bits & 2u) ? 0.f : 1.f - a.y; B[2] = (bits & 4u) ? 0.f : 1.f - a.z; B[3] = 1.f;
+    } else if constexpr (FMT == PF_A32G) {
+        const float4 a = reinterpret_cast<const float4 *>(buf)[i];
+        const float al = fabsf(a.w);
+        const float b = signbit(a.w) ? 0.f : 1.f - al;
+        A[0] = a.x; A[1] = a.y; A[2] = a.z; A[3] = al;
+        B[0] = B[1] = B[2] = B[3] = b;
+    } else if constexpr (FMT == PF_SUM1) {
+        A[0] = reinterpret_cast<const double *>(buf)[i]; A[1] = A[2] = A[3] = 0.0;
+        B[0] = B[1] = B[2] = B[3] = 1.0;
+    } else if constexpr (FMT == PF_SUM2) {
+        const double2 a = reinterpret_cast<const double2 *>(buf)[i];
+        A[0] = a.x; A[1] = a.y; A[2] = A[3] = 0.0;
+        B[0] = B[1] = B[2] = B[3] = 1.0;
+    } else {
+        const double4 a = reinterpret_cast<const double4 *>(buf)[i];
+        A[0] = a.x; A[1] = a.y; A[2] = a.z; A[3] = a.w;
+        B[0] = B[1] = B[2] = B[3] = 1.0;
+    }
 }
 
-// image_dst[k][i] = A + B * C0[i] on this rank's final strip, stored into every destination image (own frame
-// and/or peers' frames over NVLink): the gather of the strips costs no extra pass.
-constexpr int SWAP_MAX_DST = 8;
-struct SwapDst { double4 *img[SWAP_MAX_DST]; int n; };
-
-template <typename V4>
-__global__ void apply_store_kernel(const V4 *__restrict__ partial, const double4 *__restrict__ c0, SwapDst dst, long long n)
+template <int FMT, typename CT>
+__device__ __forceinline__ void pf_store(void *__restrict__ buf, long long i, const CT (&A)[4], const CT (&B)[4])
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const V4 A = partial[2 * i], B = partial[2 * i + 1];
-    const double4 c = c0[i];
-    const double4 v = make_double4(fma((double)B.x, c.x, (double)A.x), fma((double)B.y, c.y, (double)A.y),
-                                   fma((double)B.z, c.z, (double)A.z), fma((double)B.w, c.w, (double)A.w));
-    for (int k = 0; k < dst.n; k++) dst.img[k][i] = v;
+    if constexpr (FMT == PF_AB64) {
+        reinterpret_cast<double4 *>(buf)[2 * i] = make_double4(A[0], A[1], A[2], A[3]);
+        reinterpret_cast<double4 *>(buf)[2 * i + 1] = make_double4(B[0], B[1], B[2], B[3]);
+    } else if constexpr (FMT == PF_AB32) {
+        reinterpret_cast<float4 *>(buf)[2 * i] = make_float4(A[0], A[1], A[2], A[3]);
+        reinterpret_cast<float4 *>(buf)[2 * i + 1] = make_float4(B[0], B[1], B[2], B[3]);
+    } else if constexpr (FMT == PF_A32) {
+        const unsigned bits = (B[0] == CT(0) ? 1u : 0u) | (B[1] == CT(0) ? 2u : 0u) | (B[2] == CT(0) ? 4u : 0u);
+        reinterpret_cast<float4 *>(buf)[i] = make_float4(A[0], A[1], A[2], (float)bits);
+    } else if constexpr (FMT == PF_A32G) {
+        const float al = fabsf((float)A[3]);
+        reinterpret_cast<float4 *>(buf)[i] = make_float4(A[0], A[1], A[2], B[3] == CT(0) ? -al : al);
+    } else if constexpr (FMT == PF_SUM1) {
+        reinterpret_cast<double *>(buf)[i] = A[0];
+    } else if constexpr (FMT == PF_SUM2) {
+        reinterpret_cast<double2 *>(buf)[i] = make_double2(A[0], A[1]);
+    } else {
+        reinterpret_cast<double4 *>(buf)[i] = make_double4(A[0], A[1], A[2], A[3]);
+    }
 }
 
-struct SwapSignal { unsigned long long *flag[SWAP_MAX_DST]; int n; };
-
-__global__ void swap_signal_kernel(SwapSignal s, unsigned long long seq)
+// Every CTA's first `n` threads spin (in this rank's memory) until flag k has reached `seq`; gives up after ~10 s and
+// records the failure.  The fence after the barrier orders the reads that follow behind the flag observation.
+__device__ __forceinline__ void grid_wait(const unsigned long long *flags, int n, unsigned long long seq, int *error)
 {
+    if ((int)threadIdx.x < n) {
+        const volatile unsigned long long *f = flags + threadIdx.x;
+        unsigned long long t0 = 0;
+        bool timing = false;
+        while (*f < seq) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (!timing) { t0 = t; timing = true; }
+            if (t - t0 > 10000000000ULL) { *error = 1; break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
     __threadfence_system();
-    if (threadIdx.x < s.n) *reinterpret_cast<volatile unsigned long long *>(s.flag[threadIdx.x]) = seq;
-    __threadfence_system();
 }
 
-// Spin (locally) until every flag has reached `seq`; gives up after ~10 s and records the failure.
+struct SwapOut { void *buf[SWAP_MAX_DST]; int n; };   // destination buffers (own memory and / or peers')
+
+struct SwapRoundArgs {
+    const void *mine, *theirs;      // both start at the first kept pixel
+    long long n;                    // kept pixels
+    int mine_is_earlier;            // whose map is applied first
+    const unsigned long long *wait_flag; unsigned long long seq; int *error;   // partner's buffer complete?
+    SwapOut out;                    // partial-format destinations (STORE_PARTIAL)
+    const double4 *c0; double4 *image;   // APPLY: initial colours and fp64 destination of the strip (both offset to it)
+    unsigned *counter; SwapSignal done;  // whom to tell when this grid has stored
+};
+
+// APPLY == false: out[k][i] = compose(mine[i], theirs[i]);  APPLY == true: image[i] = compose(...)(c0[i])
+template <int FMT, bool APPLY>
+__global__ void __launch_bounds__(256) swap_round_kernel(const __grid_constant__ SwapRoundArgs a)
+{
+    using CT = typename pf_compute<FMT>::type;
+    grid_wait(a.wait_flag, 1, a.seq, a.error);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        CT Am[4], Bm[4], At[4], Bt[4], A[4], B[4];
+        pf_load<FMT, CT>(a.mine, i, Am, Bm);
+        pf_load<FMT, CT>(a.theirs, i, At, Bt);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const CT A1 = a.mine_is_earlier ? Am[c] : At[c], B1 = a.mine_is_earlier ? Bm[c] : Bt[c];   // applied first
+            const CT A2 = a.mine_is_earlier ? At[c] : Am[c], B2 = a.mine_is_earlier ? Bt[c] : Bm[c];   // applied second
+            A[c] = B2 * A1 + A2;
+            B[c] = B2 * B1;
+        }
+        if constexpr (APPLY) {
+            const double4 c = a.c0[i];
+            a.image[i] = make_double4(fma((double)B[0], c.x, (double)A[0]), fma((double)B[1], c.y, (double)A[1]),
+                                      fma((double)B[2], c.z, (double)A[2]), fma((double)B[3], c.w, (double)A[3]));
+        } else {
+            for (int k = 0; k < a.out.n; k++) pf_store<FMT, CT>(a.out.buf[k], i, A, B);
+        }
+    }
+    grid_tail_signal(a.counter, a.done, a.seq);
+}
+
+struct SwapApplyArgs {
+    const void *partial;            // n pixels in format FMT (the composed strips of all ranks, or this rank's own cast)
+    const double4 *c0; double4 *image; long long n;
+    const unsigned long long *wait_flags; int n_wait; unsigned long long seq; int *error;
+};
+
+// image[i] = A[i] + B[i] * c0[i] once every strip of the frame has landed (n_wait flags)
+template <int FMT>
+__global__ void __launch_bounds__(256) swap_apply_kernel(const __grid_constant__ SwapApplyArgs a)
+{
+    using CT = typename pf_compute<FMT>::type;
+    if (a.n_wait > 0) grid_wait(a.wait_flags, a.n_wait, a.seq, a.error);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        CT A[4], B[4];
+        pf_load<FMT, CT>(a.partial, i, A, B);
+        const double4 c = a.c0[i];
+        a.image[i] = make_double4(fma((double)B[0], c.x, (double)A[0]), fma((double)B[1], c.y, (double)A[1]),
+                                  fma((double)B[2], c.z, (double)A[2]), fma((double)B[3], c.w, (double)A[3]));
+    }
+}
+
+// Spin (locally) until every flag has reached `seq`: the destination rank of a host-image frame, whose stream must not
+// complete before every rank's strip has been stored.
 __global__ void swap_wait_kernel(const unsigned long long *flags, int n, unsigned long long seq, int *error)
 {
-    if (threadIdx.x >= n) return;
-    const volatile unsigned long long *f = flags + threadIdx.x;
-    unsigned long long t0;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (*f < seq) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (t - t0 > 10000000000ULL) { *error = 1; break; }
-        __nanosleep(200);
-    }
-    __threadfence_system();
+    grid_wait(flags, n, seq, error);
 }
 
 __global__ void f64_to_f32_kernel(const double *src, float *dst, long long n)

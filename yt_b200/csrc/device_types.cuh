@@ -65,11 +65,25 @@ struct DevTF {
     // kernel-parameter constant bank instead of in registers
     float colour_c0, colour_clamp_bound, colour_lo, colour_hi, colour_mid, colour_half, colour_band, colour_zrow;
     float colour_clamp_hi;   // delta layout: row coordinates are clamped to [0.5, nbins + 1.5]
-    int colour_zero_inside, colour_edge, colour_delta, colour_rows;
+    int colour_zero_inside, colour_edge, colour_delta, colour_rows, colour_nonneg;
     // LightSourceRenderSampler (image_samplers.pyx:496-600): one directional light, gradient shading
     int light_on;
     double light_dir[3], light_rgba[4];
 };
+
+// Formats of a partial image: the per-pixel affine map C -> A + B*C a rank's bricks apply to whatever lies behind them
+// (SURVEY.md A.4).  What crosses NVLink is the smallest exact description of that map:
+//   AB64 / AB32   (A[4], B[4]) in fp64 / fp32: any transfer function (64 / 32 B per pixel)
+//   A32 / A32G    the ColorTransferFunction render (non-grey / grey opacity), fp32 A[4] only (16 B): while no opacity
+//                 clamp has fired B = 1 - A per channel (grey: 1 - A_alpha for all four), and a clamp zeroes B for good
+//                 (ColourAcc), so B is "1 - A, or 0 when flagged"; flags: non-grey in the unused 4th channel (bit c =
+//                 channel c), grey in the sign of A_alpha (alpha tables are non-negative: checked at tf_create)
+//   SUM1/2/4      the projection samplers: B == 1, A = 1 / 2 / 4 fp64 sums (8 / 16 / 32 B)
+enum PartialFormat { PF_AB64 = 0, PF_AB32 = 1, PF_A32 = 2, PF_A32G = 3, PF_SUM1 = 4, PF_SUM2 = 5, PF_SUM4 = 6, PF_COUNT = 7 };
+__host__ __device__ constexpr int partial_bytes(int fmt)
+{
+    return fmt == PF_AB64 ? 64 : fmt == PF_AB32 ? 32 : (fmt == PF_A32 || fmt == PF_A32G) ? 16 : fmt == PF_SUM1 ? 8 : fmt == PF_SUM2 ? 16 : 32;
+}
 
 struct CastParams {
     DevCamera cam;
@@ -81,8 +95,13 @@ struct CastParams {
     double inv_ns;          // 1 / n_samples
     double *image;          // (nx,ny,4) fp64, in/out
     const double *zbuffer;  // (nx,ny) fp64 or nullptr (== ones)
-    double *partial;        // (nx,ny,8) affine map output (fp64, or fp32 when partial_f32), or nullptr
-    int partial_f32;
+    double *partial;        // affine-map output in format `partial_fmt` (see PartialFormat), or nullptr
+    int partial_fmt;
+    // PARTIAL casts feeding a peer swap: when the whole grid has stored its pixels, the last CTA writes `tail_seq` into
+    // `tail_flag` (the round-0 partner's flag word, over NVLink); `tail_counter` counts the CTAs (this rank's memory)
+    unsigned *tail_counter;
+    unsigned long long *tail_flag;
+    unsigned long long tail_seq;
     DevTF tf;
     unsigned long long *counters;  // [0] cells handed to sample()
 };

@@ -78,7 +78,14 @@ __global__ void __launch_bounds__(CTA_THREADS, YTB_PROJ_MINB) proj_kernel(const 
         const int h = min(map.band, map.n_stiles - b * map.band);   // s-tiles in this band
         F = r / h;
         S = b * map.band + (r - F * h);
-        if (F >= map.n_ftiles) return;   // the last band is shorter: its surplus CTAs have no tile
+        if (F >= map.n_ftiles) {   // the last band is shorter: its surplus CTAs have no tile (they still count for the tail signal)
+            if (PARTIAL && p.tail_flag != nullptr) {
+                SwapSignal sg;
+                sg.n = 1; sg.flag[0] = p.tail_flag;
+                grid_tail_signal(p.tail_counter, sg, p.tail_seq);
+            }
+            return;
+        }
     }
     int vi, vj, ti0, ti1, tj0, tj1;
     if (map.mode == 0) {
@@ -359,29 +366,28 @@ __global__ void __launch_bounds__(CTA_THREADS, YTB_PROJ_MINB) proj_kernel(const 
     }
 
     // ---- write back -----------------------------------------------------------------------------------------
-    if (!active) return;
-    double out[4] = {0.0, 0.0, 0.0, 0.0};
+    if (active) {
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int f = 0; f < NF; f++) out[f] = acc[f];
-    if (PARTIAL) {
-        if (p.partial_f32) {
-            float4 *dst = reinterpret_cast<float4 *>(p.partial) + pix * 2;
-            dst[0] = make_float4((float)out[0], (float)out[1], (float)out[2], (float)out[3]);
-            dst[1] = make_float4(1.f, 1.f, 1.f, 1.f);
+        for (int f = 0; f < NF; f++) out[f] = acc[f];
+        if (PARTIAL) {
+            const double one[4] = {1.0, 1.0, 1.0, 1.0};
+            store_partial(p.partial, p.partial_fmt, pix, out, one);
         } else {
-            double4 *dst = reinterpret_cast<double4 *>(p.partial + pix * 8);
-            dst[0] = make_double4(out[0], out[1], out[2], out[3]);
-            dst[1] = make_double4(1.0, 1.0, 1.0, 1.0);
+            if (NF < 4) {
+                // channels the sampler does not touch keep their value (image_samplers.pyx:337-343 sums min(4, n_fields))
+                const double4 px = *reinterpret_cast<const double4 *>(p.image + pix * 4);
+                if (NF < 2) out[1] = px.y;
+                if (NF < 3) out[2] = px.z;
+                out[3] = px.w;
+            }
+            *reinterpret_cast<double4 *>(p.image + pix * 4) = make_double4(out[0], out[1], out[2], out[3]);
         }
-    } else {
-        if (NF < 4) {
-            // channels the sampler does not touch keep their value (image_samplers.pyx:337-343 sums min(4, n_fields))
-            const double4 px = *reinterpret_cast<const double4 *>(p.image + pix * 4);
-            if (NF < 2) out[1] = px.y;
-            if (NF < 3) out[2] = px.z;
-            out[3] = px.w;
-        }
-        *reinterpret_cast<double4 *>(p.image + pix * 4) = make_double4(out[0], out[1], out[2], out[3]);
+    }
+    if (PARTIAL && p.tail_flag != nullptr) {
+        SwapSignal sg;
+        sg.n = 1; sg.flag[0] = p.tail_flag;
+        grid_tail_signal(p.tail_counter, sg, p.tail_seq);
     }
 }
 

@@ -722,4 +722,52 @@ __device__ __forceinline__ void make_ray(const DevCamera &cam, int vi, int vj, d
     }
 }
 
+// ---- partial images: store one pixel's map in any format; grid-wide completion signal ----------------------------
+// out / Bout: the map as the cast kernels hold it at write-back (fp64 temporaries; B is exactly 0 where a clamp fired).
+__device__ __forceinline__ void store_partial(void *buf, int fmt, size_t pix, const double (&A)[4], const double (&B)[4])
+{
+    if (fmt == PF_AB64) {
+        double4 *dst = reinterpret_cast<double4 *>(buf) + pix * 2;
+        dst[0] = make_double4(A[0], A[1], A[2], A[3]);
+        dst[1] = make_double4(B[0], B[1], B[2], B[3]);
+    } else if (fmt == PF_AB32) {
+        float4 *dst = reinterpret_cast<float4 *>(buf) + pix * 2;
+        dst[0] = make_float4((float)A[0], (float)A[1], (float)A[2], (float)A[3]);
+        dst[1] = make_float4((float)B[0], (float)B[1], (float)B[2], (float)B[3]);
+    } else if (fmt == PF_A32) {
+        const unsigned bits = (B[0] == 0.0 ? 1u : 0u) | (B[1] == 0.0 ? 2u : 0u) | (B[2] == 0.0 ? 4u : 0u);
+        reinterpret_cast<float4 *>(buf)[pix] = make_float4((float)A[0], (float)A[1], (float)A[2], (float)bits);
+    } else if (fmt == PF_A32G) {
+        const float a = fabsf((float)A[3]);
+        reinterpret_cast<float4 *>(buf)[pix] = make_float4((float)A[0], (float)A[1], (float)A[2], B[3] == 0.0 ? -a : a);
+    } else if (fmt == PF_SUM1) {
+        reinterpret_cast<double *>(buf)[pix] = A[0];
+    } else if (fmt == PF_SUM2) {
+        reinterpret_cast<double2 *>(buf)[pix] = make_double2(A[0], A[1]);
+    } else {
+        reinterpret_cast<double4 *>(buf)[pix] = make_double4(A[0], A[1], A[2], A[3]);
+    }
+}
+
+constexpr int SWAP_MAX_DST = 8;
+struct SwapSignal { unsigned long long *flag[SWAP_MAX_DST]; int n; };
+
+// Called by EVERY thread of EVERY CTA as the last thing a kernel does: when all CTAs have passed, the last one writes
+// `seq` into the flag words (which may live in a peer's memory).  The fences make every store of the grid visible
+// system-wide before the flags are.
+__device__ __forceinline__ void grid_tail_signal(unsigned *counter, const SwapSignal &sg, unsigned long long seq)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(counter, 1u) == total - 1u) {
+            *counter = 0u;   // the next kernel that counts on it is stream-ordered after this one
+            __threadfence_system();
+            for (int k = 0; k < sg.n; k++) *reinterpret_cast<volatile unsigned long long *>(sg.flag[k]) = seq;
+            __threadfence_system();
+        }
+    }
+}
+
 }  // namespace ytb

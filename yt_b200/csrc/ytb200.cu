@@ -578,6 +578,8 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
         // every product that meets dt before a clamp: alpha (grey) or alpha * colour (RGB weighted by alpha)
         d.colour_clamp_bound = (float)(1.0000002 * a_max * fmax(1.0, rgb_max));
         d.colour_zero_inside = (b0 < 0.0 && b1 > 0.0) ? 1 : 0;
+        d.colour_nonneg = 1;   // alpha never negative: a ray's alpha accumulator keeps its sign bit free (PF_A32G)
+        for (int j = 0; j < nb; j++) if (!(y[3][j] >= 0.0)) d.colour_nonneg = 0;
         // does a sample flipping across a bound change the result?  Only if the alpha table (which also
         // weights R, G, B) does not vanish there.
         const double edge = fmax(fabs(y[3][0]), fabs(y[3][nb - 1])) * fmax(1.0, rgb_max);
@@ -812,7 +814,8 @@ static cudaError_t launch_kind(const CastParams &p, unsigned grid, size_t smem, 
 
 static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order, int64_t n_order,
                        const ytb200_tf *tf, int n_samples, int precision, double *partial, ytb200_stats *stats,
-                       bool partial_f32 = false)
+                       int partial_fmt = PF_AB64, unsigned *tail_counter = nullptr, unsigned long long *tail_flag = nullptr,
+                       unsigned long long tail_seq = 0)
 {
     if (!f || !set || (!order && n_order > 0)) return fail(E_ARG, "NULL argument");
     if (kind < 0 || kind > 2) return fail(E_ARG, "bad sampler kind %d", kind);
@@ -842,7 +845,8 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
         p.bricks = set->dev; p.order = f->order_dev; p.extent = f->extent_dev; p.n_order = (int)n_order;
         p.n_samples = n_samples < 1 ? 1 : n_samples;
         p.inv_ns = 1.0 / (double)p.n_samples;
-        p.image = f->image; p.zbuffer = f->zbuffer; p.partial = partial; p.partial_f32 = partial_f32 ? 1 : 0;
+        p.image = f->image; p.zbuffer = f->zbuffer; p.partial = partial; p.partial_fmt = partial_fmt;
+        p.tail_counter = tail_counter; p.tail_flag = tail_flag; p.tail_seq = tail_seq;
         if (partial && f->zbuffer_in) p.zbuffer = f->zbuffer_in;
         if (partial && f->zbuffer_in_ones) p.zbuffer = nullptr;
         if (tf) p.tf = tf->d;
@@ -917,7 +921,7 @@ extern "C" int ytb200_frame_cast_partial_f32(ytb200_frame *f, int kind, const yt
 {
     if (!partial_dev) return fail(E_ARG, "partial_dev is NULL");
     if (precision != YTB200_PREC_FAST) return fail(E_ARG, "fp32 partial images are for FAST precision only");
-    return cast_common(f, kind, set, order, n_order, tf, n_samples, precision, reinterpret_cast<double *>(partial_dev), stats, true);
+    return cast_common(f, kind, set, order, n_order, tf, n_samples, precision, reinterpret_cast<double *>(partial_dev), stats, PF_AB32);
 }
 
 extern "C" int ytb200_frame_count(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
@@ -1125,40 +1129,57 @@ extern "C" int ytb200_frame_cast_octree(ytb200_frame *f, int kind, ytb200_octree
 // ------------------------------------------------------------------------------------------------
 // Per rank ONE cudaMalloc'd slab, shared with the peers through a CUDA IPC handle:
 //   [0, 512)            64 x u64: flag[j] (j < 16) "partner_j's buffer_j of frame `seq` is complete" (pushed by that
-//                       partner), final[w] at 16 + w "rank w has stored its strip of frame `seq` into my image",
-//                       error word at 56
+//                       partner's kernel tail), final[w] at 16 + w "rank w has stored its strip of frame `seq`",
+//                       error word at 56, CTA counter of the tail signals at 57
 //   two parity sets of buffers: buffer_0 (n_pixels, the cast's output), buffer_{j+1} (ceil(cap_j / 2)) ...
-//   the final image (n_pixels x double4): every rank stores its finished strip into the destination ranks' copy of
-//   this region, which each destination then copies into its own frame -- frames can come and go, the slab stays
+//   the final region (n_pixels, partial format): every rank's last round stores its composed strip into the destination
+//   ranks' copy of this region; the destination applies it to the initial colours -- frames can come and go, the slab stays
 // The layout is identical on every rank, so a peer's buffer address is its slab base + the same offset.
 struct SwapRound { int partner; int64_t p0, p1, k0, k1; int earlier; };
 
 struct ytb200_swap {
     ytb200_ctx *ctx = nullptr;
     int64_t npx = 0;
-    int rank = 0, world = 1, bpp = 32, k = 0;
+    int rank = 0, world = 1, fmt = PF_AB32, bpp = 32, k = 0;
     unsigned char *slab = nullptr;
     size_t slab_bytes = 0, set_bytes = 0;
     std::vector<size_t> buf_off;             // offset of buffer_j inside one parity set
     std::vector<unsigned char *> peer_slab;  // [world], own slab at [rank]
-    size_t final_off = 0;                    // offset of the final-image region
+    size_t final_off = 0;                    // offset of the final region
     std::vector<SwapRound> rounds;
-    unsigned long long seq = 0;
+    unsigned long long seq = 0;              // frames cast so far
+    unsigned long long composited = 0;       // frames composited so far
 };
 
 static const size_t SWAP_HDR = 512;
+enum { SWAP_FLAG_FINAL = 16, SWAP_WORD_ERROR = 56, SWAP_WORD_COUNTER = 57 };
 
 static unsigned long long *swap_flag(unsigned char *slab, int idx) { return reinterpret_cast<unsigned long long *>(slab) + idx; }
 
-extern "C" int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, int world, int bytes_per_pixel, ytb200_swap **out)
+extern "C" int ytb200_partial_format(int kind, const ytb200_tf *tf, int n_fields, int precision)
+{
+    if (kind == YTB200_VOLUME_RENDER) {
+        if (!tf) return fail(E_ARG, "VolumeRenderSampler needs a transfer function");
+        if (precision == YTB200_PREC_EXACT) return PF_AB64;
+        if (n_fields == 1 && tf->d.colour_fast && !tf->d.light_on && tf->d.colour_nonneg) return tf->d.grey ? PF_A32G : PF_A32;
+        return PF_AB32;
+    }
+    // image_samplers.pyx:337-343 / 393-401: the first min(4, n) / min(3, n) fields are summed
+    const int n = kind == YTB200_PROJECTION ? std::min(4, n_fields) : std::min(3, n_fields);
+    return n <= 1 ? PF_SUM1 : (n == 2 ? PF_SUM2 : PF_SUM4);
+}
+
+extern "C" int ytb200_partial_bytes(int format) { return (format >= 0 && format < PF_COUNT) ? partial_bytes(format) : 0; }
+
+extern "C" int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, int world, int format, ytb200_swap **out)
 {
     if (!ctx || !out) return fail(E_ARG, "NULL argument");
     if (world < 1 || world > SWAP_MAX_DST || (world & (world - 1))) return fail(E_ARG, "world must be a power of two <= %d", SWAP_MAX_DST);
     if (rank < 0 || rank >= world || n_pixels < 1) return fail(E_ARG, "bad rank / n_pixels");
-    if (bytes_per_pixel != 32 && bytes_per_pixel != 64) return fail(E_ARG, "bytes_per_pixel must be 32 (fp32 A,B) or 64 (fp64 A,B)");
+    if (format < 0 || format >= PF_COUNT) return fail(E_ARG, "bad partial format %d", format);
     DeviceGuard g(ctx->device);
     auto *s = new ytb200_swap;
-    s->ctx = ctx; s->npx = n_pixels; s->rank = rank; s->world = world; s->bpp = bytes_per_pixel;
+    s->ctx = ctx; s->npx = n_pixels; s->rank = rank; s->world = world; s->fmt = format; s->bpp = partial_bytes(format);
     int k = 0;
     while ((1 << k) < world) k++;
     s->k = k;
@@ -1166,12 +1187,12 @@ extern "C" int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, i
     int64_t cap = n_pixels;
     for (int j = 0; j <= k; j++) {
         s->buf_off.push_back(off);
-        off += ((size_t)cap * (size_t)bytes_per_pixel + 255) / 256 * 256;
+        off += ((size_t)cap * (size_t)s->bpp + 255) / 256 * 256;
         cap = (cap + 1) / 2;
     }
     s->set_bytes = off;
     s->final_off = SWAP_HDR + 2 * off;
-    s->slab_bytes = s->final_off + (size_t)n_pixels * sizeof(double4);
+    s->slab_bytes = s->final_off + (size_t)n_pixels * (size_t)s->bpp;
     CK(cudaMalloc(&s->slab, s->slab_bytes));
     CK(cudaMemsetAsync(s->slab, 0, SWAP_HDR, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1180,6 +1201,8 @@ extern "C" int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, i
     *out = s;
     return 0;
 }
+
+extern "C" int ytb200_swap_format(const ytb200_swap *s) { return s ? s->fmt : -1; }
 
 extern "C" int ytb200_swap_destroy(ytb200_swap *s)
 {
@@ -1238,72 +1261,150 @@ extern "C" int ytb200_swap_plan(ytb200_swap *s, int n_rounds, const int32_t *par
     return 0;
 }
 
-extern "C" void *ytb200_swap_partial(ytb200_swap *s)
+// This rank's partial cast of the next frame, straight into the swap's buffer_0 and in the swap's format; the cast
+// kernel's last CTA tells the round-0 partner.
+extern "C" int ytb200_swap_cast(ytb200_swap *s, ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order,
+                                int64_t n_order, const ytb200_tf *tf, int n_samples, int precision, ytb200_stats *stats)
 {
-    if (!s) return nullptr;
-    const unsigned long long next = s->seq + 1;
-    return s->slab + SWAP_HDR + (size_t)(next & 1) * s->set_bytes + s->buf_off[0];
-}
-
-template <typename V4>
-static int swap_run(ytb200_swap *s, ytb200_frame *f, int broadcast)
-{
-    cudaStream_t st = s->ctx->stream;
-    const unsigned long long seq = ++s->seq;
-    const size_t set = SWAP_HDR + (size_t)(seq & 1) * s->set_bytes;
-    int *err = reinterpret_cast<int *>(swap_flag(s->slab, 56));
-    auto buf = [&](unsigned char *slab, int j) { return reinterpret_cast<V4 *>(slab + set + s->buf_off[(size_t)j]); };
-    auto signal_one = [&](unsigned char *slab, int idx) {
-        SwapSignal sg{};
-        sg.n = 1; sg.flag[0] = swap_flag(slab, idx);
-        swap_signal_kernel<<<1, 32, 0, st>>>(sg, seq);
-    };
+    if (!s || !f || !set) return fail(E_ARG, "NULL argument");
+    if ((int64_t)f->cam.nx * f->cam.ny != s->npx) return fail(E_ARG, "frame has %lld pixels, swap was created for %lld", (long long)f->cam.nx * f->cam.ny, (long long)s->npx);
+    if (f->ctx != s->ctx) return fail(E_ARG, "frame and swap use different contexts");
+    if ((int)s->rounds.size() != s->k) return fail(E_STATE, "ytb200_swap_plan has not been called");
+    if (s->seq != s->composited) return fail(E_STATE, "the previous frame has been cast but not composited");
+    const int want = ytb200_partial_format(kind, tf, set->n_fields, precision);
+    if (want < 0) return want;
+    // a swap created for a wider format of the same family can carry a narrower map; anything else is a mismatch
+    const bool ok = want == s->fmt || (want == PF_AB32 && s->fmt == PF_AB64) ||
+                    ((want == PF_A32 || want == PF_A32G) && (s->fmt == PF_AB32 || s->fmt == PF_AB64)) ||
+                    (want == PF_SUM1 && (s->fmt == PF_SUM2 || s->fmt == PF_SUM4)) || (want == PF_SUM2 && s->fmt == PF_SUM4);
+    if (!ok) return fail(E_ARG, "swap was created for partial format %d, this cast produces format %d (ytb200_partial_format)", s->fmt, want);
+    if (s->fmt == PF_AB32 && precision != YTB200_PREC_FAST) return fail(E_ARG, "fp32 partial images are for FAST precision only");
     for (int j = 0; j < s->k; j++)
         if (!s->peer_slab[(size_t)s->rounds[(size_t)j].partner]) return fail(E_STATE, "peer %d not opened", s->rounds[(size_t)j].partner);
-    if (s->k > 0) signal_one(s->peer_slab[(size_t)s->rounds[0].partner], 0);   // my buffer_0 (the cast's output) is complete
-    int64_t f0 = 0, f1 = s->npx;
-    for (int j = 0; j < s->k; j++) {
-        const SwapRound &r = s->rounds[(size_t)j];
-        swap_wait_kernel<<<1, 32, 0, st>>>(swap_flag(s->slab, j), 1, seq, err);
-        const long long n = (long long)(r.k1 - r.k0);
-        if (n > 0) {
-            const V4 *mine = buf(s->slab, j) + 2 * (r.k0 - r.p0);
-            const V4 *theirs = buf(s->peer_slab[(size_t)r.partner], j) + 2 * (r.k0 - r.p0);
-            compose_peer_kernel<V4><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mine, theirs, buf(s->slab, j + 1), n, r.earlier);
-        }
-        if (j + 1 < s->k) signal_one(s->peer_slab[(size_t)s->rounds[(size_t)j + 1].partner], j + 1);
-        f0 = r.k0; f1 = r.k1;
-    }
-    // final strip -> every destination image, then tell the destinations
-    SwapDst dst{};
-    SwapSignal fin{};
-    for (int w = 0; w < s->world; w++) {
-        if (!broadcast && w != 0) continue;
-        if (!s->peer_slab[(size_t)w]) return fail(E_STATE, "destination rank %d not opened", w);
-        dst.img[dst.n++] = reinterpret_cast<double4 *>(s->peer_slab[(size_t)w] + s->final_off) + f0;
-        fin.flag[fin.n++] = swap_flag(s->peer_slab[(size_t)w], 16 + s->rank);
-    }
-    const long long nf = (long long)(f1 - f0);
-    if (nf > 0 && dst.n > 0)
-        apply_store_kernel<V4><<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(buf(s->slab, s->k), reinterpret_cast<const double4 *>(f->c0_in ? f->c0_in : f->image) + f0, dst, nf);
-    if (fin.n > 0) swap_signal_kernel<<<1, 32, 0, st>>>(fin, seq);
-    if (broadcast || s->rank == 0) {
-        // every strip of this frame has landed in my final-image region: hand it to the frame
-        swap_wait_kernel<<<1, 32, 0, st>>>(swap_flag(s->slab, 16), s->world, seq, err);
-        CK(cudaMemcpyAsync(f->image, s->slab + s->final_off, (size_t)s->npx * sizeof(double4), cudaMemcpyDeviceToDevice, st));
-    }
-    CK(cudaGetLastError());
+    const unsigned long long seq = s->seq + 1;
+    unsigned char *buf0 = s->slab + SWAP_HDR + (size_t)(seq & 1) * s->set_bytes + s->buf_off[0];
+    unsigned long long *flag = s->k > 0 ? swap_flag(s->peer_slab[(size_t)s->rounds[0].partner], 0) : nullptr;
+    int rc = cast_common(f, kind, set, order, n_order, tf, n_samples, precision, reinterpret_cast<double *>(buf0), stats, s->fmt,
+                         reinterpret_cast<unsigned *>(swap_flag(s->slab, SWAP_WORD_COUNTER)), flag, seq);
+    if (rc) return rc;
+    s->seq = seq;
     return 0;
 }
 
-extern "C" int ytb200_swap_composite(ytb200_swap *s, ytb200_frame *f, int broadcast)
+template <int FMT>
+static int swap_run(ytb200_swap *s, ytb200_frame *f, int broadcast, double *host_image)
+{
+    cudaStream_t st = s->ctx->stream;
+    const unsigned long long seq = s->seq;
+    const size_t set = SWAP_HDR + (size_t)(seq & 1) * s->set_bytes;
+    const size_t bpp = (size_t)s->bpp;
+    int *err = reinterpret_cast<int *>(swap_flag(s->slab, SWAP_WORD_ERROR));
+    unsigned *counter = reinterpret_cast<unsigned *>(swap_flag(s->slab, SWAP_WORD_COUNTER));
+    auto buf = [&](unsigned char *slab, int j) { return slab + set + s->buf_off[(size_t)j]; };
+    const double4 *c0 = reinterpret_cast<const double4 *>(f->c0_in ? f->c0_in : f->image);
+    const bool dest = broadcast || s->rank == 0;
+    auto blocks = [&](long long n) { return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)s->ctx->sm_count * 8)); };
+    for (int w = 0; w < s->world; w++)
+        if ((broadcast || w == 0) && !s->peer_slab[(size_t)w]) return fail(E_STATE, "destination rank %d not opened", w);
+    int64_t f0 = 0, f1 = s->npx;
+    for (int j = 0; j < s->k; j++) {
+        const SwapRound &r = s->rounds[(size_t)j];
+        const bool last = j + 1 == s->k;
+        SwapRoundArgs a{};
+        a.mine = buf(s->slab, j) + (size_t)(r.k0 - r.p0) * bpp;
+        a.theirs = buf(s->peer_slab[(size_t)r.partner], j) + (size_t)(r.k0 - r.p0) * bpp;
+        a.n = (long long)(r.k1 - r.k0);
+        a.mine_is_earlier = r.earlier;
+        a.wait_flag = swap_flag(s->slab, j); a.seq = seq; a.error = err;
+        a.counter = counter;
+        f0 = r.k0; f1 = r.k1;
+        if (!last) {
+            a.out.n = 1; a.out.buf[0] = buf(s->slab, j + 1);
+            a.done.n = 1; a.done.flag[0] = swap_flag(s->peer_slab[(size_t)s->rounds[(size_t)j + 1].partner], j + 1);
+            swap_round_kernel<FMT, false><<<blocks(a.n), 256, 0, st>>>(a);
+        } else if (host_image) {
+            // finished fp64 pixels of this rank's strip, straight into the caller's page-locked image over this GPU's PCIe link
+            a.c0 = c0 + f0; a.image = reinterpret_cast<double4 *>(host_image) + f0;
+            a.done.n = 1; a.done.flag[0] = swap_flag(s->peer_slab[0], SWAP_FLAG_FINAL + s->rank);
+            swap_round_kernel<FMT, true><<<blocks(a.n), 256, 0, st>>>(a);
+        } else {
+            for (int w = 0; w < s->world; w++) {
+                if (!broadcast && w != 0) continue;
+                a.out.buf[a.out.n++] = s->peer_slab[(size_t)w] + s->final_off + (size_t)f0 * bpp;
+                a.done.flag[a.done.n++] = swap_flag(s->peer_slab[(size_t)w], SWAP_FLAG_FINAL + s->rank);
+            }
+            swap_round_kernel<FMT, false><<<blocks(a.n), 256, 0, st>>>(a);
+        }
+        CK(cudaGetLastError());
+    }
+    if (host_image) {
+        if (s->k == 0) {
+            SwapApplyArgs a{};
+            a.partial = buf(s->slab, 0); a.c0 = c0; a.image = reinterpret_cast<double4 *>(host_image); a.n = (long long)s->npx;
+            swap_apply_kernel<FMT><<<blocks(a.n), 256, 0, st>>>(a);
+        } else if (s->rank == 0) {
+            swap_wait_kernel<<<1, 32, 0, st>>>(swap_flag(s->slab, SWAP_FLAG_FINAL), s->world, seq, err);
+        }
+    } else if (dest) {
+        SwapApplyArgs a{};
+        a.partial = s->k == 0 ? buf(s->slab, 0) : s->slab + s->final_off;
+        a.c0 = c0; a.image = reinterpret_cast<double4 *>(f->image); a.n = (long long)s->npx;
+        a.wait_flags = swap_flag(s->slab, SWAP_FLAG_FINAL); a.n_wait = s->k == 0 ? 0 : s->world; a.seq = seq; a.error = err;
+        swap_apply_kernel<FMT><<<blocks(a.n), 256, 0, st>>>(a);
+    }
+    CK(cudaGetLastError());
+    s->composited = seq;
+    return 0;
+}
+
+static int swap_dispatch(ytb200_swap *s, ytb200_frame *f, int broadcast, double *host_image)
+{
+    switch (s->fmt) {
+    case PF_AB64: return swap_run<PF_AB64>(s, f, broadcast, host_image);
+    case PF_AB32: return swap_run<PF_AB32>(s, f, broadcast, host_image);
+    case PF_A32: return swap_run<PF_A32>(s, f, broadcast, host_image);
+    case PF_A32G: return swap_run<PF_A32G>(s, f, broadcast, host_image);
+    case PF_SUM1: return swap_run<PF_SUM1>(s, f, broadcast, host_image);
+    case PF_SUM2: return swap_run<PF_SUM2>(s, f, broadcast, host_image);
+    default: return swap_run<PF_SUM4>(s, f, broadcast, host_image);
+    }
+}
+
+static int swap_check(ytb200_swap *s, ytb200_frame *f)
 {
     if (!s || !f) return fail(E_ARG, "NULL argument");
     if ((int64_t)f->cam.nx * f->cam.ny != s->npx) return fail(E_ARG, "frame has %lld pixels, swap was created for %lld", (long long)f->cam.nx * f->cam.ny, (long long)s->npx);
     if ((int)s->rounds.size() != s->k) return fail(E_STATE, "ytb200_swap_plan has not been called");
     if (f->ctx != s->ctx) return fail(E_ARG, "frame and swap use different contexts");
+    if (s->seq == s->composited) return fail(E_STATE, "ytb200_swap_cast first: no frame waits to be composited");
+    return 0;
+}
+
+extern "C" int ytb200_swap_composite(ytb200_swap *s, ytb200_frame *f, int broadcast)
+{
+    int rc = swap_check(s, f);
+    if (rc) return rc;
     DeviceGuard g(s->ctx->device);
-    return s->bpp == 32 ? swap_run<float4>(s, f, broadcast) : swap_run<double4>(s, f, broadcast);
+    return swap_dispatch(s, f, broadcast, nullptr);
+}
+
+static double *mapped_host_alias(const void *host);
+
+// Same composite, but every rank's last kernel stores the FINISHED pixels of its strip into `image_host`: a
+// page-locked array mapped into every rank's process (yt_b200.parallel.shared_pinned_empty), holding the initial
+// colours on entry.  The image leaves the box over all the PCIe links at once; rank 0's stream completes last.
+extern "C" int ytb200_swap_composite_host(ytb200_swap *s, ytb200_frame *f, double *image_host)
+{
+    int rc = swap_check(s, f);
+    if (rc) return rc;
+    double *img = mapped_host_alias(image_host);
+    if (!img) return fail(E_ARG, "image_host is not page-locked and mapped in this process (ytb200_host_alloc / ytb200_host_register)");
+    DeviceGuard g(s->ctx->device);
+    const double *keep = f->c0_in;
+    f->c0_in = img;   // the initial colours are read in place
+    rc = swap_dispatch(s, f, 0, img);
+    f->c0_in = keep;
+    return rc;
 }
 
 extern "C" int ytb200_swap_error(ytb200_swap *s, int *error_out)
@@ -1311,9 +1412,9 @@ extern "C" int ytb200_swap_error(ytb200_swap *s, int *error_out)
     if (!s || !error_out) return fail(E_ARG, "NULL argument");
     DeviceGuard g(s->ctx->device);
     CK(cudaStreamSynchronize(s->ctx->stream));
-    CK(cudaMemcpy(error_out, swap_flag(s->slab, 56), sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(error_out, swap_flag(s->slab, SWAP_WORD_ERROR), sizeof(int), cudaMemcpyDeviceToHost));
     // reported once: a later frame that completes must not inherit this frame's failure
-    if (*error_out) CK(cudaMemset(swap_flag(s->slab, 56), 0, sizeof(unsigned long long)));
+    if (*error_out) CK(cudaMemset(swap_flag(s->slab, SWAP_WORD_ERROR), 0, sizeof(unsigned long long)));
     return 0;
 }
 
@@ -1385,5 +1486,18 @@ extern "C" int ytb200_host_alloc(int64_t bytes, void **out)
 extern "C" int ytb200_host_free(void *p)
 {
     if (p) CK(cudaFreeHost(p));
+    return 0;
+}
+
+extern "C" int ytb200_host_register(void *p, int64_t bytes)
+{
+    if (!p || bytes <= 0) return fail(E_ARG, "bad argument");
+    CK(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return 0;
+}
+
+extern "C" int ytb200_host_unregister(void *p)
+{
+    if (p) CK(cudaHostUnregister(p));
     return 0;
 }

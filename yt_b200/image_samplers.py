@@ -214,11 +214,15 @@ class ImageSampler:
         fr.download(self.aimage_host)
         self._pending, self._batches, self._dirty = [], [], False
 
-    def peer_swap(self, path, viewpoint, rank, world):
-        """The NVLink peer-memory compositor for this sampler's frame (fp32 partials for the FAST volume render)."""
+    def partial_format(self, n_fields=1):
+        """Format of this sampler's partial images (``ytb200_partial_format``)."""
+        from .parallel import partial_format
+        return partial_format(self.kind, self._tables, n_fields, self._precision)
+
+    def peer_swap(self, path, viewpoint, rank, world, n_fields=1):
+        """The NVLink peer-memory compositor for this sampler's frame, in the sampler's partial format."""
         from .parallel import PeerSwap
-        f32 = self.kind == L.VOLUME_RENDER and self._precision == L.PREC_FAST
-        return PeerSwap(self._ctx, self._frame, path, viewpoint, rank, world, f32=f32)
+        return PeerSwap(self._ctx, self._frame, path, viewpoint, rank, world, fmt=self.partial_format(n_fields))
 
     def flush_parallel(self, swap, broadcast=True):
         """Multi-GPU flush: cast this rank's bricks into an affine partial image, composite the partials
@@ -243,8 +247,7 @@ class ImageSampler:
         from .parallel import PeerSwap
         if isinstance(swap, PeerSwap):
             # NVLink peer-memory route: no collective, the swap rounds read the partners' HBM directly
-            fr.cast_partial(self.kind, bs, order, swap.partial_ptr, tf=self._tables, n_samples=self.n_samples,
-                            precision=self._precision, f32=swap.f32)
+            swap.cast(fr, self.kind, bs, order, tf=self._tables, n_samples=self.n_samples, precision=self._precision)
             swap.composite(fr, broadcast=broadcast)
             swap.check()
         else:

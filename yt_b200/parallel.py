@@ -221,24 +221,31 @@ class BinarySwap:
 
 class PeerSwap:
     """Binary swap over NVLink peer memory (``ytb200_swap_*``): the same schedule as :class:`BinarySwap`, but each
-    round is one CUDA kernel that reads the partner's half directly from its HBM, and the final strips are stored
-    straight into the destination ranks' slabs (then copied into the frame given to ``composite``).  The object is
-    independent of any one frame: create it once per (image size, world) and ``set_view`` it when the camera moves.  torch.distributed is used once, at construction, to pass the CUDA IPC
-    handles around; a frame issues no collective at all.
+    round is one CUDA kernel that waits for the partner's flag, reads the partner's half directly from its HBM and
+    signals the next reader, and the last round stores the composed strips straight into the destination ranks'
+    slabs.  Partials travel in the smallest exact format of the affine map (``partial_format``: 16 B per pixel for the
+    ColorTransferFunction render, 8 B per summed field for the projections).  The object is independent of any one
+    frame: create it once per (image size, world, format) and ``set_view`` it when the camera moves.
+    torch.distributed is used once, at construction, to pass the CUDA IPC handles around; a frame issues no collective.
 
-        swap = PeerSwap(ctx, frame, path, viewpoint, rank, world)
-        frame.cast_partial(kind, bricks, order, swap.partial_ptr, ..., f32=swap.f32)
+        swap = PeerSwap(ctx, frame, path, viewpoint, rank, world, fmt=partial_format(kind, tf, n_fields, precision))
+        swap.cast(frame, kind, bricks, order, tf=tf)
         swap.composite(frame)            # result in rank 0's frame image (every rank's with broadcast=True)
+        swap.composite_host(frame, img)  # or: every rank stores its strip into the shared page-locked `img`
     """
 
-    def __init__(self, ctx, frame, path, viewpoint, rank, world, f32=True, group=None):
+    def __init__(self, ctx, frame, path, viewpoint, rank, world, f32=True, group=None, fmt=None):
         import torch.distributed as dist
         from . import _lib as L
         lib = L.load()
-        self.ctx, self.rank, self.world, self.f32 = ctx, rank, world, bool(f32)
+        if fmt is None:
+            fmt = L.PARTIAL_AB32 if f32 else L.PARTIAL_AB64
+        self.ctx, self.rank, self.world, self.fmt = ctx, rank, world, int(fmt)
+        self.f32 = self.fmt in (L.PARTIAL_AB32, L.PARTIAL_A32, L.PARTIAL_A32G)
+        self.bytes_per_pixel = int(lib.ytb200_partial_bytes(self.fmt))
         self.npx = frame.nx * frame.ny
         h = C.c_void_p()
-        L.check(lib.ytb200_swap_create(ctx.handle, self.npx, rank, world, 32 if f32 else 64, C.byref(h)))
+        L.check(lib.ytb200_swap_create(ctx.handle, self.npx, rank, world, self.fmt, C.byref(h)))
         self.handle = h
         self._fin = weakref.finalize(self, lib.ytb200_swap_destroy, h)
         if world > 1:
@@ -250,7 +257,8 @@ class PeerSwap:
                 if r != rank:
                     L.check(lib.ytb200_swap_open(h, int(r), slab))
         self.set_view(path, viewpoint)
-        self.launches_per_composite = 3 * len(self.rounds) + 3
+        # launches of one frame's composite on rank 0: one per round + the apply kernel
+        self.launches_per_composite = len(self.rounds) + 1
 
     def set_view(self, path, viewpoint):
         """(Re)plan the rounds for a viewpoint: which side of every kd split is composited first."""
@@ -270,15 +278,26 @@ class PeerSwap:
                                           p1.ctypes.data_as(L.i64p), k0.ctypes.data_as(L.i64p), k1.ctypes.data_as(L.i64p),
                                           earlier.ctypes.data_as(L.i32p)))
 
-    @property
-    def partial_ptr(self):
-        """Device pointer the NEXT frame's partial cast must write to (alternates between two buffer sets)."""
+    def cast(self, frame, kind, bricks, order, tf=None, n_samples=10, precision=None, timed=False):
+        """This rank's partial cast of the next frame, straight into the slab (``ytb200_swap_cast``)."""
         from . import _lib as L
-        return int(L.load().ytb200_swap_partial(self.handle))
+        o = np.ascontiguousarray(order, dtype=np.int64)
+        st = L.Stats() if timed else None
+        L.check(L.load().ytb200_swap_cast(
+            self.handle, frame.handle, int(kind), bricks.handle, o.ctypes.data_as(L.i64p), int(o.shape[0]),
+            tf.handle if tf is not None else None, int(n_samples), int(L.PREC_FAST if precision is None else precision),
+            C.byref(st) if timed else None))
+        return st
 
     def composite(self, frame, broadcast=False):
         from . import _lib as L
         L.check(L.load().ytb200_swap_composite(self.handle, frame.handle, 1 if broadcast else 0))
+
+    def composite_host(self, frame, image):
+        """Every rank stores the finished pixels of its strip into `image`: the SAME page-locked array mapped into
+        every rank's process (:func:`shared_pinned_empty`), holding the initial colours on entry."""
+        from . import _lib as L
+        L.check(L.load().ytb200_swap_composite_host(self.handle, frame.handle, image.ctypes.data))
 
     def check(self):
         """Synchronise and raise if a peer failed to arrive (the device-side waits give up after 10 s)."""
@@ -289,7 +308,51 @@ class PeerSwap:
             raise RuntimeError("binary swap: a peer did not signal within 10 s")
 
 
-def make_compositor(ctx, frame, path, viewpoint, rank, world, f32=True, group=None, prefer=None):
+def partial_format(kind, tf, n_fields, precision=None):
+    """The partial-image format the cast of (sampler kind, transfer tables, fields, precision) produces."""
+    from . import _lib as L
+    f = L.load().ytb200_partial_format(int(kind), tf.handle if tf is not None else None, int(n_fields),
+                                       int(L.PREC_FAST if precision is None else precision))
+    if f < 0:
+        L.check(f)
+    return int(f)
+
+
+def shared_pinned_empty(shape, dtype=np.float64, rank=0, world=1, group=None, tag="img"):
+    """One host array shared by every rank of the job (POSIX shared memory created by rank 0), page-locked and mapped
+    into each rank's CUDA context (``ytb200_host_register``): the image every rank's last swap kernel stores its strip
+    into.  Collective.  The mapping lives as long as the returned array."""
+    import mmap
+    from . import _lib as L
+    lib = L.load()
+    dt = np.dtype(dtype)
+    nbytes = max(int(np.prod(shape)) * dt.itemsize, 1)
+    size = (nbytes + mmap.PAGESIZE - 1) // mmap.PAGESIZE * mmap.PAGESIZE
+    name = None
+    if world > 1:
+        import torch.distributed as dist
+        box = ["/dev/shm/ytb200_%s_%d_%d" % (tag, os.getpid(), id(shape) & 0xffff)] if rank == 0 else [None]
+        if rank == 0:
+            with open(box[0], "wb") as fh:
+                fh.truncate(size)
+        dist.broadcast_object_list(box, src=0, group=group)
+        name = box[0]
+        fh = open(name, "r+b")
+        mm = mmap.mmap(fh.fileno(), size)
+        fh.close()
+        dist.barrier(group=group)
+        if rank == 0:
+            os.unlink(name)      # the mappings keep the memory alive
+    else:
+        mm = mmap.mmap(-1, size)
+    arr = np.frombuffer(mm, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    addr = arr.ctypes.data
+    L.check(lib.ytb200_host_register(C.c_void_p(addr), size))
+    weakref.finalize(mm, lib.ytb200_host_unregister, C.c_void_p(addr))
+    return arr
+
+
+def make_compositor(ctx, frame, path, viewpoint, rank, world, f32=True, group=None, prefer=None, fmt=None):
     """The compositor every rank of the job agrees on: :class:`PeerSwap` when ALL ranks can map each other's slabs
     (one host, at most 8 GPUs, peer access between the devices, CUDA IPC working), :class:`BinarySwap` over NCCL
     send/recv otherwise -- for more than 8 ranks, several nodes, or devices without peer access.  ``prefer``
@@ -314,7 +377,7 @@ def make_compositor(ctx, frame, path, viewpoint, rank, world, f32=True, group=No
         dist.all_gather_object(flags, bool(can), group=group)
         if all(flags):
             try:
-                swap = PeerSwap(ctx, frame, path, viewpoint, rank, world, f32=f32, group=group)
+                swap = PeerSwap(ctx, frame, path, viewpoint, rank, world, f32=f32, group=group, fmt=fmt)
                 ok = 1
             except Exception as exc:  # noqa: BLE001  (cudaIpcOpenMemHandle refused, out of memory, ...)
                 import sys

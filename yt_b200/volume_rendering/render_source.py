@@ -272,12 +272,13 @@ class KDTreeVolumeSource(VolumeSource):
             # one compositor per (image size, partial type): a PeerSwap's IPC-shared slab outlives the per-render
             # samplers.  make_compositor falls back to the NCCL route for > 8 ranks, several hosts or no peer access.
             from ..parallel import PeerSwap, make_compositor
-            key = (nx, ny, self.sampler.kind, self.sampler._precision, self.volume.comm_size)
+            n_fields = len(self.volume.fields)
+            fmt = self.sampler.partial_format(n_fields)
+            key = (nx, ny, fmt, self.volume.comm_size)
             cache = self.__dict__.setdefault("_swaps", {})
             if key not in cache:
-                f32 = self.sampler.kind == _L.VOLUME_RENDER and self.sampler._precision == _L.PREC_FAST
                 cache[key] = make_compositor(self.sampler._ctx, self.sampler._frame, self.volume.kd_path(), camera.lens.viewpoint,
-                                             self.volume.comm_rank, self.volume.comm_size, f32=f32)[0]
+                                             self.volume.comm_rank, self.volume.comm_size, fmt=fmt)[0]
             swap = cache[key]
             if isinstance(swap, PeerSwap):
                 swap.set_view(self.volume.kd_path(), camera.lens.viewpoint)
