@@ -141,8 +141,7 @@ class AMRKDTree:
         self.ds = ds
         self.current_vcds = []
         self.current_saved_grids = []
-        self.bricks = []
-        self.brick_dimensions = []
+        self._bricks = None          # host PartitionedGrids of every leaf, built on first use
         self.sdx = ds.index.get_smallest_dx()
         self._initialized = False
         self._id_offset = getattr(ds.index.grids[0], "_id_offset", 0)
@@ -168,10 +167,21 @@ class AMRKDTree:
             self._brick_of_node, self._device_sets, self._leaf_slot = {}, {}, None
             self._set_meta, self._piece_plan = {}, {}
             self.current_vcds, self.current_saved_grids = [], []
-        self.brick_dimensions = []
-        self.bricks = np.array(list(self.traverse()), dtype=object)
-        self.brick_dimensions = np.array([b.dims for b in self.bricks])
+        # the reference builds every brick here (amr_kdtree.py:219-227).  The batched device path never reads the host
+        # bricks (each grid's cells are vertex-centred on the device), so they are built on first use: a 1024^3
+        # grid spent over a minute in the host's vertex centring before its first frame (profiles/r02h_bench_scene_before.json)
+        self._bricks = None
         self._initialized = True
+
+    @property
+    def bricks(self):
+        if self._bricks is None:
+            self._bricks = np.array(list(self.traverse()), dtype=object)
+        return self._bricks
+
+    @property
+    def brick_dimensions(self):
+        return np.array([b.dims for b in self.bricks])
 
     def initialize_source(self, fields, log_fields, no_ghost):
         if fields == self.fields and log_fields == self.log_fields and no_ghost == self.no_ghost:

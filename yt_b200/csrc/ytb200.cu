@@ -1149,6 +1149,12 @@ struct ytb200_swap {
     std::vector<SwapRound> rounds;
     unsigned long long seq = 0;              // frames cast so far
     unsigned long long composited = 0;       // frames composited so far
+    // host-image frames: this rank's strip of the initial colours is fetched on a side stream WHILE the cast runs
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_c0 = nullptr, ev_frame = nullptr;
+    double4 *c0_stage = nullptr;             // device copy of the strip
+    int64_t stage_cap = 0;
+    bool c0_staged = false;                  // the current frame's strip is (being) staged
 };
 
 static const size_t SWAP_HDR = 512;
@@ -1198,6 +1204,9 @@ extern "C" int ytb200_swap_create(ytb200_ctx *ctx, int64_t n_pixels, int rank, i
     CK(cudaStreamSynchronize(ctx->stream));
     s->peer_slab.assign((size_t)world, nullptr);
     s->peer_slab[(size_t)rank] = s->slab;
+    CK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&s->ev_c0, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s->ev_frame, cudaEventDisableTiming));
     *out = s;
     return 0;
 }
@@ -1214,6 +1223,10 @@ extern "C" int ytb200_swap_destroy(ytb200_swap *s)
         if (s->peer_slab[(size_t)w]) cudaIpcCloseMemHandle(s->peer_slab[(size_t)w]);
     }
     cudaFree(s->slab);
+    if (s->side) { cudaStreamSynchronize(s->side); cudaStreamDestroy(s->side); }
+    if (s->ev_c0) cudaEventDestroy(s->ev_c0);
+    if (s->ev_frame) cudaEventDestroy(s->ev_frame);
+    cudaFree(s->c0_stage);
     delete s;
     return 0;
 }
@@ -1282,6 +1295,27 @@ extern "C" int ytb200_swap_cast(ytb200_swap *s, ytb200_frame *f, int kind, const
     for (int j = 0; j < s->k; j++)
         if (!s->peer_slab[(size_t)s->rounds[(size_t)j].partner]) return fail(E_STATE, "peer %d not opened", s->rounds[(size_t)j].partner);
     const unsigned long long seq = s->seq + 1;
+    s->c0_staged = false;
+    if (f->c0_in && s->k > 0) {
+        // the initial colours of this rank's final strip, read over PCIe on the side stream while the cast runs
+        // (after the previous frame's stores into the same host image have completed)
+        DeviceGuard g(s->ctx->device);
+        const SwapRound &lr = s->rounds[(size_t)s->k - 1];
+        const int64_t n = lr.k1 - lr.k0;
+        if (n > s->stage_cap) {
+            CK(cudaStreamSynchronize(s->side));
+            cudaFree(s->c0_stage); s->c0_stage = nullptr; s->stage_cap = 0;
+            CK(cudaMalloc(&s->c0_stage, (size_t)n * sizeof(double4)));
+            s->stage_cap = n;
+        }
+        if (n > 0) {
+            CK(cudaEventRecord(s->ev_frame, s->ctx->stream));
+            CK(cudaStreamWaitEvent(s->side, s->ev_frame, 0));
+            CK(cudaMemcpyAsync(s->c0_stage, reinterpret_cast<const double4 *>(f->c0_in) + lr.k0, (size_t)n * sizeof(double4), cudaMemcpyDefault, s->side));
+            CK(cudaEventRecord(s->ev_c0, s->side));
+            s->c0_staged = true;
+        }
+    }
     unsigned char *buf0 = s->slab + SWAP_HDR + (size_t)(seq & 1) * s->set_bytes + s->buf_off[0];
     unsigned long long *flag = s->k > 0 ? swap_flag(s->peer_slab[(size_t)s->rounds[0].partner], 0) : nullptr;
     int rc = cast_common(f, kind, set, order, n_order, tf, n_samples, precision, reinterpret_cast<double *>(buf0), stats, s->fmt,
@@ -1325,6 +1359,10 @@ static int swap_run(ytb200_swap *s, ytb200_frame *f, int broadcast, double *host
         } else if (host_image) {
             // finished fp64 pixels of this rank's strip, straight into the caller's page-locked image over this GPU's PCIe link
             a.c0 = c0 + f0; a.image = reinterpret_cast<double4 *>(host_image) + f0;
+            if (s->c0_staged && c0 == reinterpret_cast<const double4 *>(host_image)) {
+                CK(cudaStreamWaitEvent(st, s->ev_c0, 0));
+                a.c0 = s->c0_stage;
+            }
             a.done.n = 1; a.done.flag[0] = swap_flag(s->peer_slab[0], SWAP_FLAG_FINAL + s->rank);
             swap_round_kernel<FMT, true><<<blocks(a.n), 256, 0, st>>>(a);
         } else {

@@ -280,14 +280,41 @@ class Frame:
         return L.load().ytb200_frame_device_image(self.handle)
 
 
+_pinned_pool = {}       # nbytes -> [address, ...] of page-locked buffers whose arrays have been collected
+_PINNED_POOL_MAX = 4    # buffers kept per size
+
+
+def _pinned_release(nbytes, addr):
+    free = _pinned_pool.setdefault(nbytes, [])
+    if len(free) < _PINNED_POOL_MAX:
+        free.append(addr)
+    else:
+        L.load().ytb200_host_free(C.c_void_p(addr))
+
+
 def pinned_empty(shape, dtype=np.float64):
-    """numpy array over cudaHostAlloc'd memory (freed when the array's base is collected)."""
+    """numpy array over cudaHostAlloc'd memory.  When the array (and every view of it) is collected the buffer goes to
+    a small per-size pool instead of back to the driver: page-locking 134 MB costs tens of milliseconds, and a render
+    loop asks for the same image and z-buffer sizes every frame."""
     lib = L.load()
     dt = np.dtype(dtype)
-    n = int(np.prod(shape)) * dt.itemsize
-    p = C.c_void_p()
-    L.check(lib.ytb200_host_alloc(max(n, 1), C.byref(p)))
-    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    n = max(int(np.prod(shape)) * dt.itemsize, 1)
+    free = _pinned_pool.setdefault(n, [])
+    if not free:
+        # page-locking is slow (~1.5 ms per MB): take image-sized buffers three at a time, so that a render loop whose
+        # caller still holds the previous frame or two never waits for the driver again
+        for _ in range(3 if n >= (8 << 20) else 1):
+            p = C.c_void_p()
+            L.check(lib.ytb200_host_alloc(n, C.byref(p)))
+            free.append(p.value)
+    addr = free.pop()
+    buf = (C.c_char * n).from_address(addr)
     arr = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
-    weakref.finalize(buf, lib.ytb200_host_free, C.c_void_p(p.value))
+    weakref.finalize(buf, _pinned_release, n, addr)
     return arr
+
+
+def pinned_full(shape, value, dtype=np.float64):
+    a = pinned_empty(shape, dtype)
+    a[...] = value
+    return a

@@ -167,8 +167,10 @@ class AllData:
         key = self.ds._resolve(field)
         lo, hi = np.inf, -np.inf
         for g, mask in self.blocks:
-            v = g.fields[key][mask]
-            if non_zero:
+            v = g.fields[key]
+            if not mask.all():
+                v = v[mask]
+            if non_zero and v.size and not (v.min() > 0):   # (one pass when everything is positive, the usual case)
                 v = v[v > 0]
             if v.size:
                 lo, hi = min(lo, v.min()), max(hi, v.max())

@@ -48,11 +48,17 @@ class _OctreeRayTracing:
     def node_count(self):
         return int(L.load().ytb200_octree_node_count(self.handle))
 
-    def set_cells(self, cells):
-        """Upload the (n_cells, 14) payload of OctreeVolumeSource.render's PartitionedGrid.  Every call uploads: the
-        reference reads the host array at each cast, so in-place edits between casts must be seen."""
+    def set_cells(self, cells, token=None):
+        """Upload the (n_cells, 14) payload of OctreeVolumeSource.render's PartitionedGrid.  A bare call uploads every
+        time: the reference reads the host array at each cast, so in-place edits between casts must be seen.  A caller
+        that OWNS the array and knows it unchanged (the scene's octree source, which assembles it from the volume's
+        field data) passes a `token`: while the token is the one of the last upload the cells stay resident (75 MB per
+        frame for a 675 k-cell tree: r01 e2e 29 ms against a 12.5 ms kernel)."""
+        if token is not None and token == getattr(self, "_cells_token", None):
+            return
         flat = np.ascontiguousarray(cells, dtype=np.float64).reshape(-1, 14)
         L.check(L.load().ytb200_octree_set_cells(self.handle, flat.shape[0], flat.ctypes.data_as(L.dp)))
+        self._cells_token = token
 
 
 class OctreeRayTracing:

@@ -9,6 +9,17 @@ generate per-pixel ray arrays, which the samplers' GENERIC lens mode casts like 
 import numpy as np
 
 
+def _image_zeros(shape):
+    """A zeroed fp64 image.  Page-locked when the CUDA library is there: the cast then reads the initial colours and
+    writes the result in place over PCIe (``ytb200_render``) instead of through two staged copies -- this is an
+    allocation choice, not a compute path; pure host uses of the lens mirror get an ordinary array."""
+    try:
+        from ..device import pinned_full
+        return pinned_full(shape, 0.0)
+    except Exception:   # noqa: BLE001  (library not built / no device: host-only use of the mirror)
+        return np.zeros(shape, dtype="float64", order="C")
+
+
 class Lens:
     lens_type = None
 
@@ -28,7 +39,7 @@ class Lens:
 
     def new_image(self, camera):
         """Fresh fp64 C-order (nx, ny, 4) image (lens.py:33-43)."""
-        self.current_image = np.zeros((camera.resolution[0], camera.resolution[1], 4), dtype="float64", order="C")
+        self.current_image = _image_zeros((camera.resolution[0], camera.resolution[1], 4))
         return self.current_image
 
     def setup_box_properties(self, camera):
@@ -273,7 +284,7 @@ class FisheyeLens(Lens):
         self.set_viewpoint(camera)
 
     def new_image(self, camera):
-        self.current_image = np.zeros((camera.resolution[0], camera.resolution[0], 4), dtype="float64", order="C")
+        self.current_image = _image_zeros((camera.resolution[0], camera.resolution[0], 4))
         return self.current_image
 
     def _get_sampler_params(self, camera, render_source):

@@ -347,14 +347,21 @@ class OctreeVolumeSource(VolumeSource):
         self.set_sampler(camera)
         if self.sampler is None:
             raise RuntimeError("No sampler set. This is likely a bug as it should never happen.")
-        data = self.data_source
-        dx = data["dx"][:, None]
-        xyz = np.stack([data[k] for k in "xyz"], axis=-1)
-        LE, RE = xyz - dx / 2, xyz + dx / 2
-        dt = np.stack(list(self.volume.data) + [*LE.T, *RE.T], axis=-1).reshape(1, len(dx), 14, 1)
-        mask = np.full(dt.shape[1:], 1, dtype=np.uint8)
-        dims = np.array([1, 1, 1], dtype="int64")
-        pg = PartitionedGrid(0, dt, mask, LE.flatten(), RE.flatten(), dims, n_fields=1)
+        # the 14 doubles per cell depend only on the volume's field data and the cell geometry: assemble (and upload)
+        # them once per set_fields, not once per frame
+        token = (id(self.volume.data), id(self.volume.octree))
+        if getattr(self, "_cells_pg", None) is None or self._cells_pg[0] != token:
+            data = self.data_source
+            dx = data["dx"][:, None]
+            xyz = np.stack([data[k] for k in "xyz"], axis=-1)
+            LE, RE = xyz - dx / 2, xyz + dx / 2
+            dt = np.stack(list(self.volume.data) + [*LE.T, *RE.T], axis=-1).reshape(1, len(dx), 14, 1)
+            mask = np.full(dt.shape[1:], 1, dtype=np.uint8)
+            dims = np.array([1, 1, 1], dtype="int64")
+            pg = PartitionedGrid(0, dt, mask, LE.flatten(), RE.flatten(), dims, n_fields=1)
+            pg._resident_token = token
+            self._cells_pg = (token, pg, self.volume.data)   # keeps volume.data alive: its id stays unique
+        pg = self._cells_pg[1]
         self.sampler(pg, oct=self.volume.octree)
         self.current_image = self.finalize_image(camera, self.sampler.aimage)
         if zbuffer is None:

@@ -88,7 +88,8 @@ class Scene:
         next one (scene.py:611-622).  The image is rotated by 180 degrees to agree with a PlotWindow plot."""
         camera = self.camera if camera is None else camera
         canvas = camera.lens.new_image(camera)
-        depth = ZBuffer(canvas, np.full(canvas.shape[:2], np.inf))
+        from .utils import _filled
+        depth = ZBuffer(canvas, _filled(canvas.shape[:2], np.inf))
         image = canvas
         for _, source in self.opaque_sources:
             source.render(camera, zbuffer=depth)

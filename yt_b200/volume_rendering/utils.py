@@ -37,10 +37,24 @@ def _common_args(params, render_source):
             np.array(params["width"], dtype="float64"), render_source.volume_method]
 
 
+def _filled(shape, value):
+    """A constant fp64 array, page-locked when the CUDA library is there (see lens._image_zeros)."""
+    try:
+        from ..device import pinned_full
+        return pinned_full(shape, value)
+    except Exception:   # noqa: BLE001
+        return np.full(shape, value, dtype="float64")
+
+
+def _ones(shape):
+    """The default z-buffer (image_samplers.pyx:78-80)."""
+    return _filled(shape, 1.0)
+
+
 def _zbuffer_kwarg(params, render_source):
     if render_source.zbuffer is not None:
         return render_source.zbuffer.z
-    return np.ones(params["image"].shape[:2], "float64")
+    return _ones(params["image"].shape[:2])
 
 
 def new_volume_render_sampler(camera, render_source):
@@ -53,7 +67,7 @@ def new_volume_render_sampler(camera, render_source):
         kwargs["zbuffer"] = render_source.zbuffer.z
         args[4][:] = np.reshape(render_source.zbuffer.rgba[:], (camera.resolution[0], camera.resolution[1], 4))
     else:
-        kwargs["zbuffer"] = np.ones(params["image"].shape[:2], "float64")
+        kwargs["zbuffer"] = _ones(params["image"].shape[:2])
     return VolumeRenderSampler(*args, **kwargs)
 
 
