@@ -124,6 +124,14 @@ int ytb200_brick_from_cells(ytb200_brickset *set, int64_t index, const int64_t g
                             const int64_t hi[3], const double left_edge[3], const double right_edge[3],
                             const void *const *cells_dev, int cells_are_f32, const int32_t *log_fields,
                             const uint8_t *mask_host, ytb200_stats *stats);
+/* The ghost-zone flavour (grid.get_vertex_centered_data(no_ghost=False), grid_patch.py:298-310): cells_dev[f] hold the
+ * grid PADDED with one layer of ghost zones, shape grid_dims + 2 (the smoothed covering grid of retrieve_ghost_zones,
+ * assembled by yt_b200.loaders.smoothed_covering_grid), and every vertex is 0.125 times the sum of its 8 cells in the
+ * reference's order -- bit-identical in fp64.  Otherwise as ytb200_brick_from_cells. */
+int ytb200_brick_from_ghost_cells(ytb200_brickset *set, int64_t index, const int64_t grid_dims[3], const int64_t lo[3],
+                                  const int64_t hi[3], const double left_edge[3], const double right_edge[3],
+                                  const void *const *cells_dev, int cells_are_f32, const int32_t *log_fields,
+                                  const uint8_t *mask_host, ytb200_stats *stats);
 /* Must be called after the last upload/attach and before the first cast (uploads the brick table). */
 int ytb200_bricks_commit(ytb200_brickset *set);
 int ytb200_bricks_destroy(ytb200_brickset *set);

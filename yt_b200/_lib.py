@@ -61,6 +61,8 @@ SIGNATURES = {
     "ytb200_cells_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ytb200_brick_from_cells": (C.c_int, [C.c_void_p, C.c_int64, i64p, i64p, i64p, dp, dp, C.POINTER(C.c_void_p), C.c_int,
                                           i32p, u8p, C.POINTER(Stats)]),
+    "ytb200_brick_from_ghost_cells": (C.c_int, [C.c_void_p, C.c_int64, i64p, i64p, i64p, dp, dp, C.POINTER(C.c_void_p), C.c_int,
+                                                i32p, u8p, C.POINTER(Stats)]),
     "ytb200_brick_attach_pitched": (C.c_int, [C.c_void_p, C.c_int64, i64p, dp, dp, C.POINTER(C.c_void_p), C.c_void_p, C.c_int64]),
     "ytb200_brick_pitch": (C.c_int, [C.c_void_p, C.c_int64, i64p, i64p]),
     "ytb200_bricks_commit": (C.c_int, [C.c_void_p]),

@@ -236,7 +236,7 @@ class AMRKDTree:
         each grid's cell-centred fields go to the device once and every leaf is vertex-centred, log10'd,
         sliced and converted by ``ytb200_brick_from_cells`` (get_brick_data's arithmetic, amr_kdtree.py:343-365)."""
         if centre_on_device is None:
-            centre_on_device = bool(self.no_ghost)
+            centre_on_device = True
         key = (ctx.device, storage, bool(centre_on_device))
         if key not in self._device_sets:
             leaves = [int(i) for i in self.tree.traverse()]
@@ -257,8 +257,17 @@ class AMRKDTree:
     def _device_bricks_from_cells(self, leaves, ctx, storage):
         from . import _lib as L
         from . import device as D
-        if not self.no_ghost:
-            raise NotImplementedError("ghost-zone vertex centring is not on the device path")
+        ghost = not self.no_ghost
+
+        def grid_cells(grid):
+            """The grid's fields on the device: its cells (no ghost), or the cells padded with one layer of ghost zones
+            (the smoothed covering grid of grid_patch.py:298, assembled on the host: it gathers from other grids)."""
+            if ghost:
+                cg = grid.retrieve_ghost_zones(1, self.fields, smoothed=True)
+                return [D.DeviceCells(ctx, cg[f]) for f in self.fields]
+            if np.any(np.asarray(grid.ActiveDimensions) < 2):
+                raise NotImplementedError("no-ghost vertex centring needs >= 2 cells per grid axis")
+            return [D.DeviceCells(ctx, grid[f]) for f in self.fields]
         nd = self.tree.nodes
         # leaves too large for 32-bit offsets become several device bricks (pieces of ONE reference brick)
         plans, n_slots = [], 0
@@ -284,7 +293,7 @@ class AMRKDTree:
         for node, grid, tree, pieces, first in plans:
             if len(pieces) > 1:
                 if grid.id not in cells_of_grid:
-                    cells_of_grid[grid.id] = [D.DeviceCells(ctx, grid[f]) for f in self.fields]
+                    cells_of_grid[grid.id] = grid_cells(grid)
                 for k, (_, plo, phi) in enumerate(pieces):
                     ple = grid.LeftEdge + np.array(plo) * grid.dds
                     pre = grid.LeftEdge + np.array(phi) * grid.dds
@@ -293,14 +302,12 @@ class AMRKDTree:
                         mask, _ = self.data_source.selector.fill_mask_regular_grid(grid)
                         mask = mask[plo[0]:phi[0], plo[1]:phi[1], plo[2]:phi[2]].astype("uint8")
                     out.from_cells(first + k, [c.ptr for c in cells_of_grid[grid.id]], grid.ActiveDimensions, plo, phi, ple, pre,
-                                   log_fields=self.log_fields, mask=mask)
+                                   log_fields=self.log_fields, mask=mask, ghost=ghost)
         for node, grid, tree, pieces, slot in plans:
             if len(pieces) > 1:
                 continue
             if grid.id not in cells_of_grid:
-                if np.any(np.asarray(grid.ActiveDimensions) < 2):
-                    raise NotImplementedError("no-ghost vertex centring needs >= 2 cells per grid axis")
-                cells_of_grid[grid.id] = [D.DeviceCells(ctx, grid[f]) for f in self.fields]
+                cells_of_grid[grid.id] = grid_cells(grid)
             cells = cells_of_grid[grid.id]
             dds, gle = grid.dds, grid.LeftEdge
             nle, nre = nd["left_edge"][node].copy(), nd["right_edge"][node].copy()
@@ -311,7 +318,7 @@ class AMRKDTree:
                 mask, _ = self.data_source.selector.fill_mask_regular_grid(grid)
                 mask = mask[li[0]:ri[0], li[1]:ri[1], li[2]:ri[2]].astype("uint8")
             out.from_cells(slot, [c.ptr for c in cells], grid.ActiveDimensions, li, ri, nle, nre,
-                           log_fields=self.log_fields, mask=mask)
+                           log_fields=self.log_fields, mask=mask, ghost=ghost)
         ctx.synchronize()   # the cell arrays may be released once every leaf has been centred
         return out.commit()
 

@@ -1232,6 +1232,47 @@ __global__ void __launch_bounds__(VC_THREADS) vertex_centre_kernel(const TIN *__
     }
 }
 
+// Ghost-zone vertex centring (grid_patch.py:298-310): `cells` is the grid padded with one layer of ghost zones --
+// (nx+2, ny+2, nz+2), built on the host by the smoothed covering grid (yt_b200/loaders.py) -- and every vertex is
+// 0.125 * the sum of its 8 cells, added in the reference's order c111, c011, c101, c110, c010, c100, c001, c000
+// (first index x) with non-contracting fp64 adds, so that fp64 storage is bit-identical.  Same marching scheme,
+// fused log10 / slice / storage conversion as vertex_centre_kernel.
+template <typename TIN, typename TOUT>
+__global__ void __launch_bounds__(VC_THREADS) vertex_centre_ghost_kernel(const TIN *__restrict__ cells, TOUT *__restrict__ out,
+                                                                          int nx, int ny, int nz, int lo0, int lo1, int lo2,
+                                                                          int m0, int m1, int m2, int take_log, int out_px, int out_py)
+{
+    const int oz = blockIdx.x * VC_THREADS + threadIdx.x;
+    const int oy = blockIdx.y;
+    if (oz >= m2) return;
+    const int gz = lo2 + oz, gy = lo1 + oy;
+    const int ox0 = blockIdx.z * VC_XCHUNK, ox1 = min(m0, ox0 + VC_XCHUNK);
+    const size_t sy = (size_t)nz + 2, sx = ((size_t)ny + 2) * sy;
+    (void)nx;
+    const TIN *col = cells + (size_t)gy * sy + (size_t)gz;     // padded cell (x = 0, gy, gz): the vertex's low corner
+    TOUT *dst = out + (size_t)ox0 * out_px + (size_t)oy * out_py + oz;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    int gx = lo0 + ox0;
+    const TIN *p = col + (size_t)gx * sx;
+    double c000 = (double)__ldg(p), c001 = (double)__ldg(p + 1), c010 = (double)__ldg(p + sy), c011 = (double)__ldg(p + sy + 1);
+    for (int ox = ox0; ox < ox1; ox++, gx++, dst += (size_t)out_px) {
+        const TIN *q = col + (size_t)(gx + 1) * sx;
+        const double c100 = (double)__ldg(q), c101 = (double)__ldg(q + 1), c110 = (double)__ldg(q + sy), c111 = (double)__ldg(q + sy + 1);
+        double v = dadd(0.0, c111);
+        v = dadd(v, c011);
+        v = dadd(v, c101);
+        v = dadd(v, c110);
+        v = dadd(v, c010);
+        v = dadd(v, c100);
+        v = dadd(v, c001);
+        v = dadd(v, c000);
+        v = dmul(v, 0.125);
+        if (take_log) v = (v <= 0.0) ? qnan : log10(v);
+        *dst = (TOUT)v;
+        c000 = c100; c001 = c101; c010 = c110; c011 = c111;
+    }
+}
+
 // ---- binary-swap compositing over NVLink peer memory -----------------------------------
 // One swap round = ONE kernel: it waits (every CTA spins on a flag word in this rank's own memory) until the partner has
 // finished the buffer it is about to read, composes this rank's kept half with the partner's copy of the same pixels --

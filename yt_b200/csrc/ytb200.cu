@@ -310,17 +310,17 @@ extern "C" int ytb200_cells_free(ytb200_ctx *ctx, void *cells_dev)
     return 0;
 }
 
-extern "C" int ytb200_brick_from_cells(ytb200_brickset *s, int64_t index, const int64_t grid_dims[3], const int64_t lo[3],
-                                       const int64_t hi[3], const double le[3], const double re[3],
-                                       const void *const *cells_dev, int cells_are_f32, const int32_t *log_fields,
-                                       const uint8_t *mask_host, ytb200_stats *stats)
+static int brick_from_cells(ytb200_brickset *s, int64_t index, const int64_t grid_dims[3], const int64_t lo[3],
+                            const int64_t hi[3], const double le[3], const double re[3],
+                            const void *const *cells_dev, int cells_are_f32, const int32_t *log_fields,
+                            const uint8_t *mask_host, ytb200_stats *stats, bool ghost)
 {
     if (!s || !grid_dims || !lo || !hi || !le || !re || !cells_dev) return fail(E_ARG, "NULL argument");
     if (s->centring != YTB200_VERTEX_CENTRED) return fail(E_ARG, "vertex centring needs a VERTEX_CENTRED brick set");
     int64_t dims[3];
     for (int i = 0; i < 3; i++) {
         // ghost_zone_interpolate divides by (shape - 1): a one-cell axis is NaN in the reference
-        if (grid_dims[i] < 2 || grid_dims[i] > 0x7ffffff0) return fail(E_UNSUPPORTED, "grid_dims[%d]=%lld: no-ghost vertex centring needs >= 2 cells per axis", i, (long long)grid_dims[i]);
+        if ((!ghost && grid_dims[i] < 2) || grid_dims[i] < 1 || grid_dims[i] > 0x7ffffff0) return fail(E_UNSUPPORTED, "grid_dims[%d]=%lld: no-ghost vertex centring needs >= 2 cells per axis", i, (long long)grid_dims[i]);
         if (lo[i] < 0 || hi[i] <= lo[i] || hi[i] > grid_dims[i]) return fail(E_ARG, "bad vertex range [%lld, %lld] on axis %d", (long long)lo[i], (long long)hi[i], i);
         dims[i] = hi[i] - lo[i];
     }
@@ -349,13 +349,15 @@ extern "C" int ytb200_brick_from_cells(ytb200_brickset *s, int64_t index, const 
         s->bytes += (int64_t)(nelem * (f64 ? 8 : 4));
         const int nx = (int)grid_dims[0], ny = (int)grid_dims[1], nz = (int)grid_dims[2];
         const int l0 = (int)lo[0], l1 = (int)lo[1], l2 = (int)lo[2];
-        if (cells_are_f32) {
-            if (f64) vertex_centre_kernel<float, double><<<grid, VC_THREADS, 0, st>>>((const float *)cells_dev[f], (double *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg, opx, opy);
-            else vertex_centre_kernel<float, float><<<grid, VC_THREADS, 0, st>>>((const float *)cells_dev[f], (float *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg, opx, opy);
+#define YTB_VC_LAUNCH(K, TI, TO) K<TI, TO><<<grid, VC_THREADS, 0, st>>>((const TI *)cells_dev[f], (TO *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg, opx, opy)
+        if (ghost) {
+            if (cells_are_f32) { if (f64) YTB_VC_LAUNCH(vertex_centre_ghost_kernel, float, double); else YTB_VC_LAUNCH(vertex_centre_ghost_kernel, float, float); }
+            else               { if (f64) YTB_VC_LAUNCH(vertex_centre_ghost_kernel, double, double); else YTB_VC_LAUNCH(vertex_centre_ghost_kernel, double, float); }
         } else {
-            if (f64) vertex_centre_kernel<double, double><<<grid, VC_THREADS, 0, st>>>((const double *)cells_dev[f], (double *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg, opx, opy);
-            else vertex_centre_kernel<double, float><<<grid, VC_THREADS, 0, st>>>((const double *)cells_dev[f], (float *)dst, nx, ny, nz, l0, l1, l2, m0, m1, m2, lg, opx, opy);
+            if (cells_are_f32) { if (f64) YTB_VC_LAUNCH(vertex_centre_kernel, float, double); else YTB_VC_LAUNCH(vertex_centre_kernel, float, float); }
+            else               { if (f64) YTB_VC_LAUNCH(vertex_centre_kernel, double, double); else YTB_VC_LAUNCH(vertex_centre_kernel, double, float); }
         }
+#undef YTB_VC_LAUNCH
         CK(cudaGetLastError());
         b.data[f] = dst;
     }
@@ -382,6 +384,22 @@ extern "C" int ytb200_brick_from_cells(ytb200_brickset *s, int64_t index, const 
         }
     }
     return 0;
+}
+
+extern "C" int ytb200_brick_from_cells(ytb200_brickset *s, int64_t index, const int64_t grid_dims[3], const int64_t lo[3],
+                                       const int64_t hi[3], const double le[3], const double re[3],
+                                       const void *const *cells_dev, int cells_are_f32, const int32_t *log_fields,
+                                       const uint8_t *mask_host, ytb200_stats *stats)
+{
+    return brick_from_cells(s, index, grid_dims, lo, hi, le, re, cells_dev, cells_are_f32, log_fields, mask_host, stats, false);
+}
+
+extern "C" int ytb200_brick_from_ghost_cells(ytb200_brickset *s, int64_t index, const int64_t grid_dims[3], const int64_t lo[3],
+                                             const int64_t hi[3], const double le[3], const double re[3],
+                                             const void *const *cells_dev, int cells_are_f32, const int32_t *log_fields,
+                                             const uint8_t *mask_host, ytb200_stats *stats)
+{
+    return brick_from_cells(s, index, grid_dims, lo, hi, le, re, cells_dev, cells_are_f32, log_fields, mask_host, stats, true);
 }
 
 extern "C" int ytb200_brick_attach(ytb200_brickset *s, int64_t index, const int64_t dims[3], const double le[3],

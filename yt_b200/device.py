@@ -113,10 +113,11 @@ class BrickSet:
             m.ctypes.data_as(L.u8p) if m is not None else None))
 
     def from_cells(self, index, cells_ptrs, grid_dims, lo, hi, left_edge, right_edge, log_fields=None, mask=None,
-                   cells_are_f32=False, keep=None, timed=False):
+                   cells_are_f32=False, keep=None, timed=False, ghost=False):
         """Brick `index` := vertices lo..hi (inclusive) of the grid whose cell-centred fields live at the device
         pointers `cells_ptrs`: no-ghost vertex centring + log10 + slice + storage conversion in one kernel
-        (grid_patch.py:284-296, amr_kdtree.py:343-365)."""
+        (grid_patch.py:284-296, amr_kdtree.py:343-365).  ``ghost``: `cells_ptrs` hold the grid padded with one layer of
+        ghost zones (shape grid_dims + 2) and vertices are 8-cell means (grid_patch.py:298-310)."""
         gd = np.ascontiguousarray(grid_dims, dtype=np.int64)
         lo = np.ascontiguousarray(lo, dtype=np.int64)
         hi = np.ascontiguousarray(hi, dtype=np.int64)
@@ -131,7 +132,8 @@ class BrickSet:
                 raise ValueError(f"mask has shape {m.shape}, expected {tuple(int(h - l) for l, h in zip(lo, hi))}")
         le, re = _f64(left_edge), _f64(right_edge)
         st = L.Stats() if timed else None
-        L.check(L.load().ytb200_brick_from_cells(
+        fn = L.load().ytb200_brick_from_ghost_cells if ghost else L.load().ytb200_brick_from_cells
+        L.check(fn(
             self.handle, int(index), gd.ctypes.data_as(L.i64p), lo.ctypes.data_as(L.i64p), hi.ctypes.data_as(L.i64p),
             _dptr(le), _dptr(re), ptrs, 1 if cells_are_f32 else 0, lg.ctypes.data_as(L.i32p) if lg is not None else None,
             m.ctypes.data_as(L.u8p) if m is not None else None, C.byref(st) if timed else None))

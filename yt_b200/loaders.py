@@ -1,9 +1,11 @@
 """In-memory ("stream") grid datasets: ``load_uniform_grid`` / ``load_amr_grids``.
 
 Only what feeds the ray caster is restated from the reference: the grid hierarchy
-(yt/loaders.py:204-448 uniform, 450-688 AMR; yt/frontends/stream), the no-ghost vertex
-centring that turns cell data into brick data (grid_patch.py:270-296 ->
-interpolators.pyx:177-227) and the child mask used by the off-axis projection loop
+(yt/loaders.py:204-448 uniform, 450-688 AMR; yt/frontends/stream), the vertex centring that
+turns cell data into brick data -- no-ghost (grid_patch.py:270-296 -> interpolators.pyx:177-227)
+and with ghost zones (grid_patch.py:239-268, 298-310 on top of the smoothed covering grid,
+construction_data_containers.py:1398-1653 + misc_utilities.pyx:707-789) -- and the child mask
+used by the off-axis projection loop
 (off_axis_projection.py:506-515).  Everything is in ``code_length``; there is no unit system.
 """
 import numpy as np
@@ -76,6 +78,142 @@ def vertex_centre_no_ghost(cells):
     return ghost_zone_interpolate(1, c, [0.5] * 3, [n + 1 for n in c.shape], [0.0] * 3)
 
 
+def vertex_centre_from_ghost(src):
+    """grid_patch.py:298-310: with `src` the cells padded by one ghost layer, each vertex is 0.125 times the sum of its
+    8 surrounding cells, added in this order (fp64, so the order is part of the result)."""
+    src = np.asarray(src, dtype="float64")
+    dest = np.zeros(tuple(n - 1 for n in src.shape), dtype="float64")
+    np.add(dest, src[1:, 1:, 1:], dest)
+    np.add(dest, src[:-1, 1:, 1:], dest)
+    np.add(dest, src[1:, :-1, 1:], dest)
+    np.add(dest, src[1:, 1:, :-1], dest)
+    np.add(dest, src[:-1, 1:, :-1], dest)
+    np.add(dest, src[1:, :-1, :-1], dest)
+    np.add(dest, src[:-1, :-1, 1:], dest)
+    np.add(dest, src[:-1, :-1, :-1], dest)
+    np.multiply(dest, 0.125, dest)
+    return dest
+
+
+def fill_region(ds, key, level, left_index, dims):
+    """What misc_utilities.pyx:710-789 leaves in a zeroed (dims) box whose first cell has index `left_index` at `level`,
+    fed every cell of the level-`level` grids (a data source with min_level = max_level = level selects a grid's
+    cells whether or not finer grids cover them): each cell lands at its own index, and at its periodic images when
+    the box pokes out of the domain (the reference wraps whenever the box does; a non-periodic axis simply has no
+    cells selected beyond the domain, so its ghost cells stay zero)."""
+    out = np.zeros(tuple(int(d) for d in dims), dtype="float64")
+    rf = int(ds.refine_by) ** int(level)
+    level_dims = ds.domain_dimensions.astype("int64") * rf
+    left_index = np.asarray(left_index, dtype="int64")
+    dims = np.asarray(dims, dtype="int64")
+    shifts = []
+    for a in range(3):
+        sh = [0]
+        if ds.periodicity[a]:
+            if left_index[a] < 0:
+                sh.append(-1)          # cells near the upper domain face also appear below the lower one
+            if left_index[a] + dims[a] >= level_dims[a]:
+                sh.append(1)
+        shifts.append(sh)
+    for g in ds.index.grids:
+        if g.Level != level:
+            continue
+        gs = g.get_global_startindex()
+        ge = gs + g.ActiveDimensions
+        v = g.fields[key]
+        for sx in shifts[0]:
+            for sy in shifts[1]:
+                for sz in shifts[2]:
+                    off = np.array([sx, sy, sz], dtype="int64") * level_dims
+                    lo = np.maximum(gs + off, left_index)
+                    hi = np.minimum(ge + off, left_index + dims)
+                    if np.any(hi <= lo):
+                        continue
+                    a0, a1 = lo - left_index, hi - left_index
+                    b0, b1 = lo - off - gs, hi - off - gs
+                    out[a0[0]:a1[0], a0[1]:a1[1], a0[2]:a1[2]] = v[b0[0]:b1[0], b0[1]:b1[1], b0[2]:b1[2]]
+    return out
+
+
+def _finest_uncovered_level(ds, level, lo, hi):
+    """Coarsest level among the cells a region of level-`level` cells [lo, hi) selects when levels 0..level are allowed:
+    cells of coarser grids count only where no finer grid covers them (construction_data_containers.py:1460-1492)."""
+    out = level
+    for g in ds.index.grids:
+        if g.Level >= out:
+            continue
+        r = int(ds.refine_by) ** (level - g.Level)
+        gs = g.get_global_startindex()
+        ldims = ds.domain_dimensions.astype("int64") * int(ds.refine_by) ** level
+        for sx in (-1, 0, 1):
+            for sy in (-1, 0, 1):
+                for sz in (-1, 0, 1):
+                    sh = np.array([sx, sy, sz], dtype="int64")
+                    if any(sh[a] != 0 and not ds.periodicity[a] for a in range(3)):
+                        continue
+                    off = sh * ldims
+                    a0 = np.maximum(np.floor_divide(lo - off, r), gs) - gs
+                    a1 = np.minimum(-np.floor_divide(-(hi - off), r), gs + g.ActiveDimensions) - gs
+                    if np.any(a1 <= a0):
+                        continue
+                    if g.child_mask[a0[0]:a1[0], a0[1]:a1[1], a0[2]:a1[2]].any():
+                        out = min(out, g.Level)
+    return out
+
+
+def smoothed_covering_grid(ds, level, start_index, dims, key):
+    """YTSmoothedCoveringGrid (construction_data_containers.py:1398-1653) for one field: the box of `dims` cells at
+    `level` starting at global index `start_index`, filled level by level from the coarsest one that matters -- the
+    previous level's box is interpolated onto this level's (``ghost_zone_interpolate``), then every cell a grid of
+    this level covers with a NON-ZERO value replaces the interpolated one (the reference tests ``output != 0``).
+    At level > 0 every box carries one buffer cell per side, stripped at the end."""
+    start_index = np.asarray(start_index, dtype="int64")
+    dims = np.asarray(dims, dtype="int64")
+    rb = int(ds.refine_by)
+    base_dx = ds.domain_width / ds.domain_dimensions.astype("float64")
+    dle = ds.domain_left_edge
+    my_dx = base_dx / rb ** int(level)
+    left_edge = start_index * my_dx + dle
+    right_edge = left_edge + dims * my_dx
+    eps = np.finfo(np.float64).eps
+
+    def minimal_box(dx):                     # :1600-1618
+        cell_start = ((left_edge - dle) + eps) / dx
+        cell_end = ((right_edge - dle) + eps) / dx
+        if level == 0:
+            start = np.floor(cell_start).astype("int64")
+            d = np.rint((dims * my_dx) / dx).astype("int64")
+        else:
+            start = np.rint(cell_start).astype("int64") - 1
+            d = np.rint(cell_end).astype("int64") - start + 1
+        return start, d
+
+    # the coarsest level whose cells can survive in the box (:1460-1492)
+    min_level = 0
+    for lvl in range(int(level), 0, -1):
+        dx = base_dx / rb ** lvl
+        st, d = minimal_box(dx)
+        min_level = _finest_uncovered_level(ds, lvl, st - 1, st + d + 1)
+        if min_level >= lvl:
+            break
+    cur_start, cur_dims = minimal_box(base_dx)
+    field = np.zeros(tuple(int(x) for x in cur_dims), dtype="float64")
+    for lvl in range(int(level) + 1):
+        if lvl >= min_level:
+            out = fill_region(ds, key, lvl, cur_start, cur_dims)
+            m = out != 0
+            field[m] = out[m]
+        if lvl < level:                      # _update_level_state, :1620-1653
+            rf = float(rb)
+            old_start = cur_start
+            cur_start, cur_dims = minimal_box(base_dx / rb ** (lvl + 1))
+            field = ghost_zone_interpolate(rf, field, old_start * rf + 1, cur_dims, cur_start + 0.5)
+    if level > 0:
+        field = field[1:-1, 1:-1, 1:-1]
+    assert field.shape == tuple(int(x) for x in dims), (field.shape, dims)
+    return np.ascontiguousarray(field)
+
+
 class Grid:
     """One grid patch (AMRGridPatch): cell-centred fields on ``ActiveDimensions`` cells."""
     _id_offset = 0
@@ -114,11 +252,35 @@ class Grid:
             self._child_mask = m
         return self._child_mask
 
+    def retrieve_ghost_zones(self, n_zones, fields, all_levels=False, smoothed=False):
+        """grid_patch.py:239-268: this grid's cells plus ``n_zones`` layers around it, at the grid's own level, as
+        {field: array of shape ActiveDimensions + 2 n_zones}.  Only the smoothed form (the one vertex centring asks
+        for) is restated: ``smoothed_covering_grid``."""
+        if all_levels or not smoothed:
+            raise NotImplementedError("only retrieve_ghost_zones(n, fields, smoothed=True) is on the ray-casting path")
+        start = self.get_global_startindex() - int(n_zones)
+        dims = self.ActiveDimensions.astype("int64") + 2 * int(n_zones)
+        out = {}
+        for f in set(fields):
+            key = self.ds._resolve(f)
+            if key not in out:
+                out[key] = smoothed_covering_grid(self.ds, self.Level, start, dims, key)
+            out[f] = out[key]          # the cube answers to the name it was asked for and to the resolved one
+        return out
+
     def get_vertex_centered_data(self, fields, smoothed=True, no_ghost=False):
-        if not no_ghost:
-            raise NotImplementedError("ghost-zone vertex centring is not part of the B200 hot path yet (SURVEY.md 8f rank 1); "
-                                      "use no_ghost=True (VolumeSource.use_ghost_zones = False, the reference default)")
-        return {f: vertex_centre_no_ghost(self[f]) for f in set(fields)}
+        """grid_patch.py:270-312.  ``no_ghost``: trilinear extrapolation from the grid's own cells.  Otherwise every
+        vertex is the mean of the 8 cells around it, taken from the grid padded with one layer of ghost zones
+        (neighbouring grids of the same level, periodic images, or values interpolated from the coarser levels),
+        summed in the reference's order."""
+        out = {}
+        cg = None if no_ghost else self.retrieve_ghost_zones(1, fields, smoothed=smoothed)
+        for f in set(fields):
+            key = self.ds._resolve(f)
+            if key not in out:
+                out[key] = vertex_centre_no_ghost(self[f]) if no_ghost else vertex_centre_from_ghost(cg[key])
+            out[f] = out[key]
+        return out
 
     def __repr__(self):
         return "Grid_%04d (%s)" % (self.id, tuple(self.ActiveDimensions))
