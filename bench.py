@@ -385,6 +385,9 @@ def run_ours(args):
         else:
             # ---- this rank's convex sub-volume of the single grid, resident in HBM -------------------
             lo, hi, path = kd_slab(n, rank, world)
+            if args.shard:     # one GPU casting the sub-volume rank R of P would own (kernel studies; not a bench line)
+                r_, p_ = (int(x) for x in args.shard.split("/"))
+                lo, hi, _ = kd_slab(n, r_, p_)
             vd = np.asarray(sargs[1], dtype=np.float64).ravel()[:3]
             pieces = split_slab(lo, hi, vd, centred)
             bricks = D.BrickSet(ctx, len(pieces), 1, L.CELL_CENTRED if kind == "proj" else L.VERTEX_CENTRED, L.STORE_F32)
@@ -502,6 +505,12 @@ def run_ours(args):
                 composite()   # keeps the ranks' frame counters in step
             kt.append(s.kernel_ms)
         kernel_ms = float(np.mean(kt))
+        rank_kernel_ms = [kernel_ms]
+        if world > 1:
+            t = torch.zeros(world, dtype=torch.float64, device=dev)
+            t[rank] = kernel_ms
+            dist.all_reduce(t)
+            rank_kernel_ms = [float(x) for x in t.tolist()]
 
         # ---- the N-rank frame against the SAME frame cast by rank 0 alone (SCALE lines carry multi-GPU parity) ----
         parity_vs_n1 = None
@@ -576,6 +585,10 @@ def run_ours(args):
         "clocks": clk,
         "roofline": roofline_block(args.workload, kind, world, my_samples, kernel_ms, alg_bytes, clk, ctx.sm_count),
     }
+    if world > 1:
+        line["rank_kernel_ms"] = rank_kernel_ms
+    if args.shard:
+        line["config"]["shard"] = args.shard
     if parity_vs_n1 is not None:
         line["parity_vs_n1"] = {"value": parity_vs_n1, "bar": 1e-4 if kind == "vr" else 1e-6,
                                 "what": ("normalised max |RGBA difference| (SURVEY.md A.5)" if kind == "vr" else "max |difference| / max |reference|")
@@ -599,6 +612,7 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=256)
     ap.add_argument("--cpu-res", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--shard", default="", help="R/P at --gpus 1: cast only the sub-volume rank R of P would own (kernel studies)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip rank 0's single-GPU render of the same frame (parity_vs_n1)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -781,6 +781,31 @@ cast_kernel(const __grid_constant__ CastParams p)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // ---- this thread's pixel: warps are 4(i) x 8(j) pixel patches, j fastest (image is C-order) ----
+    const int tiles_j = (p.cam.ny + TILE_J - 1) / TILE_J;
+    const int ti0 = (blockIdx.x / tiles_j) * TILE_I, tj0 = (blockIdx.x % tiles_j) * TILE_J;
+    const int vi = ti0 + (warp >> 1) * 4 + (lane >> 3);
+    const int vj = tj0 + (warp & 1) * 8 + (lane & 7);
+    const bool active = vi < p.cam.nx && vj < p.cam.ny;
+    const size_t pix = (size_t)(active ? vi : 0) * p.cam.ny + (active ? vj : 0);
+
+    if (!tile_has_bricks(p.extent, p.n_order, ti0, ti0 + TILE_I, tj0, tj0 + TILE_J)) {
+        // nothing of the brick list reaches this tile: the image keeps its pixels; a partial gets the identity map
+        if (PARTIAL) {
+            if (active) {
+                const double zero[4] = {0.0, 0.0, 0.0, 0.0}, one[4] = {1.0, 1.0, 1.0, 1.0};
+                store_partial(p.partial, p.partial_fmt, pix, zero, one);
+            }
+            if (p.tail_flag != nullptr) {
+                SwapSignal sg;
+                sg.n = 1; sg.flag[0] = p.tail_flag;
+                grid_tail_signal(p.tail_counter, sg, p.tail_seq);
+            }
+        }
+        return;
+    }
+
+
     typename pick_sampler<EXACT, ExactSampler<KIND, PARTIAL>, FastSampler<KIND, TFM, PARTIAL, NF1, T>>::type smp;
     smp.tf = &p.tf;
     smp.ray = s_ray;
@@ -823,14 +848,6 @@ cast_kernel(const __grid_constant__ CastParams p)
             smp.pairs = sp;
         }
     }
-
-    // ---- this thread's pixel: warps are 4(i) x 8(j) pixel patches, j fastest (image is C-order) ----
-    const int tiles_j = (p.cam.ny + TILE_J - 1) / TILE_J;
-    const int ti0 = (blockIdx.x / tiles_j) * TILE_I, tj0 = (blockIdx.x % tiles_j) * TILE_J;
-    const int vi = ti0 + (warp >> 1) * 4 + (lane >> 3);
-    const int vj = tj0 + (warp & 1) * 8 + (lane & 7);
-    const bool active = vi < p.cam.nx && vj < p.cam.ny;
-    const size_t pix = (size_t)(active ? vi : 0) * p.cam.ny + (active ? vj : 0);
 
     double max_t = 1.0;
     {
@@ -1361,9 +1378,9 @@ __device__ __forceinline__ void grid_wait(const unsigned long long *flags, int n
             if (t - t0 > 10000000000ULL) { *error = 1; break; }
             __nanosleep(100);
         }
+        __threadfence_system();   // the pollers' fence, then the barrier: every thread's reads come after the flag
     }
     __syncthreads();
-    __threadfence_system();
 }
 
 struct SwapOut { void *buf[SWAP_MAX_DST]; int n; };   // destination buffers (own memory and / or peers')

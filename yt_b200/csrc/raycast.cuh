@@ -722,6 +722,19 @@ __device__ __forceinline__ void make_ray(const DevCamera &cam, int vi, int vj, d
     }
 }
 
+// Does any brick of the order list reach this CTA's pixel box?  (CTA-uniform; every thread must call it.)  A tile no brick
+// reaches reads neither its initial colours nor its z-buffer and stores nothing (a partial cast stores the identity map):
+// with page-locked host arrays bound in place, that is PCIe traffic not spent on the empty part of the image.
+__device__ __forceinline__ bool tile_has_bricks(const int4 *__restrict__ extent, int n_order, int ti0, int ti1, int tj0, int tj1)
+{
+    int hit = 0;
+    for (int k = threadIdx.x; k < n_order; k += blockDim.x) {
+        const int4 e = extent[k];
+        hit |= (e.x < ti1 && e.y > ti0 && e.z < tj1 && e.w > tj0) ? 1 : 0;
+    }
+    return __syncthreads_or(hit) != 0;
+}
+
 // ---- partial images: store one pixel's map in any format; grid-wide completion signal ----------------------------
 // out / Bout: the map as the cast kernels hold it at write-back (fp64 temporaries; B is exactly 0 where a clamp fired).
 __device__ __forceinline__ void store_partial(void *buf, int fmt, size_t pix, const double (&A)[4], const double (&B)[4])
@@ -753,13 +766,14 @@ constexpr int SWAP_MAX_DST = 8;
 struct SwapSignal { unsigned long long *flag[SWAP_MAX_DST]; int n; };
 
 // Called by EVERY thread of EVERY CTA as the last thing a kernel does: when all CTAs have passed, the last one writes
-// `seq` into the flag words (which may live in a peer's memory).  The fences make every store of the grid visible
-// system-wide before the flags are.
+// `seq` into the flag words (which may live in a peer's memory).  One system-scope fence per CTA, by thread 0 AFTER the
+// barrier (the barrier orders the CTA's stores before the fence, the fence is cumulative -- the grid-sync idiom); a fence
+// per thread cost 0.27 ms on a 2048^2 frame (r02j vs r02k: 5.80 against 5.54 ms for the same sub-volume).
 __device__ __forceinline__ void grid_tail_signal(unsigned *counter, const SwapSignal &sg, unsigned long long seq)
 {
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned total = gridDim.x * gridDim.y * gridDim.z;
         if (atomicAdd(counter, 1u) == total - 1u) {
             *counter = 0u;   // the next kernel that counts on it is stream-ordered after this one
