@@ -772,12 +772,16 @@ __global__ void __launch_bounds__(CTA_THREADS, (KIND == KIND_PROJ && !EXACT) ? Y
 cast_kernel(const __grid_constant__ CastParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int s_list[CTA_THREADS];
-    __shared__ int s_warp_cnt[CTA_THREADS / 32];
+    // MANY: the tile's WHOLE culled list is gathered before any brick is walked (LIST_CAP entries at a time), so the warps
+    // of a CTA meet at a barrier once per ~1000 list entries instead of once per 256 scanned bricks (ncu r02m, cfg4: 58
+    // barrier pairs per CTA with 3-4 bricks of uneven work between them; `barrier` was 9 % of the stall samples)
+    constexpr int LIST_CAP = MANY ? 4 * CTA_THREADS : CTA_THREADS;
+    __shared__ int s_list[LIST_CAP];
+    __shared__ int s_warp_cnt[2][CTA_THREADS / 32];
     // the rays of this tile, component-major: only needed when a ray enters a brick, so they live here
     // instead of in 12 registers per thread
     __shared__ double s_ray[(MANY ? 9 : 6) * CTA_THREADS];
-    __shared__ int4 s_ext[MANY ? CTA_THREADS : 1];
+    __shared__ int4 s_ext[MANY ? LIST_CAP : 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -789,7 +793,7 @@ cast_kernel(const __grid_constant__ CastParams p)
     const bool active = vi < p.cam.nx && vj < p.cam.ny;
     const size_t pix = (size_t)(active ? vi : 0) * p.cam.ny + (active ? vj : 0);
 
-    if (!tile_has_bricks(p.extent, p.n_order, ti0, ti0 + TILE_I, tj0, tj0 + TILE_J)) {
+    if (!tile_has_bricks(p.extent, p.chunk_extent, p.n_order, ti0, ti0 + TILE_I, tj0, tj0 + TILE_J)) {
         // nothing of the brick list reaches this tile: the image keeps its pixels; a partial gets the identity map
         if (PARTIAL) {
             if (active) {
@@ -884,31 +888,45 @@ cast_kernel(const __grid_constant__ CastParams p)
     // ---- walk the ordered brick list; cull bricks whose pixel footprint misses this tile ----
     const int ti1 = ti0 + TILE_I, tj1 = tj0 + TILE_J;
     const int wi0 = ti0 + (warp >> 1) * 4, wj0 = tj0 + (warp & 1) * 8;   // this warp's 4x8 pixel patch
-    for (int base = 0; base < p.n_order; base += CTA_THREADS) {
-        const int k = base + tid;
-        bool hit = false;
-        int b = -1;
-        int4 e = make_int4(0, 0, 0, 0);
-        if (k < p.n_order) {
-            e = p.extent[k];
-            hit = e.x < ti1 && e.y > ti0 && e.z < tj1 && e.w > tj0;
-            b = p.order[k];
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s_warp_cnt[warp] = __popc(m);
-        __syncthreads();
-        int off = 0, total = 0;
+    for (int base = 0, chunk = 0; base < p.n_order;) {
+        // ordered compaction of the next chunk(s) of the brick list: one chunk unless MANY, else until the list is full.
+        // s_warp_cnt is double-buffered so that a chunk costs one barrier (a warp rewrites a buffer two chunks later,
+        // after every warp has passed the barrier of the chunk in between).
+        int total = 0;
+        do {
+            // the union footprint of these CTA_THREADS consecutive bricks (kd order: a compact subtree) misses the tile:
+            // nothing to scan (CTA-uniform, so the barrier below stays collective)
+            const int4 ce = p.chunk_extent[base / CTA_THREADS];
+            if (ce.x < ti1 && ce.y > ti0 && ce.z < tj1 && ce.w > tj0) {
+                const int k = base + tid;
+                bool hit = false;
+                int b = -1;
+                int4 e = make_int4(0, 0, 0, 0);
+                if (k < p.n_order) {
+                    e = p.extent[k];
+                    hit = e.x < ti1 && e.y > ti0 && e.z < tj1 && e.w > tj0;
+                    b = p.order[k];
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_warp_cnt[chunk & 1][warp] = __popc(m);
+                __syncthreads();
+                int off = 0, ctotal = 0;
 #pragma unroll
-        for (int w = 0; w < CTA_THREADS / 32; w++) {
-            const int cnt = s_warp_cnt[w];
-            if (w < warp) off += cnt;
-            total += cnt;
-        }
-        if (hit) {
-            const int slot = off + __popc(m & ((1u << lane) - 1u));
-            s_list[slot] = b;
-            if constexpr (MANY) s_ext[slot] = e;
-        }
+                for (int w = 0; w < CTA_THREADS / 32; w++) {
+                    const int cnt = s_warp_cnt[chunk & 1][w];
+                    if (w < warp) off += cnt;
+                    ctotal += cnt;
+                }
+                if (hit) {
+                    const int slot = total + off + __popc(m & ((1u << lane) - 1u));
+                    s_list[slot] = b;
+                    if constexpr (MANY) s_ext[slot] = e;
+                }
+                total += ctotal;
+                chunk++;
+            }
+            base += CTA_THREADS;
+        } while (MANY && base < p.n_order && total + CTA_THREADS <= LIST_CAP);
         __syncthreads();
         if (active) {
             for (int q = 0; q < total; q++) {
@@ -1134,6 +1152,29 @@ __global__ void extent_kernel(DevCamera cam, const DevBrick *bricks, const int *
         }
     }
     extent[k] = e;
+}
+
+// Union footprint of every CTA_THREADS consecutive entries of the order list (the chunk a cast CTA scans at a time): in
+// kd order such a chunk is a compact subtree, so most chunks of a long list miss a given 16x16 tile and are skipped
+// without reading their entries.  An entry with an empty footprint does not widen the union.
+__global__ void __launch_bounds__(CTA_THREADS) chunk_extent_kernel(const int4 *extent, int n_order, int4 *chunk_extent)
+{
+    const int k = blockIdx.x * CTA_THREADS + threadIdx.x;
+    int x = 0x7fffffff, y = -0x7fffffff, z = 0x7fffffff, w = -0x7fffffff;
+    if (k < n_order) {
+        const int4 e = extent[k];
+        if (e.x < e.y && e.z < e.w) { x = e.x; y = e.y; z = e.z; w = e.w; }
+    }
+    x = __reduce_min_sync(0xffffffffu, x); y = __reduce_max_sync(0xffffffffu, y);
+    z = __reduce_min_sync(0xffffffffu, z); w = __reduce_max_sync(0xffffffffu, w);
+    __shared__ int4 s[CTA_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = make_int4(x, y, z, w);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int4 r = s[0];
+        for (int i = 1; i < CTA_THREADS / 32; i++) { r.x = min(r.x, s[i].x); r.y = max(r.y, s[i].y); r.z = min(r.z, s[i].z); r.w = max(r.w, s[i].w); }
+        chunk_extent[blockIdx.x] = r;
+    }
 }
 
 // ---- affine partial images -----------------------------------------------------
@@ -1449,6 +1490,15 @@ __global__ void __launch_bounds__(256) swap_apply_kernel(const __grid_constant__
 __global__ void swap_wait_kernel(const unsigned long long *flags, int n, unsigned long long seq, int *error)
 {
     grid_wait(flags, n, seq, error);
+}
+
+// One flag word (in a peer's slab) set from a kernel: stream-ordered behind whatever the stream did before (a copy-engine
+// transfer of a finished strip, for one).
+__global__ void swap_signal_kernel(unsigned long long *flag, unsigned long long seq)
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(flag) = seq;
+    __threadfence_system();
 }
 
 __global__ void f64_to_f32_kernel(const double *src, float *dst, long long n)

@@ -90,6 +90,7 @@ struct CastParams {
     const DevBrick *bricks;
     const int *order;       // brick indices in the reference's traversal order
     const int4 *extent;     // per order entry: [i0,i1) x [j0,j1) pixel footprint
+    const int4 *chunk_extent;   // per CTA_THREADS consecutive order entries: the union of their footprints
     int n_order;
     int n_samples;
     double inv_ns;          // 1 / n_samples

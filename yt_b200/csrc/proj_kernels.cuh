@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(CTA_THREADS, YTB_PROJ_MINB) proj_kernel(const 
     const bool active = vi >= 0 && vj >= 0 && vi < p.cam.nx && vj < p.cam.ny;
     const size_t pix = (size_t)(active ? vi : 0) * p.cam.ny + (active ? vj : 0);
 
-    if (!tile_has_bricks(p.extent, p.n_order, ti0, ti1, tj0, tj1)) {
+    if (!tile_has_bricks(p.extent, p.chunk_extent, p.n_order, ti0, ti1, tj0, tj1)) {
         if (PARTIAL) {
             if (active) {
                 const double zero[4] = {0.0, 0.0, 0.0, 0.0}, one[4] = {1.0, 1.0, 1.0, 1.0};

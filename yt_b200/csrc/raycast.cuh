@@ -725,12 +725,18 @@ __device__ __forceinline__ void make_ray(const DevCamera &cam, int vi, int vj, d
 // Does any brick of the order list reach this CTA's pixel box?  (CTA-uniform; every thread must call it.)  A tile no brick
 // reaches reads neither its initial colours nor its z-buffer and stores nothing (a partial cast stores the identity map):
 // with page-locked host arrays bound in place, that is PCIe traffic not spent on the empty part of the image.
-__device__ __forceinline__ bool tile_has_bricks(const int4 *__restrict__ extent, int n_order, int ti0, int ti1, int tj0, int tj1)
+__device__ __forceinline__ bool tile_has_bricks(const int4 *__restrict__ extent, const int4 *__restrict__ chunk_extent, int n_order,
+                                                int ti0, int ti1, int tj0, int tj1)
 {
     int hit = 0;
-    for (int k = threadIdx.x; k < n_order; k += blockDim.x) {
-        const int4 e = extent[k];
-        hit |= (e.x < ti1 && e.y > ti0 && e.z < tj1 && e.w > tj0) ? 1 : 0;
+    for (int base = 0; base < n_order; base += CTA_THREADS) {
+        const int4 ce = chunk_extent[base / CTA_THREADS];   // union footprint of this chunk of the list (chunk_extent_kernel)
+        if (!(ce.x < ti1 && ce.y > ti0 && ce.z < tj1 && ce.w > tj0)) continue;
+        const int k = base + (int)threadIdx.x;
+        if (k < n_order) {
+            const int4 e = extent[k];
+            hit |= (e.x < ti1 && e.y > ti0 && e.z < tj1 && e.w > tj0) ? 1 : 0;
+        }
     }
     return __syncthreads_or(hit) != 0;
 }

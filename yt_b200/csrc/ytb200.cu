@@ -780,14 +780,17 @@ static int prepare_order(ytb200_frame *f, const ytb200_brickset *set, const int6
         cudaFree(f->order_dev); cudaFree(f->extent_dev);
         f->order_dev = nullptr; f->extent_dev = nullptr;
         CK(cudaMalloc(&f->order_dev, sizeof(int) * (size_t)n_order));
-        CK(cudaMalloc(&f->extent_dev, sizeof(int4) * (size_t)n_order));
+        // footprints of the entries, then the union footprints of every CTA_THREADS consecutive entries (chunk_extent_kernel)
+        CK(cudaMalloc(&f->extent_dev, sizeof(int4) * ((size_t)n_order + (size_t)n_order / CTA_THREADS + 1)));
         f->order_cap = n_order;
     }
     if (n_order) {
         CK(cudaMemcpyAsync(f->order_dev, f->order_host.data(), sizeof(int) * (size_t)n_order, cudaMemcpyHostToDevice, f->ctx->stream));
         extent_kernel<<<(unsigned)((n_order + 127) / 128), 128, 0, f->ctx->stream>>>(f->cam, set->dev, f->order_dev, (int)n_order, f->extent_dev);
         CK(cudaGetLastError());
-        if (launches) (*launches)++;
+        chunk_extent_kernel<<<(unsigned)((n_order + CTA_THREADS - 1) / CTA_THREADS), CTA_THREADS, 0, f->ctx->stream>>>(f->extent_dev, (int)n_order, f->extent_dev + f->order_cap);
+        CK(cudaGetLastError());
+        if (launches) (*launches) += 2;
     }
     f->order_generation = set->generation;
     return 0;
@@ -860,7 +863,7 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
     if (n_order > 0 || partial) {
         CastParams p{};
         p.cam = f->cam;
-        p.bricks = set->dev; p.order = f->order_dev; p.extent = f->extent_dev; p.n_order = (int)n_order;
+        p.bricks = set->dev; p.order = f->order_dev; p.extent = f->extent_dev; p.chunk_extent = f->extent_dev + f->order_cap; p.n_order = (int)n_order;
         p.n_samples = n_samples < 1 ? 1 : n_samples;
         p.inv_ns = 1.0 / (double)p.n_samples;
         p.image = f->image; p.zbuffer = f->zbuffer; p.partial = partial; p.partial_fmt = partial_fmt;
@@ -955,7 +958,7 @@ extern "C" int ytb200_frame_count(ytb200_frame *f, int kind, const ytb200_bricks
     CK(cudaMemsetAsync(f->ctx->counters, 0, 8 * sizeof(unsigned long long), st));
     CastParams p{};
     p.cam = f->cam;
-    p.bricks = set->dev; p.order = f->order_dev; p.extent = f->extent_dev; p.n_order = (int)n_order;
+    p.bricks = set->dev; p.order = f->order_dev; p.extent = f->extent_dev; p.chunk_extent = f->extent_dev + f->order_cap; p.n_order = (int)n_order;
     p.zbuffer = f->zbuffer; p.counters = f->ctx->counters;
     const unsigned grid = (unsigned)(((f->cam.nx + TILE_I - 1) / TILE_I) * ((f->cam.ny + TILE_J - 1) / TILE_J));
     CK(cudaEventRecord(f->ctx->ev0, st));
@@ -1375,14 +1378,24 @@ static int swap_run(ytb200_swap *s, ytb200_frame *f, int broadcast, double *host
             a.done.n = 1; a.done.flag[0] = swap_flag(s->peer_slab[(size_t)s->rounds[(size_t)j + 1].partner], j + 1);
             swap_round_kernel<FMT, false><<<blocks(a.n), 256, 0, st>>>(a);
         } else if (host_image) {
-            // finished fp64 pixels of this rank's strip, straight into the caller's page-locked image over this GPU's PCIe link
+            // finished fp64 pixels of this rank's strip into the caller's page-locked image over this GPU's PCIe link
             a.c0 = c0 + f0; a.image = reinterpret_cast<double4 *>(host_image) + f0;
             if (s->c0_staged && c0 == reinterpret_cast<const double4 *>(host_image)) {
+                // The strip of initial colours was staged in HBM during the cast: finish the pixels in place there and let
+                // the copy engine carry them out -- one bulk PCIe write instead of 32-byte stores from the SMs (r02j: the
+                // in-kernel stores of eight ranks together sustained 48 GB/s, 2.8 ms for the 134 MB image) -- then tell
+                // the destination rank from a one-thread kernel that is stream-ordered behind the copy.
                 CK(cudaStreamWaitEvent(st, s->ev_c0, 0));
-                a.c0 = s->c0_stage;
+                a.c0 = s->c0_stage; a.image = s->c0_stage;
+                a.done.n = 0;
+                swap_round_kernel<FMT, true><<<blocks(a.n), 256, 0, st>>>(a);
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(reinterpret_cast<double4 *>(host_image) + f0, s->c0_stage, (size_t)a.n * sizeof(double4), cudaMemcpyDefault, st));
+                swap_signal_kernel<<<1, 1, 0, st>>>(swap_flag(s->peer_slab[0], SWAP_FLAG_FINAL + s->rank), seq);
+            } else {
+                a.done.n = 1; a.done.flag[0] = swap_flag(s->peer_slab[0], SWAP_FLAG_FINAL + s->rank);
+                swap_round_kernel<FMT, true><<<blocks(a.n), 256, 0, st>>>(a);
             }
-            a.done.n = 1; a.done.flag[0] = swap_flag(s->peer_slab[0], SWAP_FLAG_FINAL + s->rank);
-            swap_round_kernel<FMT, true><<<blocks(a.n), 256, 0, st>>>(a);
         } else {
             for (int w = 0; w < s->world; w++) {
                 if (!broadcast && w != 0) continue;
