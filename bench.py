@@ -40,11 +40,13 @@ WORKLOADS = {
     "cfg3_proj_1024c_2048px": (1024, 2048, "proj"),
     "iproj_1024c_2048px": (1024, 2048, "iproj"),               # InterpolatedProjectionSampler on the north-star volume
     "cfg4_amr_vr_15kbricks_persp_2048px": (128, 2048, "vr"),   # nested-box AMR, PerspectiveLens (BASELINE configs[3])
+    "cfg4_amr_vr_24kbricks_persp_2048px": (144, 2048, "vr"),   # the same on 144^3 root cells: 23 328 grids, 23 952 kd leaves ("~20k bricks")
     "cfg5_vr_2048c_4096px": (2048, 4096, "vr"),                # BASELINE configs[4]; 34.4 GB of vertex data
     "tiny_vr_64c_256px": (64, 256, "vr"),
     "tiny_amr_vr_persp_256px": (16, 256, "vr"),
 }
-AMR_WORKLOADS = {"cfg4_amr_vr_15kbricks_persp_2048px": (128, 8, 4), "tiny_amr_vr_persp_256px": (16, 8, 3)}
+AMR_WORKLOADS = {"cfg4_amr_vr_15kbricks_persp_2048px": (128, 8, 4), "cfg4_amr_vr_24kbricks_persp_2048px": (144, 8, 4),
+                 "tiny_amr_vr_persp_256px": (16, 8, 3)}
 MAX_BRICK_ELEMS = 2 ** 31    # the kernels follow a ray with 32-bit running offsets
 N_SAMPLES = 10
 SEED = 0

@@ -69,7 +69,7 @@ typedef struct ytb200_camera {
 typedef struct ytb200_stats {
     double kernel_ms;    /* CUDA-event time of the cast kernels on the context stream (0 if not timed) */
     int64_t n_launches;  /* kernels launched by the call */
-    int64_t n_cells;     /* cells handed to sample() (only filled by ytb200_frame_count) */
+    int64_t n_cells;     /* cells handed to sample() (ytb200_frame_count; an early-termination cast: the cells it sampled) */
     int64_t n_samples;   /* n_cells * n_samples for the sampling kinds, n_cells for PROJECTION */
 } ytb200_stats;
 
@@ -214,6 +214,15 @@ int ytb200_frame_cast_partial_f32(ytb200_frame *f, int kind, const ytb200_bricks
  * strip, in place over PCIe instead of from uploaded copies (a rank reads 1/P of the image instead of uploading all of
  * it).  image_host = NULL unbinds. */
 int ytb200_frame_bind_host(ytb200_frame *f, const double *image_host, const double *zbuffer_host);
+/* Early ray termination (ours; the reference has none).  With eps > 0, volume renders through a GREY-OPACITY
+ * ColorTransferFunction (fp32 storage, FAST precision, one field) run the reversed cast: FIT_eval_transfer's composition
+ * C <- e + a C (field_interpolation_tables.pxd:103-110) is evaluated from its far end, front to back, and a ray stops once
+ * the transmittance of what it has composited is below eps -- the pixel then differs from the full composition by at most
+ * eps times the brightest colour the skipped part could have reached.  Other tables and samplers ignore the setting (a
+ * non-grey table absorbs each channel with its own emission, and a ray saturates only where all three channels do).
+ * A timed cast reports the cells the rays actually sampled in ytb200_stats.n_cells / n_samples; the algorithmic count
+ * stays ytb200_frame_count's.  eps = 0 (the default) disables. */
+int ytb200_frame_set_early_termination(ytb200_frame *f, double eps);
 typedef struct ytb200_swap ytb200_swap;
 #define YTB200_PARTIAL_AB64 0   /* fp64 (A[4], B[4]): 64 B per pixel -- EXACT precision */
 #define YTB200_PARTIAL_AB32 1   /* fp32 (A[4], B[4]): 32 B -- FAST volume render, any transfer function */

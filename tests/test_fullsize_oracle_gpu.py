@@ -199,3 +199,92 @@ def test_cfg2_full_frame_matches_the_reference(gpu):
     err = T.normalised_diff(got, want, False)
     print("cfg2 full frame vs %s: normalised max diff %.3g" % (label, err))
     assert err <= 1e-4
+
+
+def test_cfg4_amr_frame_matches_the_reference_on_a_ray_lattice(gpu):
+    """BASELINE configs[3] as bench.py times it (nested-box AMR, 16 384 grids / 14 848 kd leaves of 8^3 cells,
+    PerspectiveLens at 2048^2, the whole view-ordered leaf list in one launch), against the reference casting a 64x64
+    lattice of the same perspective rays through the same leaves in the same kd order, leaf by leaf.  The leaves reach
+    the reference as the host mirror builds them (get_brick_data: the reference's own per-grid vertex centring),
+    rounded to the fp32 the device stores."""
+    from bench import AMR_WORKLOADS, N_SAMPLES, amr_camera, bench_tf
+    from yt_b200 import _lib as L
+    from yt_b200 import image_samplers as S
+    from yt_b200 import loaders, synthetic
+    from yt_b200.amr_kdtree import AMRKDTree
+    R = 2048
+    base, tile, levels = AMR_WORKLOADS["cfg4_amr_vr_15kbricks_persp_2048px"]
+    grids, dd = synthetic.nested_amr_grids(base_cells=base, tile=tile, levels=levels, seed=SEED)
+    ds = loaders.load_amr_grids(grids, dd)
+    kd = AMRKDTree(ds, comm_rank=0, comm_size=1)
+    kd.set_fields([ds.default_field], [False], True)
+    cam, tf = amr_camera(R), bench_tf()
+    args, kw = T.sampler_args(cam)
+    s = S.VolumeRenderSampler(*args, tf, N_SAMPLES, **kw)
+    bricks = kd.device_bricks(s._ctx, L.STORE_F32)
+    order = np.ascontiguousarray(kd.view_order(cam.lens.viewpoint), dtype=np.int64)
+    assert len(order) > 14000
+    s.cast_bricks(bricks, order)
+    got = np.array(s.aimage)
+
+    Sref, Gref, label = _reference()
+    ii, jj = _lattice(R), _lattice(R)[::-1].copy()
+    pos = np.ascontiguousarray(np.asarray(args[0], "float64")[np.ix_(ii, jj)])
+    dirs = np.ascontiguousarray(np.asarray(args[1], "float64")[np.ix_(ii, jj)])
+    img = np.zeros((len(ii), len(jj), 4))
+    a = list(args)
+    a[0], a[1], a[4] = pos, dirs, img
+    ref = Sref.VolumeRenderSampler(*a, tf, N_SAMPLES, lens_type="lattice", zbuffer=np.ones(img.shape[:2]))
+    n_leaves = 0
+    for node in kd.tree.traverse(cam.lens.viewpoint):
+        b = kd.get_brick_data(int(node))
+        data = [np.ascontiguousarray(d.astype("float32").astype("float64")) for d in b.my_data]
+        ref(Gref.PartitionedGrid(0, data, np.asarray(b.source_mask, "uint8"), np.asarray(b.LeftEdge, "float64"), np.asarray(b.RightEdge, "float64"),
+                                 np.asarray(b.dims, "int64")), num_threads=0)
+        n_leaves += 1
+    assert n_leaves == len(order)
+    want = np.array(ref.aimage)
+    sub = got[np.ix_(ii, jj)]
+    assert (want[:, :, :3].sum(axis=2) > 0).mean() > 0.3, label
+    err = T.normalised_diff(sub, want, False)
+    print("cfg4 vs %s on a %dx%d ray lattice over %d leaves: normalised max diff %.3g" % (label, len(ii), len(jj), n_leaves, err))
+    assert err <= 1e-4
+    assert np.array_equal(sub[:, :, 3], want[:, :, 3])
+
+
+@pytest.mark.parametrize("opacity", [1.0, 30.0])
+def test_grey_opacity_frames_match_the_reference_on_a_ray_lattice(opacity, gpu):
+    """The north-star volume through the benchmark's table with grey opacity (and 30x more opaque: the case early ray
+    termination is for), plain cast and terminated cast (eps 1e-6), against the reference: ~18 000 fp32 compositing
+    steps per ray in either direction."""
+    import torch
+    from bench import N_SAMPLES, bench_camera, bench_tf
+    from yt_b200 import _lib as L
+    from yt_b200 import device as D
+    from yt_b200 import image_samplers as S
+    from yt_b200 import synthetic
+    from yt_b200.volume_rendering.transfer_functions import ColorTransferFunction
+    N, R = 1024, 2048
+    _need_memory(12)
+    dev = torch.device("cuda", gpu.device)
+    cam, base = bench_camera(R), bench_tf()
+    tf = ColorTransferFunction(base.x_bounds, base.nbins, grey_opacity=True)
+    for c in range(4):
+        tf.funcs[c].y[:] = base.funcs[c].y * (opacity if c == 3 else 1.0)
+    args, kw = T.sampler_args(cam)
+    kw.pop("camera_data")
+    vol = synthetic.vertex_slab(N, [0, 0, 0], [N, N, N], SEED, dev)
+    _torch_done()
+    ii, jj = _lattice(R), _lattice(R)[::-1].copy()
+    want, label = reference_on_lattice("vr", cam, args, ii, jj, N, lambda x0, x1: vol[x0:x1 + 1].cpu().numpy().astype("float64"), 1,
+                                       tf=tf, n_samples=N_SAMPLES)
+    for ert in (0.0, 1e-6):
+        s = S.VolumeRenderSampler(*args, tf, N_SAMPLES, early_termination=ert, **kw)
+        bs = D.BrickSet(s._ctx, 1, 1, L.VERTEX_CENTRED, L.STORE_F32)
+        bs.attach(0, [vol.data_ptr()], 0, [0.0] * 3, [1.0] * 3, [N] * 3, keep=vol)
+        bs.commit()
+        s.cast_bricks(bs, np.arange(1, dtype=np.int64))
+        sub = np.array(s.aimage)[np.ix_(ii, jj)]
+        err = T.normalised_diff(sub, want, True)
+        print("grey opacity x%g, early termination %g vs %s: normalised max diff %.3g" % (opacity, ert, label, err))
+        assert err <= 1e-4

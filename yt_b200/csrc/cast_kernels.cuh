@@ -134,7 +134,7 @@ struct ExactSampler {
 // in fp64, in the reference's evaluation order (image_samplers.pyx:472-487, fixed_interpolator.cpp:34-52),
 // followed by the fp32 table lookup / compositing of the fast path.  The re-walk sits outside the hot
 // loop, so its registers cost the fast path nothing.
-template <bool PARTIAL, bool GREY, typename T>
+template <bool PARTIAL, bool GREY, typename T, bool ERT = false>
 struct CarefulSampler {
     const double *ray;
     const DevBrick *br;
@@ -143,6 +143,7 @@ struct CarefulSampler {
     int n_samples;
     int cur[3], stp[3];
     ColourAcc ca;
+    float dt_scale;   // ERT: the reversed ray is parametrised over [0, max_t] of the caller's ray (see cast_kernel)
 
     template <bool MASKED>
     __device__ __forceinline__ void begin(const int (&c)[3], const int (&s)[3])
@@ -170,7 +171,8 @@ struct CarefulSampler {
         const double c000 = (double)__ldg(d), c001 = (double)__ldg(d + 1), c010 = (double)__ldg(d + sy), c011 = (double)__ldg(d + sy + 1);
         const double c100 = (double)__ldg(d + sx), c101 = (double)__ldg(d + sx + 1), c110 = (double)__ldg(d + sx + sy), c111 = (double)__ldg(d + sx + sy + 1);
         const double dt = ddiv(dsub(exit_t, enter_t), (double)n_samples);
-        const float dtf = (float)((exit_t - enter_t) * (1.0 / (double)n_samples));
+        float dtf = (float)((exit_t - enter_t) * (1.0 / (double)n_samples));
+        if (ERT) dtf *= dt_scale;
         const double b0 = tf->b0[0], b1 = tf->b1[0], idbin = tf->idbin[0];
         // a valid sample must read a data row: clamp its row coordinate into [2, hi) against fp32 rounding
         const float hi = __int_as_float(__float_as_int(tf->colour_hi) - 1);
@@ -198,7 +200,7 @@ struct CarefulSampler {
             const bool valid = !(xv >= b1 || xv <= b0) && is_normal64(xv);
             float fs = 0.5f;
             if (valid) fs = fminf(fmaxf((float)fma(xv - b0, idbin, 2.0), 2.0f), hi);
-            colour_sample<PARTIAL, GREY>(ct, fs, dtf, ca);
+            colour_sample<PARTIAL, GREY, ERT>(ct, fs, dtf, ca);
 #pragma unroll
             for (int i = 0; i < 3; i++) dp[i] = dadd(dp[i], ds[i]);
         }
@@ -214,10 +216,12 @@ struct CarefulSampler {
 //          the point at parameter t is fma(t, dc[i], ob[i])
 // NF1: the brick set has exactly one field (corners cached in registers per cell).
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int TFM, bool PARTIAL, bool NF1, typename T>
+template <int KIND, int TFM, bool PARTIAL, bool NF1, typename T, bool ERT = false>
 struct FastSampler {
     const double *ray;   // shared memory: this CTA's rays, component-major [6][CTA_THREADS] (vp then vd)
     const DevBrick *br;
+    float dt_scale;      // ERT: max_t of the caller's ray (the reversed ray runs over [0, 1] of [0, max_t])
+    unsigned cells;      // ERT: cells this ray sampled (the rest of the algorithmic count was skipped)
     double ob[3], dc[3];
     float dcf[3];
     unsigned off, moff;
@@ -412,15 +416,21 @@ struct FastSampler {
                     const float x = fmaf(q0, dcx[0], bse[0]), y = fmaf(q1, dcx[1], bse[1]), z = fmaf(q2, dcx[2], bse[2]);
                     const float sxs = dcx[0] * dt, sys = dcx[1] * dt, szs = dcx[2] * dt;
                     float m;
-                    const bool clamp = !(dt * tf->colour_clamp_bound <= 1.f);
+                    const float dte = ERT ? dt * dt_scale : dt;   // dt of the caller's ray: what the emission is weighted with
+                    const bool clamp = !(dte * tf->colour_clamp_bound <= 1.f);
                     if (tf->colour_delta) {
-                        if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM), true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
-                        else m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM), true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+                        if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM), true, ERT>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dte, ca);
+                        else m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM), true, ERT>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dte, ca);
                     } else {
-                        if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM), false>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
-                        else m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM), false>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dt, ca);
+                        if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM), false, ERT>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dte, ca);
+                        else m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM), false, ERT>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dte, ca);
                     }
                     if (tfm_edge(TFM)) doubt = doubt || (m < tf->colour_band);
+                    if (ERT) {
+                        // everything still to come is seen through `tb`: below the threshold the ray is finished
+                        cells++;
+                        if (ca.tb < prm->ert_eps) cont = 0u;
+                    }
                 }
             }
             // the exit face of the step axis becomes the entry face; the loaded face is the new exit face
@@ -767,10 +777,19 @@ template <class A, class B> struct pick_sampler<false, A, B> { using type = B; }
 // of set-up per (ray, brick) against ~4900 of sampling).  It skips, warp-wide, the bricks whose pixel footprint misses the
 // warp's 4x8 patch, and computes 1 / v_dir once per ray.  A separate instantiation so that the single-brick kernel of the
 // north-star frame keeps its register allocation (an in-place attempt cost it 13 %).
-template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T, bool MANY = false>
+// ERT (ert.cu; grey-opacity ColorTransferFunction casts only): EARLY RAY TERMINATION.  The reference composites a ray's
+// samples in walk order with C <- e + a C (field_interpolation_tables.pxd:103-110), so the samples processed LAST weigh
+// most and everything before them is seen through the product of their a's.  The ERT cast therefore runs the composition
+// from the other end: the host hands the order list REVERSED, every ray is reversed in place (origin vp + max_t vd,
+// direction -max_t vd: the same cells and the same sample points, met in the opposite order), the affine maps are
+// applied front to back (A <- A + B e, B <- B a) and a ray stops as soon as B < ert_eps -- what is left
+// can change the pixel by at most B times the brightest colour the rest could reach.  A warp whose rays are all
+// finished skips the remaining bricks (one vote per brick), a CTA whose warps are all finished leaves the list.
+template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T, bool MANY = false, bool ERT = false>
 __global__ void __launch_bounds__(CTA_THREADS, (KIND == KIND_PROJ && !EXACT) ? YTB_MIN_BLOCKS_PROJ : YTB_MIN_BLOCKS)
 cast_kernel(const __grid_constant__ CastParams p)
 {
+    static_assert(!ERT || (KIND == KIND_VR && !EXACT && tfm_grey(TFM) && NF1), "early termination: grey-opacity colour casts only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // MANY: the tile's WHOLE culled list is gathered before any brick is walked (LIST_CAP entries at a time), so the warps
     // of a CTA meet at a barrier once per ~1000 list entries instead of once per 256 scanned bricks (ncu r02m, cfg4: 58
@@ -810,7 +829,7 @@ cast_kernel(const __grid_constant__ CastParams p)
     }
 
 
-    typename pick_sampler<EXACT, ExactSampler<KIND, PARTIAL>, FastSampler<KIND, TFM, PARTIAL, NF1, T>>::type smp;
+    typename pick_sampler<EXACT, ExactSampler<KIND, PARTIAL>, FastSampler<KIND, TFM, PARTIAL, NF1, T, ERT>>::type smp;
     smp.tf = &p.tf;
     smp.ray = s_ray;
     // ---- stage the transfer-function tables into shared memory -------------------------------
@@ -860,10 +879,18 @@ cast_kernel(const __grid_constant__ CastParams p)
         if (active) {
             make_ray(p.cam, vi, vj, vp, vd);
             if (p.zbuffer) { const double z = p.zbuffer[pix]; max_t = fmin(fmax(z, 0.0), 1.0); }
-            if (!PARTIAL) {
+            if (!PARTIAL && !ERT) {
                 const double4 px = *reinterpret_cast<const double4 *>(p.image + pix * 4);
                 init[0] = px.x; init[1] = px.y; init[2] = px.z; init[3] = px.w;
             }
+        }
+        if constexpr (ERT) {
+            // the reversed ray: t' in [0, 1] is t = max_t (1 - t') of the caller's ray; a cell's dt' times max_t is its dt
+#pragma unroll
+            for (int i = 0; i < 3; i++) { vp[i] = fma(max_t, vd[i], vp[i]); vd[i] = -(max_t * vd[i]); }
+            smp.dt_scale = (float)max_t;
+            smp.cells = 0u;
+            max_t = 1.0;
         }
 #pragma unroll
         for (int i = 0; i < 3; i++) { s_ray[i * CTA_THREADS + tid] = vp[i]; s_ray[(3 + i) * CTA_THREADS + tid] = vd[i]; }
@@ -879,6 +906,7 @@ cast_kernel(const __grid_constant__ CastParams p)
             for (int c = 0; c < 4; c++) { smp.acc[c] = init[c]; smp.rgba[c] = (float)init[c]; smp.B[c] = 1.f; }
             smp.ca.c01 = make_float2((float)init[0], (float)init[1]); smp.ca.c2 = (float)init[2]; smp.ca.c3 = (float)init[3];
             smp.ca.fired = 0u;
+            smp.ca.tb = 1.f;   // ERT: nothing composited yet (its accumulators start from zero: init[] stays 0)
             smp.prm = &p;
         }
     }
@@ -888,6 +916,7 @@ cast_kernel(const __grid_constant__ CastParams p)
     // ---- walk the ordered brick list; cull bricks whose pixel footprint misses this tile ----
     const int ti1 = ti0 + TILE_I, tj1 = tj0 + TILE_J;
     const int wi0 = ti0 + (warp >> 1) * 4, wj0 = tj0 + (warp & 1) * 8;   // this warp's 4x8 pixel patch
+    const unsigned wmask = __ballot_sync(0xffffffffu, active);             // the lanes of this warp that own a pixel
     for (int base = 0, chunk = 0; base < p.n_order;) {
         // ordered compaction of the next chunk(s) of the brick list: one chunk unless MANY, else until the list is full.
         // s_warp_cnt is double-buffered so that a chunk costs one barrier (a warp rewrites a buffer two chunks later,
@@ -930,6 +959,13 @@ cast_kernel(const __grid_constant__ CastParams p)
         __syncthreads();
         if (active) {
             for (int q = 0; q < total; q++) {
+                if constexpr (ERT) {
+                    // the vote: bricks are skipped by the warp once every ray of it is finished (lanes of a warp that are
+                    // off the image never get here, hence the active mask)
+                    const bool live = smp.ca.tb >= p.ert_eps;
+                    if (!__any_sync(wmask, live)) break;
+                    if (!live) continue;
+                }
                 if constexpr (MANY) {
                     const int4 we = s_ext[q];   // warp-uniform: the footprint misses every pixel of this warp
                     if (!(we.x < wi0 + 4 && we.y > wi0 && we.z < wj0 + 8 && we.w > wj0)) continue;
@@ -947,14 +983,17 @@ cast_kernel(const __grid_constant__ CastParams p)
                     volatile float entry[8];
                     entry[0] = smp.ca.c01.x; entry[1] = smp.ca.c01.y; entry[2] = smp.ca.c2; entry[3] = smp.ca.c3;
                     if (PARTIAL) entry[4] = __uint_as_float(smp.ca.fired);
+                    if (ERT) entry[5] = smp.ca.tb;
                     smp.doubt = false;
                     cast_colour(g, vp, vd, max_t, smp, masked);
                     if (smp.doubt) {
-                        CarefulSampler<PARTIAL, tfm_grey(TFM), T> cs;
+                        CarefulSampler<PARTIAL, tfm_grey(TFM), T, ERT> cs;
                         cs.ray = s_ray; cs.br = br; cs.tf = &p.tf; cs.base = smp.ct.base; cs.n_samples = p.n_samples;
                         cs.ca.c01 = make_float2(entry[0], entry[1]); cs.ca.c2 = entry[2]; cs.ca.c3 = entry[3];
                         cs.ca.fired = 0u;
+                        cs.ca.tb = 1.f;
                         if (PARTIAL) cs.ca.fired = __float_as_uint(entry[4]);
+                        if (ERT) { cs.ca.tb = entry[5]; cs.dt_scale = smp.dt_scale; }
                         // reload geometry and ray so that nothing of them stays live across the fast walk
                         BrickGeom g2;
                         load_geom(g2, br);
@@ -993,7 +1032,11 @@ cast_kernel(const __grid_constant__ CastParams p)
                 }
             }
         }
-        __syncthreads();
+        if constexpr (ERT) {
+            if (__syncthreads_and(!active || smp.ca.tb < p.ert_eps)) break;   // every ray of the tile is finished
+        } else {
+            __syncthreads();
+        }
     }
 
     // ---- write back ---------------------------------------------------------------------------------
@@ -1002,6 +1045,25 @@ cast_kernel(const __grid_constant__ CastParams p)
     if constexpr (EXACT) {
 #pragma unroll
         for (int c = 0; c < 4; c++) { out[c] = smp.acc[c]; Bout[c] = smp.B64[c]; }
+    } else if (ERT) {
+        // (A, B) of everything composited, front to back; B counts as 0 once the ray was cut (what it hides stays hidden)
+        const float b = smp.ca.tb;
+        out[0] = (double)smp.ca.c01.x; out[1] = (double)smp.ca.c01.y; out[2] = (double)smp.ca.c2; out[3] = (double)smp.ca.c3;
+        Bout[0] = Bout[1] = Bout[2] = Bout[3] = (double)b;
+        if (!PARTIAL) {
+            const double4 c0 = *reinterpret_cast<const double4 *>(p.image + pix * 4);
+            if (b == 1.f && smp.ca.c3 == 0.f && smp.ca.c01.x == 0.f && smp.ca.c01.y == 0.f && smp.ca.c2 == 0.f) {
+                out[0] = c0.x; out[1] = c0.y; out[2] = c0.z; out[3] = c0.w;   // untouched pixel: bit-identical
+            } else {
+                out[0] = fma((double)b, c0.x, out[0]); out[1] = fma((double)b, c0.y, out[1]);
+                out[2] = fma((double)b, c0.z, out[2]); out[3] = fma((double)b, c0.w, out[3]);
+            }
+        }
+        // cells sampled by this warp's rays
+        unsigned n = smp.cells;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) n += __shfl_xor_sync(wmask, n, sft);
+        if (p.counters != nullptr && lane == (__ffs(wmask) - 1) && n) atomicAdd(p.counters + 1, (unsigned long long)n);
     } else if (KIND == KIND_VR) {
         if (tfm_is_colour(TFM)) {
             smp.rgba[0] = smp.ca.c01.x; smp.rgba[1] = smp.ca.c01.y; smp.rgba[2] = smp.ca.c2; smp.rgba[3] = smp.ca.c3;
@@ -1047,6 +1109,7 @@ cast_kernel(const __grid_constant__ CastParams p)
     }
 }
 
+#ifndef YTB_CAST_KERNEL_ONLY   // (ert.cu instantiates cast_kernel only: the kernels below have one home, ytb200.cu)
 // Counting pass: the same traversal, `hit` summed over rays (VR excludes masked cells).
 struct CountSampler {
     const unsigned char *mask;
@@ -1522,5 +1585,7 @@ __global__ void fill_f64_kernel(double *dst, double v, long long n)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = v;
 }
+
+#endif  // YTB_CAST_KERNEL_ONLY
 
 }  // namespace ytb

@@ -104,7 +104,11 @@ struct CastParams {
     unsigned long long *tail_flag;
     unsigned long long tail_seq;
     DevTF tf;
-    unsigned long long *counters;  // [0] cells handed to sample()
+    unsigned long long *counters;  // [0] cells handed to sample(); [1] cells the early-termination cast sampled
+    // Early ray termination (ert.cu; grey-opacity ColorTransferFunction only): > 0 selects the REVERSED cast -- the order
+    // list arrives reversed and every ray is walked from its far end, compositing front to back, until the transmittance
+    // of everything processed so far drops below ert_eps (see cast_kernel<..., ERT>)
+    float ert_eps;
 };
 
 }  // namespace ytb

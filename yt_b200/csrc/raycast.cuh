@@ -551,6 +551,7 @@ __device__ __forceinline__ bool rows_from_raw(CornersP &c, const RawCorners &r, 
 struct ColourAcc {
     float2 c01; float c2, c3;
     unsigned fired;
+    float tb;   // ERT casts only: transmittance of the samples composited so far (front to back), see colour_cell_run
 };
 
 // All n_samples samples of one cell: trilinear value -> 4-table lookup -> composite
@@ -564,7 +565,10 @@ struct ColourAcc {
 //   * rejected samples (out of bounds, NaN, inf) are steered between the two zero rows by ONE select on
 //     the row coordinate instead of selects on fraction and alpha; exact zeros are rejected per cell;
 //   * CLAMP=false drops the max(1 - dt*T, 0) clamps when the caller proved dt*T <= 1 for the cell.
-template <bool PARTIAL, bool GREY, bool CLAMP, bool EDGE, bool DELTA>
+// ERT (grey opacity only): the samples arrive in REVERSE composition order (the last sample the reference composites
+// comes first), so the affine maps are applied front to back -- A <- A + B e, B <- B a, field_interpolation_tables.pxd:
+// 103-110 read from the other end -- and B is the transmittance the termination test looks at.
+template <bool PARTIAL, bool GREY, bool CLAMP, bool EDGE, bool DELTA, bool ERT = false>
 __device__ __forceinline__ float colour_cell_run(const CornersP &c, const ColourTable &ct, int n_samples, float x, float y, float z,
                                                 float sx, float sy, float sz, float dt, ColourAcc &A)
 {
@@ -599,7 +603,14 @@ __device__ __forceinline__ float colour_cell_run(const CornersP &c, const Colour
         const float adt = ba.y * dt;                   // dt * alpha-table value
         const float2 e01 = mul2(rg, bcast2(adt));      // dt * T_r, dt * T_g (RGB weighted by alpha)
         const float e2 = ba.x * adt;
-        if (GREY) {
+        if (GREY && ERT) {
+            float ta = 1.f - adt;
+            if (CLAMP) ta = fmaxf(ta, 0.f);
+            A.c01 = fma2(bcast2(A.tb), e01, A.c01);
+            A.c2 = fmaf(A.tb, e2, A.c2);
+            A.c3 = fmaf(A.tb, adt, A.c3);
+            A.tb *= ta;
+        } else if (GREY) {
             float ta = 1.f - adt;
             if (CLAMP) {
                 if (PARTIAL && ta < 0.f) A.fired |= 15u;
@@ -672,7 +683,7 @@ __device__ __forceinline__ float colour_cell_run(const CornersP &c, const Colour
 
 // One sample on the careful path: `fs` is the row coordinate (0.5 if the sample was rejected); same table
 // lookup and compositing as colour_cell_run, with the clamps always on.
-template <bool PARTIAL, bool GREY>
+template <bool PARTIAL, bool GREY, bool ERT = false>
 __device__ __forceinline__ void colour_sample(const ColourTable &ct, float fs, float dt, ColourAcc &A)
 {
     const float t = __fadd_rd(fs, COLOUR_MAGIC);
@@ -685,7 +696,11 @@ __device__ __forceinline__ void colour_sample(const ColourTable &ct, float fs, f
     const float r = fmaf(fr, t1.x, t0.x), g = fmaf(fr, t1.y, t0.y), b = fmaf(fr, t1.z, t0.z);
     const float adt = fmaf(fr, t1.w, t0.w) * dt;
     const float e0 = r * adt, e1 = g * adt, e2 = b * adt;
-    if (GREY) {
+    if (GREY && ERT) {
+        const float ta = fmaxf(1.f - adt, 0.f);
+        A.c01.x = fmaf(A.tb, e0, A.c01.x); A.c01.y = fmaf(A.tb, e1, A.c01.y); A.c2 = fmaf(A.tb, e2, A.c2); A.c3 = fmaf(A.tb, adt, A.c3);
+        A.tb *= ta;
+    } else if (GREY) {
         if (PARTIAL && 1.f - adt < 0.f) A.fired |= 15u;
         const float ta = fmaxf(1.f - adt, 0.f);
         A.c01.x = fmaf(ta, A.c01.x, e0); A.c01.y = fmaf(ta, A.c01.y, e1); A.c2 = fmaf(ta, A.c2, e2); A.c3 = fmaf(ta, A.c3, adt);

@@ -16,6 +16,7 @@
 
 #include "cast_kernels.cuh"
 #include "octree_cast.cuh"
+#include "ert.h"
 #include "proj.h"
 
 using namespace ytb;
@@ -99,6 +100,7 @@ struct ytb200_frame {
     std::vector<int> order_host;
     bool image_is_host = false;      // f->image currently aliases a page-locked host array (ytb200_render, in place)
     uint64_t order_generation = 0;   // ytb200_brickset::generation the cached order / footprints belong to (0: none)
+    float ert_eps = 0.f;             // > 0: grey-opacity colour casts run the early-termination cast (ytb200_frame_set_early_termination)
 };
 
 struct DeviceGuard {
@@ -858,6 +860,15 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
     cudaStream_t st = f->ctx->stream;
     int launches = 0;
     if (stats) CK(cudaEventRecord(f->ctx->ev0, st));
+    // early ray termination: the composition order is walked from its far end, so the list goes in reversed
+    const bool ert = f->ert_eps > 0.f && kind == YTB200_VOLUME_RENDER && !exact && set->n_fields == 1 && set->storage == YTB200_STORE_F32 &&
+                     tf->d.colour_fast && tf->d.grey && !tf->d.light_on;
+    std::vector<int64_t> reversed;
+    if (ert && n_order > 1) {
+        reversed.assign(order, order + n_order);
+        std::reverse(reversed.begin(), reversed.end());
+        order = reversed.data();
+    }
     int rc = prepare_order(f, set, order, n_order, &launches);
     if (rc) return rc;
     if (n_order > 0 || partial) {
@@ -883,7 +894,12 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
             else if (colour) smem = ((size_t)tf->d.colour_rows << tf->d.colour_copy_shift) * sizeof(float4) * (tf->d.colour_delta ? 2 : 1);
             else smem = (size_t)tf->d.total_bins * sizeof(float2);
             if (smem > 200 * 1024) return fail(E_UNSUPPORTED, "transfer function tables (%zu B) exceed shared memory", smem);
-            if (colour) {
+            if (colour && ert) {
+                p.ert_eps = f->ert_eps;
+                if (stats) CK(cudaMemsetAsync(f->ctx->counters + 1, 0, sizeof(unsigned long long), st));
+                e = launch_ert(p, grid, smem, (tf->d.colour_zero_inside ? TFM_ZERO_INSIDE : 0) | (tf->d.colour_edge ? TFM_EDGE : 0),
+                               partial != nullptr, p.n_order > 32, st);
+            } else if (colour) {
                 const int mode = (tf->d.grey ? TFM_GREY : 0) | (tf->d.colour_zero_inside ? TFM_ZERO_INSIDE : 0) | (tf->d.colour_edge ? TFM_EDGE : 0);
                 const bool pt = partial != nullptr;
                 switch (mode) {
@@ -918,7 +934,23 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
         stats->n_launches = launches;
         stats->n_cells = 0;
         stats->n_samples = 0;
+        if (ert && (n_order > 0 || partial)) {
+            // cells the terminated rays actually sampled (the algorithmic count is ytb200_frame_count's)
+            unsigned long long done = 0;
+            CK(cudaMemcpyAsync(&done, f->ctx->counters + 1, sizeof(done), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            stats->n_cells = (int64_t)done;
+            stats->n_samples = (int64_t)done * (n_samples < 1 ? 1 : n_samples);
+        }
     }
+    return 0;
+}
+
+extern "C" int ytb200_frame_set_early_termination(ytb200_frame *f, double eps)
+{
+    if (!f) return fail(E_ARG, "frame is NULL");
+    if (!(eps >= 0.0) || eps >= 1.0) return fail(E_ARG, "early termination threshold %g not in [0, 1)", eps);
+    f->ert_eps = (float)eps;
     return 0;
 }
 

@@ -236,6 +236,11 @@ class Frame:
             zbuffer.ctypes.data if (image is not None and zbuffer is not None) else None))
         self._bound = (image, zbuffer)
 
+    def set_early_termination(self, eps):
+        """Early ray termination for grey-opacity ColorTransferFunction renders (``ytb200_frame_set_early_termination``);
+        0 disables."""
+        L.check(L.load().ytb200_frame_set_early_termination(self.handle, float(eps)))
+
     def _order(self, order):
         o = np.ascontiguousarray(order, dtype=np.int64)
         return o, o.ctypes.data_as(L.i64p), int(o.shape[0])

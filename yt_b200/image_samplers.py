@@ -13,6 +13,8 @@ All compute is in libytb200.so (CUDA, sm_100a).  There is no CPU path here.
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from . import _lib as L
@@ -21,7 +23,10 @@ from .partitioned_grid import PartitionedGrid, build_brickset
 
 #: module-wide defaults; "f32"/"fast" is the product path, "f64"/"exact" reproduces the
 #: reference's fp64 evaluation order bit-for-bit (validation mode).
-config = {"storage": "f32", "precision": "fast"}
+#: "early_termination": threshold of the early-ray-termination cast (ours; 0 = off, the default): grey-opacity
+#: ColorTransferFunction renders stop a ray once what it has composited -- walking the reference's composition order
+#: from its far end -- transmits less than this (``ytb200_frame_set_early_termination``).  ``YTB200_ERT`` overrides.
+config = {"storage": "f32", "precision": "fast", "early_termination": 0.0}
 
 _STORAGE = {"f32": L.STORE_F32, "f64": L.STORE_F64}
 _PRECISION = {"fast": L.PREC_FAST, "exact": L.PREC_EXACT}
@@ -75,6 +80,7 @@ class ImageSampler:
         self._ctx = kwargs.pop("context", None) or D.get_context()
         self._storage = _STORAGE[kwargs.pop("storage", config["storage"])]
         self._precision = _PRECISION[kwargs.pop("precision", config["precision"])]
+        self._ert = float(os.environ.get("YTB200_ERT", kwargs.pop("early_termination", config["early_termination"])) or 0.0)
         nx, ny = image.shape[0], image.shape[1]
         if self.lens_type == "plane-parallel":
             lens = L.LENS_PLANE_PARALLEL
@@ -129,6 +135,8 @@ class ImageSampler:
             for i in range(15):
                 cam.camera_data[i] = cd[i]
         self._frame = D.Frame(self._ctx, cam, keep=tuple(keep))
+        if self._ert > 0.0:
+            self._frame.set_early_termination(self._ert)
         self._pending = []         # PartitionedGrids recorded by __call__, in call order
         self._batches = []         # (brickset, order) recorded by cast_bricks
         self._dirty = False
