@@ -279,6 +279,8 @@ def test_grey_opacity_frames_match_the_reference_on_a_ray_lattice(opacity, gpu):
     want, label = reference_on_lattice("vr", cam, args, ii, jj, N, lambda x0, x1: vol[x0:x1 + 1].cpu().numpy().astype("float64"), 1,
                                        tf=tf, n_samples=N_SAMPLES)
     for ert in (0.0, 1e-6):
+        args, kw = T.sampler_args(cam)      # a fresh (zeroed) image: the sampler composites onto what it is given
+        kw.pop("camera_data")
         s = S.VolumeRenderSampler(*args, tf, N_SAMPLES, early_termination=ert, **kw)
         bs = D.BrickSet(s._ctx, 1, 1, L.VERTEX_CENTRED, L.STORE_F32)
         bs.attach(0, [vol.data_ptr()], 0, [0.0] * 3, [1.0] * 3, [N] * 3, keep=vol)

@@ -1,8 +1,3 @@
-mkdir -p gpurun_out/r02p
-timeout 1200 python -m pytest tests -m gpu -x -q -s 2>&1 | grep -v "^$" | tail -25 > gpurun_out/r02p/pytest_gpu.log; cat gpurun_out/r02p/pytest_gpu.log
-timeout 300 python tools/bench_ert.py > gpurun_out/r02p/bench_ert.json 2> gpurun_out/r02p/bench_ert.err; cat gpurun_out/r02p/bench_ert.json; tail -5 gpurun_out/r02p/bench_ert.err
-for W in northstar_vr_1024c_2048px cfg4_amr_vr_15kbricks_persp_2048px cfg4_amr_vr_24kbricks_persp_2048px; do
-  timeout 300 python bench.py --workload $W --no-cpu --steps 5 > gpurun_out/r02p/bench_$W.json 2> gpurun_out/r02p/bench_$W.err
-  python -c "
-import json; d=json.loads(open('gpurun_out/r02p/bench_$W.json').read().strip().splitlines()[-1]); print('$W N=1 step %.3f e2e %.3f kernel %.3f' % (d['ms_per_step'], d['e2e']['ms_per_frame'], d['roofline']['kernel_ms']))" || tail -5 gpurun_out/r02p/bench_$W.err
-done
+mkdir -p gpurun_out/r02s
+timeout 1200 python -m pytest tests/test_fullsize_oracle_gpu.py tests/test_ert_gpu.py -m gpu -x -q -s 2>&1 | grep -v "^$" | tail -25 > gpurun_out/r02s/pytest_gpu.log; cat gpurun_out/r02s/pytest_gpu.log
+true

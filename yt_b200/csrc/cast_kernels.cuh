@@ -801,6 +801,7 @@ cast_kernel(const __grid_constant__ CastParams p)
     // instead of in 12 registers per thread
     __shared__ double s_ray[(MANY ? 9 : 6) * CTA_THREADS];
     __shared__ int4 s_ext[MANY ? LIST_CAP : 1];
+    __shared__ __align__(8) unsigned long long s_table_bar;   // mbarrier of the transfer-table bulk copy
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -848,16 +849,19 @@ cast_kernel(const __grid_constant__ CastParams p)
         if (KIND == KIND_VR && tfm_is_colour(TFM)) {
             // replicate each row COLOUR_COPIES times: copy k sits in 16-byte bank group k (rows are already
             // padded with the zero / duplicate rows by ytb200_tf_create)
+            // (delta layout: row = [8 copies of the values | 8 copies of the increments].)  The replicated image is
+            // kept in global memory (ytb200_tf_create) and arrives by ONE bulk async copy issued by thread 0 -- the TMA
+            // engine moves the 64 KiB while the CTA generates its rays and reads its pixels; every thread waits on the
+            // mbarrier right before the walk.
             float4 *sc = reinterpret_cast<float4 *>(smem_raw);
-            const int nrows = p.tf.colour_rows;
-            if (p.tf.colour_delta) {
-                // row = [8 copies of the values | 8 copies of the increments]
-                for (int i = tid; i < nrows * 2 * COLOUR_COPIES; i += CTA_THREADS) {
-                    const int r = i / (2 * COLOUR_COPIES), h = (i / COLOUR_COPIES) & 1;
-                    sc[i] = p.tf.colour[2 * r + h];
-                }
-            } else {
-                for (int i = tid; i < nrows * COLOUR_COPIES; i += CTA_THREADS) sc[i] = p.tf.colour[i / COLOUR_COPIES];
+            if (tid == 0) {
+                const unsigned bytes = ((unsigned)p.tf.colour_rows * COLOUR_COPIES * (unsigned)sizeof(float4)) * (p.tf.colour_delta ? 2u : 1u);
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_table_bar);
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"((unsigned)__cvta_generic_to_shared(sc)), "l"(p.tf.colour_image), "r"(bytes), "r"(bar) : "memory");
             }
             // colour_cell_run forms the address as float_as_int(2^23 + row) * ROW_BYTES + base: fold the
             // (wrapping) bias of the exponent bits into base
@@ -912,6 +916,12 @@ cast_kernel(const __grid_constant__ CastParams p)
     }
     smp.n_samples = p.n_samples;
     __syncthreads();
+    if constexpr (!EXACT && KIND == KIND_VR && tfm_is_colour(TFM)) {
+        // the table image has landed (phase 0 of the mbarrier completes when the copy's bytes have)
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_table_bar);
+        asm volatile("{\n\t.reg .pred p;\n\tTABLE_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra TABLE_DONE;\n\t"
+                     "bra TABLE_WAIT;\n\tTABLE_DONE:\n\t}" :: "r"(bar) : "memory");
+    }
 
     // ---- walk the ordered brick list; cull bricks whose pixel footprint misses this tile ----
     const int ti1 = ti0 + TILE_I, tj1 = tj0 + TILE_J;

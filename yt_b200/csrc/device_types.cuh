@@ -61,6 +61,8 @@ struct DevTF {
     // colour_fast payload: (r,g,b,a) rows [0, 0, y_0 .. y_{n-1}, y_{n-1}]; replicated 2^colour_copy_shift times in smem
     const float4 *colour;
     int colour_copy_shift;
+    // the same rows as a cast CTA holds them in shared memory (every row 2^colour_copy_shift times): one bulk async copy
+    const float4 *colour_image;
     // row-coordinate constants of the colour fast path (see ColourTable in raycast.cuh); they stay in the
     // kernel-parameter constant bank instead of in registers
     float colour_c0, colour_clamp_bound, colour_lo, colour_hi, colour_mid, colour_half, colour_band, colour_zrow;

@@ -588,6 +588,12 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
             d.colour_rows = nb + COLOUR_PAD_ROWS;
         }
         rc |= to_device(t, col, &d.colour);
+        {
+            // the shared-memory image of the table, staged by a cast CTA with ONE bulk async copy (cp.async.bulk)
+            std::vector<float4> image(col.size() * COLOUR_COPIES);
+            for (size_t i = 0; i < image.size(); i++) image[i] = col[i / COLOUR_COPIES];
+            rc |= to_device(t, image, &d.colour_image);
+        }
         // every row is replicated 8x in shared memory (bank-conflict-free): 64.4 KiB (value layout, 512 bins)
         // or 64.5 KiB (delta layout, 256 bins)
         d.colour_copy_shift = 3;
