@@ -787,14 +787,16 @@ constexpr int SWAP_MAX_DST = 8;
 struct SwapSignal { unsigned long long *flag[SWAP_MAX_DST]; int n; };
 
 // Called by EVERY thread of EVERY CTA as the last thing a kernel does: when all CTAs have passed, the last one writes
-// `seq` into the flag words (which may live in a peer's memory).  One system-scope fence per CTA, by thread 0 AFTER the
-// barrier (the barrier orders the CTA's stores before the fence, the fence is cumulative -- the grid-sync idiom); a fence
-// per thread cost 0.27 ms on a 2048^2 frame (r02j vs r02k: 5.80 against 5.54 ms for the same sub-volume).
+// `seq` into the flag words (which may live in a peer's memory).  One fence per CTA, by thread 0 AFTER the barrier (the
+// barrier orders the CTA's stores before the fence, the fence is cumulative -- the grid-sync idiom); a fence per thread
+// cost 0.27 ms on a 2048^2 frame (r02j vs r02k: 5.80 against 5.54 ms for the same sub-volume).  The per-CTA fence is
+// DEVICE scope: it orders the CTA's stores before its count at the L2, which is where a peer's NVLink reads arrive; the
+// one CTA that counts last raises that to system scope before it publishes the flag.
 __device__ __forceinline__ void grid_tail_signal(unsigned *counter, const SwapSignal &sg, unsigned long long seq)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        __threadfence();
         const unsigned total = gridDim.x * gridDim.y * gridDim.z;
         if (atomicAdd(counter, 1u) == total - 1u) {
             *counter = 0u;   // the next kernel that counts on it is stream-ordered after this one
