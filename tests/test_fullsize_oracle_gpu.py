@@ -290,3 +290,36 @@ def test_grey_opacity_frames_match_the_reference_on_a_ray_lattice(opacity, gpu):
         err = T.normalised_diff(sub, want, True)
         print("grey opacity x%g, early termination %g vs %s: normalised max diff %.3g" % (opacity, ert, label, err))
         assert err <= 1e-4
+
+
+def test_interpolated_projection_matches_the_reference_on_a_ray_lattice(gpu):
+    """InterpolatedProjectionSampler over the north-star volume (bench workload iproj_1024c_2048px): fp32 cell sums on the
+    corner-reuse walk, fp64 accumulation, against the reference's fp64 samples; bar rtol 1e-6 of the largest integral."""
+    import torch
+    from bench import N_SAMPLES, bench_camera
+    from yt_b200 import _lib as L
+    from yt_b200 import device as D
+    from yt_b200 import image_samplers as S
+    from yt_b200 import synthetic
+    N, R = 1024, 2048
+    _need_memory(12)
+    dev = torch.device("cuda", gpu.device)
+    cam = bench_camera(R)
+    args, kw = T.sampler_args(cam)
+    kw.pop("camera_data")
+    s = S.InterpolatedProjectionSampler(*args, N_SAMPLES, **kw)
+    vol = synthetic.vertex_slab(N, [0, 0, 0], [N, N, N], SEED, dev)
+    bs = D.BrickSet(s._ctx, 1, 1, L.VERTEX_CENTRED, L.STORE_F32)
+    bs.attach(0, [vol.data_ptr()], 0, [0.0] * 3, [1.0] * 3, [N] * 3, keep=vol)
+    bs.commit()
+    _torch_done()
+    s.cast_bricks(bs, np.arange(1, dtype=np.int64))
+    got = np.array(s.aimage)
+    ii, jj = _lattice(R), _lattice(R)[::-1].copy()
+    want, label = reference_on_lattice("iproj", cam, args, ii, jj, N, lambda x0, x1: vol[x0:x1 + 1].cpu().numpy().astype("float64"), 1,
+                                       n_samples=N_SAMPLES)
+    sub = got[np.ix_(ii, jj)]
+    err = np.abs(sub[:, :, 0] - want[:, :, 0]).max() / np.abs(want[:, :, 0]).max()
+    print("iproj vs %s on a %dx%d ray lattice: max diff / max %.3g" % (label, len(ii), len(jj), err))
+    assert np.abs(want[:, :, 0]).max() > 0
+    assert err <= 1e-6

@@ -96,6 +96,7 @@ struct CastParams {
     int n_order;
     int n_samples;
     double inv_ns;          // 1 / n_samples
+    float iproj_s0, iproj_s1, iproj_s2, iproj_s3;   // sum over s = 0 .. n_samples-1 of s^0, s^1, s^2, s^3 (interpolated projection)
     double *image;          // (nx,ny,4) fp64, in/out
     const double *zbuffer;  // (nx,ny) fp64 or nullptr (== ones)
     double *partial;        // affine-map output in format `partial_fmt` (see PartialFormat), or nullptr

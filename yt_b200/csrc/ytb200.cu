@@ -883,6 +883,10 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
         p.bricks = set->dev; p.order = f->order_dev; p.extent = f->extent_dev; p.chunk_extent = f->extent_dev + f->order_cap; p.n_order = (int)n_order;
         p.n_samples = n_samples < 1 ? 1 : n_samples;
         p.inv_ns = 1.0 / (double)p.n_samples;
+        {
+            const double nn = (double)p.n_samples, s1 = 0.5 * nn * (nn - 1.0);
+            p.iproj_s0 = (float)nn; p.iproj_s1 = (float)s1; p.iproj_s2 = (float)(nn * (nn - 1.0) * (2.0 * nn - 1.0) / 6.0); p.iproj_s3 = (float)(s1 * s1);
+        }
         p.image = f->image; p.zbuffer = f->zbuffer; p.partial = partial; p.partial_fmt = partial_fmt;
         p.tail_counter = tail_counter; p.tail_flag = tail_flag; p.tail_seq = tail_seq;
         if (partial && f->zbuffer_in) p.zbuffer = f->zbuffer_in;
