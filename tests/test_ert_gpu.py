@@ -121,3 +121,29 @@ def test_terminated_partials_compose_like_the_plain_cast(height, gpu):
     L.check(lib.ytb200_partial_apply(ctx.handle, bufs[0].data_ptr(), fr.device_image, npx))
     got = fr.download(np.empty_like(img))
     assert T.normalised_diff(got, want, True) <= 1e-4
+
+
+@pytest.mark.parametrize("height", [60.0, 30000.0])
+def test_terminated_cast_through_the_swap_object(height, gpu):
+    """The compact partial format of the grey render (fp32 A only, B = 1 - A_alpha or 0 where a clamp fired) must carry
+    the terminated cast's map too: there B is tracked explicitly and A_alpha = 1 - B by construction."""
+    from yt_b200 import _lib as L
+    from yt_b200.parallel import PeerSwap, partial_format
+    base = {s.name: s for s in T.scenarios()}
+    sc = copy.copy(base["vr_8bricks_perspective_grey"])
+    sc.tf = T.colour_tf(grey=True, height=height)
+    nx, ny = sc.cam.resolution
+    sc.image0 = np.random.RandomState(6).uniform(0, 0.4, size=(nx, ny, 4))
+    want = T.run_scenario(sc, O, O, num_threads=0)
+    s, bs, img = _sampler(sc, EPS)
+    fr = s._frame
+    fmt = partial_format(s.kind, s._tables, bs.n_fields)
+    assert fmt == L.PARTIAL_A32G
+    swap = PeerSwap(s._ctx, fr, [], sc.cam.lens.viewpoint, 0, 1, fmt=fmt)
+    for _ in range(2):
+        fr.upload(img, s.azbuffer)
+        swap.cast(fr, s.kind, bs, np.array(sc.order, dtype=np.int64), tf=s._tables, n_samples=s.n_samples)
+        swap.composite(fr)
+        swap.check()
+        got = fr.download(np.empty_like(img))
+        assert T.normalised_diff(got, want, True) <= 1e-4

@@ -34,7 +34,9 @@
 namespace ytb {
 
 #ifndef YTB_PROJ_UNROLL
-#define YTB_PROJ_UNROLL 2      // slabs per group: 3 * UNROLL loads of one ray per register stage
+#define YTB_PROJ_UNROLL 3      // slabs per group: 3 * UNROLL loads of one ray per register stage
+                               // r02w/r02x A/B on cfg3 (3 CTAs/SM unless noted): U=2 2.22 ms, U=3 1.99 ms (80 registers, 32 B
+                               // spilled), U=4 2.11; U=2 at 4 CTAs/SM (64 registers) 2.02, U=3 there 2.02, U=6 at 2 CTAs/SM 1.99
 #endif
 #ifndef YTB_PROJ_MINB
 #define YTB_PROJ_MINB 3        // resident CTAs per SM the register allocation is bounded for
