@@ -66,7 +66,13 @@ struct DevTF {
     // row-coordinate constants of the colour fast path (see ColourTable in raycast.cuh); they stay in the
     // kernel-parameter constant bank instead of in registers
     float colour_c0, colour_clamp_bound, colour_lo, colour_hi, colour_mid, colour_half, colour_band, colour_zrow;
-    float colour_clamp_hi;   // delta layout: row coordinates are clamped to [0.5, nbins + 1.5]
+    float colour_clamp_hi;   // delta layout: row coordinates are clamped to [colour_clamp_lo, colour_clamp_hi] = [0.5, nbins + 1.5] - origin
+    // LINE form of the delta layout (colour_line, decided per table at ytb200_tf_create): a row holds (c, d) with the bin's
+    // line written in the row coordinate itself, y = d * fs + c, so the lerp needs no fractional part.  Every row coordinate
+    // of the fast path is then measured from `origin` (an integer, folded into colour_c0): clamps and the round-down magic
+    // constant move with it (colour_magic = 2^23 + origin, so the mantissa bits still hold the true row index).
+    float colour_clamp_lo, colour_magic;
+    int colour_line;
     int colour_zero_inside, colour_edge, colour_delta, colour_rows, colour_nonneg;
     // LightSourceRenderSampler (image_samplers.pyx:496-600): one directional light, gradient shading
     int light_on;

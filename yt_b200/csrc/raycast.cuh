@@ -601,7 +601,8 @@ struct ColourAcc {
 // ERT (grey opacity only): the samples arrive in REVERSE composition order (the last sample the reference composites
 // comes first), so the affine maps are applied front to back -- A <- A + B e, B <- B a, field_interpolation_tables.pxd:
 // 103-110 read from the other end -- and B is the transmittance the termination test looks at.
-template <bool PARTIAL, bool GREY, bool CLAMP, bool EDGE, bool DELTA, bool ERT = false>
+// LINE (delta layout only; no EDGE): the rows hold (c, d) of y = d * fs + c in the (origin-shifted) row coordinate, see DevTF.
+template <bool PARTIAL, bool GREY, bool CLAMP, bool EDGE, bool DELTA, bool ERT = false, bool LINE = false>
 __device__ __forceinline__ float colour_cell_run(const CornersP &c, const ColourTable &ct, int n_samples, float x, float y, float z,
                                                 float sx, float sy, float sz, float dt, ColourAcc &A)
 {
@@ -615,10 +616,18 @@ __device__ __forceinline__ float colour_cell_run(const CornersP &c, const Colour
         // EDGE: keep the smallest distance to a bound of the cell; the caller compares it with the fp32 error band.
         if (EDGE) closest = fminf(closest, fabsf(fabsf(fb - ct.tf->colour_mid) - ct.tf->colour_half));
         float2 rg, ba;
-        if (DELTA) {
-            const float fs = fminf(fmaxf(fb, 0.5f), ct.tf->colour_clamp_hi);   // rejected samples land on zero rows
-            const float t = __fadd_rd(fs, COLOUR_MAGIC);   // 2^23 + floor(fs)
-            const float fr = fs - (t - COLOUR_MAGIC);
+        if (DELTA && LINE) {
+            const float fs = fminf(fmaxf(fb, ct.tf->colour_clamp_lo), ct.tf->colour_clamp_hi);   // rejected samples land on zero rows
+            const float t = __fadd_rd(fs, ct.tf->colour_magic);   // 2^23 + floor(fs + origin)
+            const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_DELTA_ROW_BYTES + ct.base;
+            const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
+            const float2 fs2 = bcast2(fs);
+            rg = fma2(fs2, make_float2(t1.x, t1.y), make_float2(t0.x, t0.y));
+            ba = fma2(fs2, make_float2(t1.z, t1.w), make_float2(t0.z, t0.w));
+        } else if (DELTA) {
+            const float fs = fminf(fmaxf(fb, ct.tf->colour_clamp_lo), ct.tf->colour_clamp_hi);   // rejected samples land on zero rows
+            const float t = __fadd_rd(fs, ct.tf->colour_magic);   // 2^23 + floor(fs)
+            const float fr = fs - (t - ct.tf->colour_magic);
             const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_DELTA_ROW_BYTES + ct.base;
 #ifdef YTB_TABLE_F16INC
             const float4 t0 = lds128(addr);

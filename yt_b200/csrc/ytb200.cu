@@ -589,6 +589,55 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
             col[(size_t)nb + 2] = col[(size_t)nb + 1];
             d.colour_rows = nb + COLOUR_PAD_ROWS;
         }
+        // does a sample flipping across a bound change the result?  Only if the alpha table (which also
+        // weights R, G, B) does not vanish there.
+        const double edge = fmax(fabs(y[3][0]), fabs(y[3][nb - 1])) * fmax(1.0, rgb_max);
+        d.colour_edge = edge > 1e-30 ? 1 : 0;
+        d.colour_line = 0; d.colour_clamp_lo = 0.5f; d.colour_magic = COLOUR_MAGIC;
+        int origin = 0;
+        if (d.colour_delta && !d.colour_edge && !getenv("YTB200_NO_LINE")) {
+            // LINE form (DevTF): row r holds (c, d) with c = y - (r - origin) * d, so that y(fs) = d * (fs - origin) + c needs
+            // no fractional part (two instructions fewer per sample).  What it costs is accuracy: c is rounded to fp32 at a
+            // magnitude of up to |r - origin| * |d|, so the form is used only if EVERY bin keeps a relative accuracy of 4e-6 of
+            // its own mean magnitude (plus 1e-9 of the channel's maximum) -- computed here, per table, against the fp64
+            // table; a table that fails keeps the (value, increment) rows.  d is the fp32 increment as stored, so the product
+            // in c is exact and the error of a bin is |fl(c) - c| + |fl(d) - d| (the latter times the fractional position,
+            // <= 1).  The origin is the integer row that minimises the worst bin.
+            double cmax[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int c = 0; c < 4; c++)
+                for (int j = 0; j < nb; j++) cmax[c] = fmax(cmax[c], fabs(y[c][j]));
+            auto worst_bin = [&](int o, std::vector<float4> *out) {
+                double worst = 0.0;
+                for (int c = 0; c < 4; c++) {
+                    for (int j = 0; j + 1 < nb; j++) {
+                        const size_t r = (size_t)j + 2;
+                        const float df = (&col[2 * r + 1].x)[c];
+                        const double d64 = y[c][j + 1] - y[c][j];
+                        const double c64 = y[c][j] - ((double)r - (double)o) * (double)df;
+                        const float cf = (float)c64;
+                        if (out) { (&(*out)[2 * r].x)[c] = cf; (&(*out)[2 * r + 1].x)[c] = df; }
+                        const double abs_err = fabs((double)cf - c64) + fabs((double)df - d64);
+                        const double lim = 4e-6 * 0.5 * (fabs(y[c][j]) + fabs(y[c][j + 1])) + 1e-9 * cmax[c];
+                        if (!(abs_err <= lim)) worst = fmax(worst, lim > 0.0 ? abs_err / lim : 1e300);
+                        else if (lim > 0.0) worst = fmax(worst, abs_err / lim);
+                    }
+                }
+                return worst;
+            };
+            double best = 1e300;
+            for (int o = 2; o < nb + 2; o++) {
+                const double w = worst_bin(o, nullptr);
+                if (w < best) { best = w; origin = o; }
+            }
+            std::vector<float4> line(col.size(), make_float4(0.f, 0.f, 0.f, 0.f));
+            const bool ok = best <= 1.0 && worst_bin(origin, &line) <= 1.0;
+            if (ok) {
+                col.swap(line);
+                d.colour_line = 1;
+                d.colour_clamp_lo = 0.5f - (float)origin;
+                d.colour_magic = COLOUR_MAGIC + (float)origin;
+            } else origin = 0;
+        }
         rc |= to_device(t, col, &d.colour);
         {
             // the shared-memory image of the table, staged by a cast CTA with ONE bulk async copy (cp.async.bulk)
@@ -614,18 +663,14 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
         const double b0 = bounds[0], b1 = bounds[1];
         const double idbin = d.idbin[0];
         // fb = (val - b0_hi) * idbin + c0 with c0 = 2 - b0_lo * idbin  (== (val - b0) * idbin + 2)
-        d.colour_c0 = (float)(2.0 - (b0 - (double)d.b0_hi[0]) * idbin);
+        d.colour_c0 = (float)(2.0 - (b0 - (double)d.b0_hi[0]) * idbin - (double)origin);
         // every product that meets dt before a clamp: alpha (grey) or alpha * colour (RGB weighted by alpha)
         d.colour_clamp_bound = (float)(1.0000002 * a_max * fmax(1.0, rgb_max));
         d.colour_zero_inside = (b0 < 0.0 && b1 > 0.0) ? 1 : 0;
         d.colour_nonneg = 1;   // alpha never negative: a ray's alpha accumulator keeps its sign bit free (PF_A32G)
         for (int j = 0; j < nb; j++) if (!(y[3][j] >= 0.0)) d.colour_nonneg = 0;
-        // does a sample flipping across a bound change the result?  Only if the alpha table (which also
-        // weights R, G, B) does not vanish there.
-        const double edge = fmax(fabs(y[3][0]), fabs(y[3][nb - 1])) * fmax(1.0, rgb_max);
-        d.colour_edge = edge > 1e-30 ? 1 : 0;
         d.colour_lo = 2.f; d.colour_hi = (float)(nb + 1);
-        d.colour_clamp_hi = (float)nb + 1.5f;
+        d.colour_clamp_hi = (float)nb + 1.5f - (float)origin;
         d.colour_mid = 0.5f * (float)(nb + 3); d.colour_half = 0.5f * (float)(nb - 1);
         d.colour_band = 4e-6f * (float)(nb + 512);
         // row coordinate of the value 0, with the very operations load_corners_rows applies to a corner
