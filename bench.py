@@ -582,7 +582,8 @@ def run_ours(args):
         "e2e": {"value": gs_e2e, "unit": "Gsamples/s", "ms_per_frame": ms_e2e,
                 "h2d_bytes_per_step": res * res * 40 if not peer else res * res * 8 * world + res * res * 32,
                 "d2h_bytes_per_step": res * res * 32,
-                "note": ("host (page-locked) image+zbuffer in, host image out through ytb200_render: the cast kernel reads/writes the host arrays in place over PCIe; bricks device-resident across frames" if world == 1 else "one page-locked image + z-buffer mapped into every rank: each rank reads max_t and its strip of the initial colours in place and stores its finished strip over its own PCIe link (ytb200_swap_composite_host); checked equal to the device-route image")},
+                "note": (("host (page-locked) image+zbuffer in, host image out through ytb200_render: staged in 8 row bands (copy-in, cast, copy-out overlapped on three streams); bricks device-resident across frames" if kind == "proj" else
+                          "host (page-locked) image+zbuffer in, host image out through ytb200_render: the cast kernel reads/writes the host arrays in place over PCIe; bricks device-resident across frames") if world == 1 else "one page-locked image + z-buffer mapped into every rank: each rank reads max_t in place, fetches its strip of the initial colours with the copy engine during the cast and sends its finished strip out with one bulk copy over its own PCIe link (ytb200_swap_composite_host); checked equal to the device-route image")},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk,
         "roofline": roofline_block(args.workload, kind, world, my_samples, kernel_ms, alg_bytes, clk, ctx.sm_count),

@@ -104,3 +104,48 @@ def test_many_bricks(lens, gpu):
 def test_camera_inside_the_brick(gpu):
     cam = T.make_camera("perspective", resolution=(40, 40), position=[0.55, 0.45, 0.6], focus=[0.1, 0.2, 0.0], width=[0.8, 0.8, 0.5])
     _compare(cam, [_brick((18, 18, 18), 31)], [0])
+
+
+@pytest.mark.parametrize("name", ["proj_offaxis_zbuf", "proj_corner", "proj_perspective"])
+def test_banded_render_equals_the_in_place_render(gpu, name, monkeypatch):
+    """ytb200_render stages a projection frame on page-locked arrays in row bands (copy-in, cast and copy-out of different
+    bands overlap on three streams): bit-identical to the one-launch render that touches the host arrays in place, with and
+    without a z-buffer, for odd image sizes (the last band is clipped) and with initial values in the image."""
+    import numpy as np
+    from oracle import oracle as O
+    from tests import common as T
+    from yt_b200 import device as D
+    from yt_b200 import image_samplers as S
+    from yt_b200 import partitioned_grid as G
+    from yt_b200.partitioned_grid import build_brickset
+    sc = [s for s in T.scenarios(small=False) if s.name == name][0]
+    nx, ny = sc.cam.resolution
+    assert nx >= 64                      # the banded route needs at least four tile rows
+    rng = np.random.RandomState(11)
+    image0 = rng.uniform(0, 2.0, size=(nx, ny, 4))
+    sc.image0 = image0
+    want = T.run_scenario(sc, O, O, num_threads=0)
+    outs = []
+    for banded in (True, False):
+        if banded:
+            monkeypatch.delenv("YTB200_NO_BANDS", raising=False)
+        else:
+            monkeypatch.setenv("YTB200_NO_BANDS", "1")
+        img = D.pinned_empty((nx, ny, 4))
+        img[:] = image0
+        zb = None
+        if sc.zbuffer is not None:
+            zb = D.pinned_empty((nx, ny))
+            zb[:] = sc.zbuffer
+        args, kwargs = T.sampler_args(sc.cam, zbuffer=zb, image=img)
+        kwargs.pop("camera_data")
+        s = S.ProjectionSampler(*args, sc.n_samples, **kwargs)
+        grids = [G.PartitionedGrid(i, list(b[0]), b[1], np.array(b[2], "float64"), np.array(b[3], "float64"), np.array(b[4], "int64"))
+                 for i, b in enumerate(sc.bricks)]
+        bs = build_brickset(grids, s._ctx, s._storage)
+        for _ in range(2):   # twice: the streams and events of the banded route are reused
+            img[:] = image0
+            s._frame.render(s.kind, bs, np.array(sc.order), img, zbuffer=zb, tf=None, n_samples=sc.n_samples)
+        outs.append(np.array(img, copy=True))
+    assert np.array_equal(outs[0], outs[1])
+    assert np.abs(outs[0] - want).max() <= 1e-6 * np.abs(want).max()

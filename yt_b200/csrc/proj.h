@@ -15,6 +15,7 @@ struct ProjMap {
     float slope;     // mode 1: shift along s per pixel along f, |slope| <= 1
     int s_lo;        // mode 1: s of row 0 of tile row 0 (<= 0: the shear needs rows above the image)
     int n_ftiles, n_stiles, band;   // tile grid and the number of s-tiles issued together (both modes)
+    int s_first;     // mode 0: the launch covers s-tiles [s_first, s_first + n_stiles) only (one row band of a staged frame)
 };
 
 // `first`: the first brick of the order list (its cell size fixes the dominant axis), or nullptr.

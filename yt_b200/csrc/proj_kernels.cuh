@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(CTA_THREADS, YTB_PROJ_MINB) proj_kernel(const 
     }
     int vi, vj, ti0, ti1, tj0, tj1;
     if (map.mode == 0) {
+        S += map.s_first;
         ti0 = S * TILE_I; tj0 = F * TILE_J;
         ti1 = ti0 + TILE_I; tj1 = tj0 + TILE_J;
         vi = ti0 + (warp >> 1) * 4 + (lane >> 3);

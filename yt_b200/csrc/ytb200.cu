@@ -103,6 +103,11 @@ struct ytb200_frame {
     bool image_is_host = false;      // f->image currently aliases a page-locked host array (ytb200_render, in place)
     uint64_t order_generation = 0;   // ytb200_brickset::generation the cached order / footprints belong to (0: none)
     float ert_eps = 0.f;             // > 0: grey-opacity colour casts run the early-termination cast (ytb200_frame_set_early_termination)
+    // staged, banded frames (ytb200_render of a projection): copy-in / copy-out streams and one event pair per band
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    cudaEvent_t ev_start = nullptr, ev_out = nullptr;
+    int band_first = 0, band_tiles = -1;   // s-tile range of the launch being issued (-1: the whole image)
 };
 
 struct DeviceGuard {
@@ -783,6 +788,12 @@ extern "C" int ytb200_frame_destroy(ytb200_frame *f)
     cudaStreamSynchronize(f->ctx->stream);
     cudaFree(f->image); cudaFree(f->zbuffer); cudaFree(f->pos_px); cudaFree(f->dir_px);
     cudaFree(f->order_dev); cudaFree(f->extent_dev);
+    if (f->s_in) cudaStreamDestroy(f->s_in);
+    if (f->s_out) cudaStreamDestroy(f->s_out);
+    for (cudaEvent_t e : f->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : f->ev_done) cudaEventDestroy(e);
+    if (f->ev_start) cudaEventDestroy(f->ev_start);
+    if (f->ev_out) cudaEventDestroy(f->ev_out);
     delete f;
     return 0;
 }
@@ -986,7 +997,8 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
             e = launch_kind<KIND_IPROJ, TFM_NONE>(p, grid, 0, st, exact, f64, partial != nullptr, nf1);
         } else if (!exact && !f64 && !getenv("YTB200_PROJ_DDA")) {
             // fp32 storage, FAST: the slab walk (proj_kernels.cuh); image_samplers.pyx:337-343 sums min(4, n_fields) fields
-            const ProjMap pm = make_proj_map(f->cam, n_order > 0 ? &set->host[(size_t)order[0]] : nullptr, f->image_is_host);
+            ProjMap pm = make_proj_map(f->cam, n_order > 0 ? &set->host[(size_t)order[0]] : nullptr, f->image_is_host || f->band_tiles >= 0);
+            if (f->band_tiles >= 0) { pm.s_first = f->band_first; pm.n_stiles = f->band_tiles; }
             e = launch_proj(p, pm, std::min(4, set->n_fields), partial != nullptr, st);
         } else {
             e = launch_kind<KIND_PROJ, TFM_NONE>(p, grid, 0, st, exact, f64, partial != nullptr, nf1);
@@ -1614,6 +1626,75 @@ extern "C" int ytb200_frame_bind_host(ytb200_frame *f, const double *image_host,
     return 0;
 }
 
+// A cast SHORTER than its PCIe traffic (the slab-walk projection: 2 ms of kernel for 302 MB of fp64 image and z-buffer at
+// 2048^2) gains nothing from touching the host arrays in place -- SM-issued PCIe accesses sustain ~34 GB/s, the frame took
+// 10.8 ms.  Such a frame is staged instead, in ROW BANDS through three streams: band k's rows of the image and the z-buffer
+// come in with the copy engine while band k-1 is cast and band k-2 goes out, so the frame costs about the longer of the
+// two transfers.  (A volume render is the other way round: 41 ms of kernel hide the same traffic, in place.)
+static int render_projection_banded(ytb200_frame *f, const ytb200_brickset *set, const int64_t *order, int64_t n_order,
+                                    int n_samples, int precision, const double *zbuffer_host, double *image_host, ytb200_stats *stats)
+{
+    DeviceGuard g(f->ctx->device);
+    const int nx = f->cam.nx, ny = f->cam.ny;
+    const int n_stiles = (nx + TILE_I - 1) / TILE_I;
+    const int n_bands = std::min(8, n_stiles);
+    if (!f->s_in) {
+        CK(cudaStreamCreateWithFlags(&f->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&f->ev_start, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&f->ev_out, cudaEventDisableTiming));
+    }
+    while ((int)f->ev_in.size() < n_bands) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        f->ev_in.push_back(a); f->ev_done.push_back(b);
+    }
+    cudaStream_t st = f->ctx->stream;
+    if (stats) CK(cudaEventRecord(f->ctx->ev0, st));
+    // footprints once, on the compute stream (cached while the list is unchanged); the copy-in stream starts behind
+    // whatever the compute stream was doing with the frame's buffers
+    int launches = 0;
+    int rc = prepare_order(f, set, order, n_order, &launches);
+    if (rc) return rc;
+    CK(cudaEventRecord(f->ev_start, st));
+    CK(cudaStreamWaitEvent(f->s_in, f->ev_start, 0));
+    CK(cudaStreamWaitEvent(f->s_out, f->ev_start, 0));
+    const size_t row_px = (size_t)ny;
+    for (int b = 0; b < n_bands; b++) {
+        const int s0 = (int)((long long)n_stiles * b / n_bands), s1 = (int)((long long)n_stiles * (b + 1) / n_bands);
+        const size_t r0 = (size_t)s0 * TILE_I, r1 = std::min((size_t)nx, (size_t)s1 * TILE_I);
+        if (r1 <= r0) continue;
+        const size_t px0 = r0 * row_px, npx = (r1 - r0) * row_px;
+        CK(cudaMemcpyAsync(f->image + px0 * 4, image_host + px0 * 4, npx * 4 * sizeof(double), cudaMemcpyHostToDevice, f->s_in));
+        if (zbuffer_host) CK(cudaMemcpyAsync(f->zbuffer + px0, zbuffer_host + px0, npx * sizeof(double), cudaMemcpyHostToDevice, f->s_in));
+        CK(cudaEventRecord(f->ev_in[(size_t)b], f->s_in));
+        CK(cudaStreamWaitEvent(st, f->ev_in[(size_t)b], 0));
+        if (!zbuffer_host) {
+            fill_f64_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(f->zbuffer + px0, 1.0, (long long)npx);
+            CK(cudaGetLastError());
+        }
+        f->band_first = s0; f->band_tiles = s1 - s0;
+        rc = cast_common(f, YTB200_PROJECTION, set, order, n_order, nullptr, n_samples, precision, nullptr, nullptr);
+        f->band_first = 0; f->band_tiles = -1;
+        if (rc) return rc;
+        CK(cudaEventRecord(f->ev_done[(size_t)b], st));
+        CK(cudaStreamWaitEvent(f->s_out, f->ev_done[(size_t)b], 0));
+        CK(cudaMemcpyAsync(image_host + px0 * 4, f->image + px0 * 4, npx * 4 * sizeof(double), cudaMemcpyDeviceToHost, f->s_out));
+    }
+    CK(cudaEventRecord(f->ev_out, f->s_out));
+    CK(cudaStreamWaitEvent(st, f->ev_out, 0));
+    if (stats) {
+        CK(cudaEventRecord(f->ctx->ev1, st));
+        CK(cudaEventSynchronize(f->ctx->ev1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, f->ctx->ev0, f->ctx->ev1));
+        stats->kernel_ms = ms; stats->n_launches = n_bands + launches; stats->n_cells = 0; stats->n_samples = 0;
+    }
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
 extern "C" int ytb200_render(ytb200_frame *f, int kind, const ytb200_brickset *set, const int64_t *order, int64_t n_order,
                              const ytb200_tf *tf, int n_samples, int precision, const double *zbuffer_host,
                              double *image_host_inout, ytb200_stats *stats)
@@ -1625,6 +1706,9 @@ extern "C" int ytb200_render(ytb200_frame *f, int kind, const ytb200_brickset *s
     // The frame's device image is not touched on this route.  Pageable arrays take the copy-in / copy-out route.
     double *img = mapped_host_alias(image_host_inout);
     double *zb = zbuffer_host ? mapped_host_alias(zbuffer_host) : nullptr;
+    if (img && (zb || !zbuffer_host) && set && kind == YTB200_PROJECTION && precision == YTB200_PREC_FAST && set->storage == YTB200_STORE_F32 &&
+        f->cam.nx >= 4 * TILE_I && !getenv("YTB200_PROJ_DDA") && !getenv("YTB200_NO_BANDS"))
+        return render_projection_banded(f, set, order, n_order, n_samples, precision, zbuffer_host, image_host_inout, stats);
     if (img && (zb || !zbuffer_host) && !getenv("YTB200_NO_ZEROCOPY")) {
         double *keep_img = f->image, *keep_zb = f->zbuffer;
         f->image = img;
