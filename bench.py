@@ -210,6 +210,16 @@ def roofline_block(workload, kind, world, my_samples, kernel_ms, alg_bytes, clk,
               "lsu_pipe": lsu, "issue": issue}
     if kind == "proj":
         common.update({"bound": "hbm", "achieved": hbm, "peak": peak, "unit": "GB/s", "frac": hbm / peak})
+    elif kind == "iproj":
+        # no table lookups: the cast is the cell walk itself, bound by instruction issue (ncu r02y: 123 warp-instructions per
+        # warp-cell, issue 61 % at two CTAs per SM); reported against the issue rate of the chip
+        cells = my_samples / N_SAMPLES
+        wi = 123.0 * cells / 32.0
+        peak_wi = sm_count * 4 * sm_mhz * 1e-3          # G warp-instructions per second
+        common["lsu_pipe"] = None
+        common.update({"bound": "issue", "achieved": wi / (kernel_ms * 1e-3) / 1e9, "peak": peak_wi, "unit": "Gwarp-instructions/s",
+                       "frac": wi / (kernel_ms * 1e-3) / 1e9 / peak_wi,
+                       "note": "123 warp-instructions per warp-cell from ncu (profiles/r02y_iproj_cast_kernel.txt), counted cells from this run"})
     else:
         gw = lsu["wavefronts"] / (kernel_ms * 1e-3) / 1e9
         common.update({"bound": "l1_lsu_pipe", "achieved": gw, "peak": sm_count * sm_mhz * 1e-3, "unit": "Gwavefronts/s",
@@ -487,11 +497,16 @@ def run_ours(args):
                 ms = float(t.item())
             return ms
 
-        for _ in range(max(args.warmup, 3)):
-            frame_device()
+        # the clock sampler (nvidia-smi -lms 100) starts BEFORE the warm-up: its NVML start-up stalls the GPU for a few
+        # milliseconds once, which must not land in the timed region (r02zz: 41.69 ms per step over 5 steps against 41.13
+        # over 10); it keeps sampling through the timed region
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
+            time.sleep(0.3)
+        for _ in range(max(args.warmup, 3)):
+            frame_device()
+        ctx.synchronize()
         ms_total = timed(frame_device, args.steps)
         clk = clocks.stop() if rank == 0 else None
         ms_step = ms_total / args.steps
@@ -608,7 +623,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="northstar_vr_1024c_2048px", choices=sorted(WORKLOADS))
