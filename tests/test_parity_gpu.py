@@ -67,6 +67,21 @@ def test_fast_path_matches_golden(sc, gpu):
     _check(sc, got, want, exact=False)
 
 
+@pytest.mark.parametrize("sc", [s for s in T.scenarios() if s.kind == "vr"], ids=lambda s: s.name)
+def test_fast_path_without_the_line_form_tables(sc, gpu, monkeypatch):
+    """Tables that pass the accuracy guard of ytb200_tf_create sample through LINE-form rows (y = d * fs + c); a table that
+    fails it keeps (value, increment) rows.  YTB200_NO_LINE forces the latter for every table: both forms must give the
+    oracle's image, and they agree with each other far inside the bar."""
+    S, G = _gpu_mods()
+    want = T.run_scenario(sc, O, O, num_threads=0)
+    with_line = T.run_scenario(sc, S, G)
+    monkeypatch.setenv("YTB200_NO_LINE", "1")
+    without = T.run_scenario(sc, S, G)
+    _check(sc, without, want, exact=False)
+    _check(sc, with_line, want, exact=False)
+    assert T.normalised_diff(with_line, without, sc.grey) <= 2e-5
+
+
 @pytest.mark.parametrize("sc", [s for s in T.scenarios() if s.kind != "proj"][:6], ids=lambda s: s.name)
 def test_f64_storage_fast_arithmetic(sc, gpu):
     S, G = _gpu_mods()

@@ -620,7 +620,15 @@ __device__ __forceinline__ float colour_cell_run(const CornersP &c, const Colour
             const float fs = fminf(fmaxf(fb, ct.tf->colour_clamp_lo), ct.tf->colour_clamp_hi);   // rejected samples land on zero rows
             const float t = __fadd_rd(fs, ct.tf->colour_magic);   // 2^23 + floor(fs + origin)
             const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_DELTA_ROW_BYTES + ct.base;
+#ifdef YTB_TABLE_TEX
+            // EXPERIMENT (r02ze A/B, not the product): the slope half of the row comes through the texture path (unfiltered
+            // float4 fetch from linear memory), the other half from shared memory -- does the idle TEX data pipe take load
+            // off the LSU data pipe?
+            const float4 t0 = lds128(addr);
+            const float4 t1 = tex1Dfetch<float4>((cudaTextureObject_t)ct.tf->colour_tex, 2 * (__float_as_int(t) - 0x4B000000) + 1);
+#else
             const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
+#endif
             const float2 fs2 = bcast2(fs);
             rg = fma2(fs2, make_float2(t1.x, t1.y), make_float2(t0.x, t0.y));
             ba = fma2(fs2, make_float2(t1.z, t1.w), make_float2(t0.z, t0.w));

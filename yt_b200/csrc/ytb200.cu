@@ -644,6 +644,20 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
             } else origin = 0;
         }
         rc |= to_device(t, col, &d.colour);
+#ifdef YTB_TABLE_TEX
+        if (!rc) {
+            cudaResourceDesc rd{};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = const_cast<float4 *>(d.colour);
+            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+            rd.res.linear.sizeInBytes = col.size() * sizeof(float4);
+            cudaTextureDesc td{};
+            td.readMode = cudaReadModeElementType;
+            cudaTextureObject_t tex = 0;
+            if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) != cudaSuccess) rc = fail(E_ARG, "texture object");
+            d.colour_tex = (unsigned long long)tex;
+        }
+#endif
         {
             // the shared-memory image of the table, staged by a cast CTA with ONE bulk async copy (cp.async.bulk)
             std::vector<float4> image(col.size() * COLOUR_COPIES);
