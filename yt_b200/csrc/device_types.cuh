@@ -63,7 +63,6 @@ struct DevTF {
     int colour_copy_shift;
     // the same rows as a cast CTA holds them in shared memory (every row 2^colour_copy_shift times): one bulk async copy
     const float4 *colour_image;
-    unsigned long long colour_tex;   // EXPERIMENT (YTB_TABLE_TEX): texture object over `colour` (float4 texels, row 2r = first half, 2r+1 = second)
     // row-coordinate constants of the colour fast path (see ColourTable in raycast.cuh); they stay in the
     // kernel-parameter constant bank instead of in registers
     float colour_c0, colour_clamp_bound, colour_lo, colour_hi, colour_mid, colour_half, colour_band, colour_zrow;

@@ -505,39 +505,6 @@ __device__ __forceinline__ float4 lds128(unsigned addr)
     return v;
 }
 
-#ifdef YTB_TABLE_F16INC
-// EXPERIMENT (r02u A/B, not the product): delta-layout rows keep their increments as fp16 -- 8 copies of the fp32 values
-// (128 B) followed by 16 copies of the four fp16 increments (8 B each, 128 B): LDS.128 + LDS.64 = 6 wavefronts per
-// warp-sample instead of 8 -- and the lerp is four mixed-precision FMAs (fma.rn.f32.f16 = FHFMA on sm_100: fp16 x fp16 +
-// fp32), the fraction rounded to fp16 as well.  Error per lookup <= 2^-11 |increment|: no table-level guard keeps a
-// frame inside the 1e-4 bar, so this stays a build variant.
-__device__ __forceinline__ uint2 lds64(unsigned addr)
-{
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-    return v;
-}
-// lane's byte offset from its fp32 copy (copy lane & 7 of 8, 16 B each) to its fp16 copy (copy lane & 15 of 16, 8 B each)
-__device__ __forceinline__ unsigned f16inc_offset()
-{
-    const unsigned lane = threadIdx.x & 31u;
-    return 128u + (lane & 15u) * 8u - (lane & 7u) * 16u;
-}
-__device__ __forceinline__ void lerp_f16inc(const float4 &t0, const uint2 &d, float fr, float2 &rg, float2 &ba)
-{
-    asm("{\n\t.reg .f16 f, d0, d1, d2, d3;\n\t"
-        "cvt.rn.f16.f32 f, %8;\n\t"
-        "mov.b32 {d0, d1}, %9;\n\t"
-        "mov.b32 {d2, d3}, %10;\n\t"
-        "fma.rn.f32.f16 %0, d0, f, %4;\n\t"
-        "fma.rn.f32.f16 %1, d1, f, %5;\n\t"
-        "fma.rn.f32.f16 %2, d2, f, %6;\n\t"
-        "fma.rn.f32.f16 %3, d3, f, %7;\n\t}"
-        : "=f"(rg.x), "=f"(rg.y), "=f"(ba.x), "=f"(ba.y)
-        : "f"(t0.x), "f"(t0.y), "f"(t0.z), "f"(t0.w), "f"(fr), "r"(d.x), "r"(d.y));
-}
-#endif
-
 // sm_100 packed fp32 (FFMA2/FMUL2): two lanes of fp32 per issue slot.  The cast kernel is
 // instruction-issue bound (ncu round 1: 82 % issue-active, 69 instr/sample), so halving the issue
 // slots of the paired arithmetic is the lever.
@@ -608,9 +575,6 @@ __device__ __forceinline__ float colour_cell_run(const CornersP &c, const Colour
 {
     float closest = 3.0e38f;
     const float2 neg1 = make_float2(-1.f, -1.f), one2 = make_float2(1.f, 1.f);
-#ifdef YTB_TABLE_F16INC
-    const unsigned f16off = f16inc_offset();
-#endif
     // FIT_get_value for the 4 tables at once + FIT_eval_transfer, for the sample whose row coordinate is fb
     auto sample = [&](const float fb) {
         // EDGE: keep the smallest distance to a bound of the cell; the caller compares it with the fp32 error band.
@@ -620,15 +584,7 @@ __device__ __forceinline__ float colour_cell_run(const CornersP &c, const Colour
             const float fs = fminf(fmaxf(fb, ct.tf->colour_clamp_lo), ct.tf->colour_clamp_hi);   // rejected samples land on zero rows
             const float t = __fadd_rd(fs, ct.tf->colour_magic);   // 2^23 + floor(fs + origin)
             const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_DELTA_ROW_BYTES + ct.base;
-#ifdef YTB_TABLE_TEX
-            // EXPERIMENT (r02ze A/B, not the product): the slope half of the row comes through the texture path (unfiltered
-            // float4 fetch from linear memory), the other half from shared memory -- does the idle TEX data pipe take load
-            // off the LSU data pipe?
-            const float4 t0 = lds128(addr);
-            const float4 t1 = tex1Dfetch<float4>((cudaTextureObject_t)ct.tf->colour_tex, 2 * (__float_as_int(t) - 0x4B000000) + 1);
-#else
             const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
-#endif
             const float2 fs2 = bcast2(fs);
             rg = fma2(fs2, make_float2(t1.x, t1.y), make_float2(t0.x, t0.y));
             ba = fma2(fs2, make_float2(t1.z, t1.w), make_float2(t0.z, t0.w));
@@ -637,16 +593,10 @@ __device__ __forceinline__ float colour_cell_run(const CornersP &c, const Colour
             const float t = __fadd_rd(fs, ct.tf->colour_magic);   // 2^23 + floor(fs)
             const float fr = fs - (t - ct.tf->colour_magic);
             const unsigned addr = (unsigned)__float_as_int(t) * COLOUR_DELTA_ROW_BYTES + ct.base;
-#ifdef YTB_TABLE_F16INC
-            const float4 t0 = lds128(addr);
-            const uint2 dh = lds64(addr + f16off);
-            lerp_f16inc(t0, dh, fr, rg, ba);
-#else
             const float4 t0 = lds128(addr), t1 = lds128(addr + COLOUR_ROW_BYTES);
             const float2 fr2 = bcast2(fr);
             rg = fma2(fr2, make_float2(t1.x, t1.y), make_float2(t0.x, t0.y));
             ba = fma2(fr2, make_float2(t1.z, t1.w), make_float2(t0.z, t0.w));
-#endif
         } else {
             // margin < 0 <=> b0 < value < b1 (false for NaN)
             const bool valid = fabsf(fb - ct.tf->colour_mid) - ct.tf->colour_half < 0.f;
@@ -750,23 +700,10 @@ __device__ __forceinline__ void colour_sample(const ColourTable &ct, float fs, f
     const bool delta = ct.tf->colour_delta != 0;
     const unsigned addr = (unsigned)__float_as_int(t) * (delta ? COLOUR_DELTA_ROW_BYTES : COLOUR_ROW_BYTES) + ct.base;
     const float4 t0 = lds128(addr);
-#ifdef YTB_TABLE_F16INC
-    float r, g, b, adt;
-    if (delta) {
-        float2 rg, ba;
-        lerp_f16inc(t0, lds64(addr + f16inc_offset()), fr, rg, ba);
-        r = rg.x; g = rg.y; b = ba.x; adt = ba.y * dt;
-    } else {
-        const float4 t1 = lds128(addr + COLOUR_ROW_BYTES);
-        r = fmaf(fr, t1.x - t0.x, t0.x); g = fmaf(fr, t1.y - t0.y, t0.y); b = fmaf(fr, t1.z - t0.z, t0.z);
-        adt = fmaf(fr, t1.w - t0.w, t0.w) * dt;
-    }
-#else
     float4 t1 = lds128(addr + COLOUR_ROW_BYTES);
     if (!delta) t1 = make_float4(t1.x - t0.x, t1.y - t0.y, t1.z - t0.z, t1.w - t0.w);
     const float r = fmaf(fr, t1.x, t0.x), g = fmaf(fr, t1.y, t0.y), b = fmaf(fr, t1.z, t0.z);
     const float adt = fmaf(fr, t1.w, t0.w) * dt;
-#endif
     const float e0 = r * adt, e1 = g * adt, e2 = b * adt;
     if (GREY && ERT) {
         const float ta = fmaxf(1.f - adt, 0.f);

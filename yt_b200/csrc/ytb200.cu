@@ -3,8 +3,6 @@
 // No CPU compute path exists: every call needs a CUDA device and fails loudly otherwise.
 #include "../../include/ytb200.h"
 
-#include <cuda_fp16.h>
-
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -644,36 +642,10 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
             } else origin = 0;
         }
         rc |= to_device(t, col, &d.colour);
-#ifdef YTB_TABLE_TEX
-        if (!rc) {
-            cudaResourceDesc rd{};
-            rd.resType = cudaResourceTypeLinear;
-            rd.res.linear.devPtr = const_cast<float4 *>(d.colour);
-            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
-            rd.res.linear.sizeInBytes = col.size() * sizeof(float4);
-            cudaTextureDesc td{};
-            td.readMode = cudaReadModeElementType;
-            cudaTextureObject_t tex = 0;
-            if (cudaCreateTextureObject(&tex, &rd, &td, nullptr) != cudaSuccess) rc = fail(E_ARG, "texture object");
-            d.colour_tex = (unsigned long long)tex;
-        }
-#endif
         {
             // the shared-memory image of the table, staged by a cast CTA with ONE bulk async copy (cp.async.bulk)
             std::vector<float4> image(col.size() * COLOUR_COPIES);
             for (size_t i = 0; i < image.size(); i++) image[i] = col[i / COLOUR_COPIES];
-#ifdef YTB_TABLE_F16INC
-            if (d.colour_delta) {
-                // experiment (raycast.cuh): the increment half of every row as 16 copies of four fp16 values
-                for (size_t r = 0; r < col.size() / 2; r++) {
-                    const float4 inc = col[2 * r + 1];
-                    const __half h[4] = {__float2half_rn(inc.x), __float2half_rn(inc.y), __float2half_rn(inc.z), __float2half_rn(inc.w)};
-                    unsigned short *dst = reinterpret_cast<unsigned short *>(&image[(2 * r + 1) * COLOUR_COPIES]);
-                    for (int c = 0; c < 16; c++)
-                        for (int k = 0; k < 4; k++) dst[c * 4 + k] = __half_as_ushort(h[k]);
-                }
-            }
-#endif
             rc |= to_device(t, image, &d.colour_image);
         }
         // every row is replicated 8x in shared memory (bank-conflict-free): 64.4 KiB (value layout, 512 bins)
