@@ -147,3 +147,32 @@ def test_terminated_cast_through_the_swap_object(height, gpu):
         swap.check()
         got = fr.download(np.empty_like(img))
         assert T.normalised_diff(got, want, True) <= 1e-4
+
+
+@pytest.mark.parametrize("height", [300.0, 30000.0])
+def test_terminated_cast_over_a_long_brick_list_with_masked_and_nan_cells(height, gpu):
+    """More than 32 bricks select the long-list instantiation of the cast (the one AMR hierarchies use); here 64 bricks of
+    4^3 cells in view order through a perspective lens, with masked cells and NaN / zero vertices in the data."""
+    base = {s.name: s for s in T.scenarios()}
+    src = base["vr_mask_nan"]                      # data with NaN and 0 vertices, a mask with holes
+    data, mask, le, re, dims = src.bricks[0]
+    sub = T.split_brick(data, mask, le, re, (4, 4, 4))
+    cam = T.make_camera("perspective", resolution=(48, 48), position=[1.6, 1.4, 1.2], width=[0.6, 0.6, 1.0])
+    order = T.view_order([(b[2], b[3]) for b in sub], cam.lens.viewpoint)
+    assert len(sub) == 64
+    img0 = np.random.RandomState(9).uniform(0, 0.3, size=(48, 48, 4))
+    sc = T.Scenario("ert_64bricks", "vr", cam, sub, order, tf=T.colour_tf(grey=True, height=height), image0=img0, grey=True)
+    want = T.run_scenario(sc, O, O, num_threads=0)
+    cells = {}
+    for ert in (0.0, EPS):
+        s, bs, img = _sampler(sc, ert)
+        fr = s._frame
+        fr.upload(img, s.azbuffer)
+        st = fr.cast(s.kind, bs, np.array(sc.order, dtype=np.int64), tf=s._tables, n_samples=s.n_samples, timed=True)
+        got = fr.download(np.empty_like(img))
+        cells[ert] = int(st.n_cells)
+        ok = ~np.isnan(want)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert T.normalised_diff(np.where(ok, got, 0.0), np.where(ok, want, 0.0), True) <= 1e-4, (height, ert)
+    if height > 1000:
+        assert 0 < cells[EPS]
