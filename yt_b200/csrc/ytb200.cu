@@ -754,16 +754,29 @@ extern "C" int ytb200_frame_create(ytb200_ctx *ctx, const ytb200_camera *cam, yt
             if (cam->camera_data[3] != 0.0 && cam->camera_data[5] != 0.0) c.ext_mode = 2;
         }
     }
-    cudaError_t e;
-    if ((e = cudaMalloc(&f->image, npx * 4 * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc(&f->zbuffer, npx * sizeof(double))) != cudaSuccess) {
-        ytb200_frame_destroy(f);
-        return fail(-100 - (int)e, "frame buffers: %s", cudaGetErrorString(e));
-    }
+    // the device image / z-buffer are allocated on first use (ensure_buffers): a frame that only ever renders page-locked
+    // host arrays in place (ytb200_render, what a Scene does every frame) never needs them, and 167 MB of cudaMalloc +
+    // cudaFree per frame were 21 ms of a 2048^2 scene render (tools/profile_scene.py)
+    (void)npx;
     *out = f;
-    int rc = ytb200_frame_clear(f);
-    if (rc) { ytb200_frame_destroy(f); *out = nullptr; return rc; }
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Device image (zeros) and z-buffer (ones) of a frame, allocated and initialised on first use.
+static int ensure_buffers(ytb200_frame *f)
+{
+    if (f->image && f->zbuffer) return 0;
+    if (f->image_is_host) return fail(E_STATE, "frame is rendering a host image in place");
+    DeviceGuard g(f->ctx->device);
+    const size_t npx = (size_t)f->cam.nx * f->cam.ny;
+    cudaError_t e;
+    if ((!f->image && (e = cudaMalloc(&f->image, npx * 4 * sizeof(double))) != cudaSuccess) ||
+        (!f->zbuffer && (e = cudaMalloc(&f->zbuffer, npx * sizeof(double))) != cudaSuccess))
+        return fail(-100 - (int)e, "frame buffers: %s", cudaGetErrorString(e));
+    CK(cudaMemsetAsync(f->image, 0, npx * 4 * sizeof(double), f->ctx->stream));
+    fill_f64_kernel<<<(unsigned)((npx + 255) / 256), 256, 0, f->ctx->stream>>>(f->zbuffer, 1.0, (long long)npx);
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -787,6 +800,7 @@ extern "C" int ytb200_frame_destroy(ytb200_frame *f)
 extern "C" int ytb200_frame_upload(ytb200_frame *f, const double *image_host, const double *zbuffer_host)
 {
     if (!f || !image_host) return fail(E_ARG, "NULL argument");
+    { int rc = ensure_buffers(f); if (rc) return rc; }
     DeviceGuard g(f->ctx->device);
     const size_t npx = (size_t)f->cam.nx * f->cam.ny;
     CK(cudaMemcpyAsync(f->image, image_host, npx * 4 * sizeof(double), cudaMemcpyHostToDevice, f->ctx->stream));
@@ -802,6 +816,7 @@ extern "C" int ytb200_frame_upload(ytb200_frame *f, const double *image_host, co
 extern "C" int ytb200_frame_clear(ytb200_frame *f)
 {
     if (!f) return fail(E_ARG, "frame is NULL");
+    if (!f->image || !f->zbuffer) return ensure_buffers(f);   // a fresh allocation is a cleared one
     DeviceGuard g(f->ctx->device);
     const size_t npx = (size_t)f->cam.nx * f->cam.ny;
     CK(cudaMemsetAsync(f->image, 0, npx * 4 * sizeof(double), f->ctx->stream));
@@ -813,6 +828,7 @@ extern "C" int ytb200_frame_clear(ytb200_frame *f)
 extern "C" int ytb200_frame_download(ytb200_frame *f, double *image_host)
 {
     if (!f || !image_host) return fail(E_ARG, "NULL argument");
+    { int rc = ensure_buffers(f); if (rc) return rc; }
     DeviceGuard g(f->ctx->device);
     const size_t npx = (size_t)f->cam.nx * f->cam.ny;
     CK(cudaMemcpyAsync(image_host, f->image, npx * 4 * sizeof(double), cudaMemcpyDeviceToHost, f->ctx->stream));
@@ -820,7 +836,7 @@ extern "C" int ytb200_frame_download(ytb200_frame *f, double *image_host)
     return 0;
 }
 
-extern "C" void *ytb200_frame_device_image(ytb200_frame *f) { return f ? (void *)f->image : nullptr; }
+extern "C" void *ytb200_frame_device_image(ytb200_frame *f) { return (f && ensure_buffers(f) == 0) ? (void *)f->image : nullptr; }
 
 // Upload the order list and compute per-brick pixel footprints (cached while unchanged).
 static int prepare_order(ytb200_frame *f, const ytb200_brickset *set, const int64_t *order, int64_t n_order, int *launches)
@@ -921,6 +937,7 @@ static int cast_common(ytb200_frame *f, int kind, const ytb200_brickset *set, co
     DeviceGuard g(f->ctx->device);
     cudaStream_t st = f->ctx->stream;
     int launches = 0;
+    if (!f->image_is_host) { int rcb = ensure_buffers(f); if (rcb) return rcb; }
     if (stats) CK(cudaEventRecord(f->ctx->ev0, st));
     // early ray termination: the composition order is walked from its far end, so the list goes in reversed
     const bool ert = f->ert_eps > 0.f && kind == YTB200_VOLUME_RENDER && !exact && set->n_fields == 1 && set->storage == YTB200_STORE_F32 &&
@@ -1214,6 +1231,7 @@ extern "C" int ytb200_frame_cast_octree(ytb200_frame *f, int kind, ytb200_octree
         CK(cudaStreamSynchronize(st));
         o->dirty = false;
     }
+    { int rcb = ensure_buffers(f); if (rcb) return rcb; }
     if (stats) CK(cudaEventRecord(f->ctx->ev0, st));
     OctParams p{};
     p.nx = f->cam.nx; p.ny = f->cam.ny;
@@ -1455,6 +1473,7 @@ static int swap_run(ytb200_swap *s, ytb200_frame *f, int broadcast, double *host
     int *err = reinterpret_cast<int *>(swap_flag(s->slab, SWAP_WORD_ERROR));
     unsigned *counter = reinterpret_cast<unsigned *>(swap_flag(s->slab, SWAP_WORD_COUNTER));
     auto buf = [&](unsigned char *slab, int j) { return slab + set + s->buf_off[(size_t)j]; };
+    { int rcb = ensure_buffers(f); if (rcb) return rcb; }
     const double4 *c0 = reinterpret_cast<const double4 *>(f->c0_in ? f->c0_in : f->image);
     const bool dest = broadcast || s->rank == 0;
     auto blocks = [&](long long n) { return (unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)s->ctx->sm_count * 8)); };
@@ -1637,6 +1656,7 @@ static int render_projection_banded(ytb200_frame *f, const ytb200_brickset *set,
         f->ev_in.push_back(a); f->ev_done.push_back(b);
     }
     cudaStream_t st = f->ctx->stream;
+    { int rcb = ensure_buffers(f); if (rcb) return rcb; }
     if (stats) CK(cudaEventRecord(f->ctx->ev0, st));
     // footprints once, on the compute stream (cached while the list is unchanged); the copy-in stream starts behind
     // whatever the compute stream was doing with the frame's buffers

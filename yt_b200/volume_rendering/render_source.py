@@ -236,7 +236,12 @@ class VolumeSource(RenderSource, abc.ABC):
     def finalize_image(self, camera, image):
         image = image.reshape(*camera.resolution, 4)
         if not self.transfer_function.grey_opacity:
-            image[:, :, 3] = 1          # the non-grey composite never touches alpha (render_source.py:535-536)
+            # the non-grey composite never touches alpha (render_source.py:535-536)
+            try:
+                from ..device import parallel_assign
+                parallel_assign(image[:, :, 3], 1)
+            except Exception:   # noqa: BLE001  (host-only use of the mirror)
+                image[:, :, 3] = 1
         return image
 
     def __repr__(self):
