@@ -171,16 +171,18 @@ def measured_peak():
 def lsu_pipe_estimate(kind, samples, kernel_ms, sm_mhz, sm_count):
     """Busy fraction of the L1/shared LSU data pipe (one wavefront per cycle per SM).  Shared-memory wavefronts are
     exact by construction (two LDS.128 per sample, 4 wavefronts each, zero bank conflicts); wavefronts per global
-    load are the ncu averages (VR, profiles/r01zn: 4 corner loads per cell x 6.0 -- the walk reuses the face two
-    consecutive cells share; PROJ, profiles/r01zd: 8.4 per load)."""
+    load are the ncu averages (VR, profiles/r02zz_vr_northstar_cast_kernel.txt: 4 corner loads per cell x 6.0 -- the walk
+    reuses the face two consecutive cells share; slab-walk projection, profiles/r02zz_proj_cfg3_proj_kernel.txt: 3.3
+    wavefronts per warp of cell visits)."""
     if kind == "vr":
         cells = samples / N_SAMPLES
         wf = samples / 32.0 * 8.0 + cells / 32.0 * 4 * 6.0
     else:
-        wf = samples / 32.0 * 8.4
+        wf = samples / 32.0 * 3.32
     cycles = kernel_ms * 1e-3 * sm_mhz * 1e6
     return {"wavefronts": wf, "frac": wf / sm_count / cycles,
-            "source": "LDS wavefronts counted, LDG wavefronts per request from ncu (profiles/r01zn_vr_*, r01zd_proj_*); ncu measured 0.849 (VR) / 0.570 (PROJ)"}
+            "source": "LDS wavefronts counted, LDG wavefronts per request from ncu (profiles/r02zz_vr_northstar_cast_kernel.txt, "
+                      "r02zz_proj_cfg3_proj_kernel.txt); ncu measured 0.895 (VR) / 0.595 (PROJ) on the same kernels"}
 
 
 def recorded_traffic(workload):
