@@ -223,6 +223,14 @@ int ytb200_frame_bind_host(ytb200_frame *f, const double *image_host, const doub
  * A timed cast reports the cells the rays actually sampled in ytb200_stats.n_cells / n_samples; the algorithmic count
  * stays ytb200_frame_count's.  eps = 0 (the default) disables. */
 int ytb200_frame_set_early_termination(ytb200_frame *f, double eps);
+/* Host-only probe (no device needed; ours): would ytb200_tf_create sample a ColorTransferFunction's four tables -- the
+ * (r, g, b, a) arrays of FIT_initialize_table, field_interpolation_tables.pxd:27-50 -- through LINE-form rows (y = d*fs + c
+ * in the table's row coordinate, two instructions fewer per sample), or keep (value, increment) rows?  The decision is an
+ * accuracy guard computed against the fp64 table: every bin must keep 5e-6 of its own mean magnitude (+ 1e-9 of the channel
+ * maximum) for the best integer origin.  Returns 1 / 0; *origin_out and *worst_ratio_out (error / allowance of the worst bin)
+ * may be NULL. */
+int ytb200_tf_line_form_probe(int nbins, const double *r, const double *g, const double *b, const double *a,
+                              int *origin_out, double *worst_ratio_out);
 typedef struct ytb200_swap ytb200_swap;
 #define YTB200_PARTIAL_AB64 0   /* fp64 (A[4], B[4]): 64 B per pixel -- EXACT precision */
 #define YTB200_PARTIAL_AB32 1   /* fp32 (A[4], B[4]): 32 B -- FAST volume render, any transfer function */

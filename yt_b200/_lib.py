@@ -88,6 +88,7 @@ SIGNATURES = {
                                                 C.c_int, C.c_void_p, C.POINTER(Stats)]),
     "ytb200_frame_bind_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ytb200_frame_set_early_termination": (C.c_int, [C.c_void_p, C.c_double]),
+    "ytb200_tf_line_form_probe": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "ytb200_swap_create": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "ytb200_swap_destroy": (C.c_int, [C.c_void_p]),
     "ytb200_swap_handle": (C.c_int, [C.c_void_p, C.c_void_p]),

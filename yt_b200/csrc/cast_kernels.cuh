@@ -448,9 +448,9 @@ struct FastSampler {
                     float m;
                     const float dte = ERT ? dt * dt_scale : dt;   // dt of the caller's ray: what the emission is weighted with
                     const bool clamp = !(dte * tf->colour_clamp_bound <= 1.f);
-                    if (!tfm_edge(TFM) && tf->colour_line) {
-                        if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, false, true, ERT, true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dte, ca);
-                        else m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, false, true, ERT, true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dte, ca);
+                    if (tf->colour_line) {
+                        if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM), true, ERT, true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dte, ca);
+                        else m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM), true, ERT, true>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dte, ca);
                     } else if (tf->colour_delta) {
                         if (!clamp) m = colour_cell_run<PARTIAL, tfm_grey(TFM), false, tfm_edge(TFM), true, ERT>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dte, ca);
                         else m = colour_cell_run<PARTIAL, tfm_grey(TFM), true, tfm_edge(TFM), true, ERT>(cp, ct, n_samples, x, y, z, sxs, sys, szs, dte, ca);

@@ -568,7 +568,7 @@ struct ColourAcc {
 // ERT (grey opacity only): the samples arrive in REVERSE composition order (the last sample the reference composites
 // comes first), so the affine maps are applied front to back -- A <- A + B e, B <- B a, field_interpolation_tables.pxd:
 // 103-110 read from the other end -- and B is the transmittance the termination test looks at.
-// LINE (delta layout only; no EDGE): the rows hold (c, d) of y = d * fs + c in the (origin-shifted) row coordinate, see DevTF.
+// LINE (delta layout only): the rows hold (c, d) of y = d * fs + c in the (origin-shifted) row coordinate, see DevTF.
 template <bool PARTIAL, bool GREY, bool CLAMP, bool EDGE, bool DELTA, bool ERT = false, bool LINE = false>
 __device__ __forceinline__ float colour_cell_run(const CornersP &c, const ColourTable &ct, int n_samples, float x, float y, float z,
                                                 float sx, float sy, float sz, float dt, ColourAcc &A)
@@ -702,8 +702,10 @@ __device__ __forceinline__ void colour_sample(const ColourTable &ct, float fs, f
     const float4 t0 = lds128(addr);
     float4 t1 = lds128(addr + COLOUR_ROW_BYTES);
     if (!delta) t1 = make_float4(t1.x - t0.x, t1.y - t0.y, t1.z - t0.z, t1.w - t0.w);
-    const float r = fmaf(fr, t1.x, t0.x), g = fmaf(fr, t1.y, t0.y), b = fmaf(fr, t1.z, t0.z);
-    const float adt = fmaf(fr, t1.w, t0.w) * dt;
+    // LINE-form rows hold (c, d) of y = d * (fs - origin) + c; this path keeps TRUE row coordinates (origin = magic - 2^23)
+    const float w = ct.tf->colour_line ? fs - (ct.tf->colour_magic - COLOUR_MAGIC) : fr;
+    const float r = fmaf(w, t1.x, t0.x), g = fmaf(w, t1.y, t0.y), b = fmaf(w, t1.z, t0.z);
+    const float adt = fmaf(w, t1.w, t0.w) * dt;
     const float e0 = r * adt, e1 = g * adt, e2 = b * adt;
     if (GREY && ERT) {
         const float ta = fmaxf(1.f - adt, 0.f);

@@ -501,6 +501,77 @@ static int to_device(ytb200_tf *t, const std::vector<T> &h, const T **out)
     return 0;
 }
 
+// LINE form of a delta-layout colour table (DevTF::colour_line): row r = bin + 2 holds (c, d) with d the fp32 increment as
+// stored in `col` and c = y - (r - origin) * d, so the product in c is exact and the error of a bin against the fp64 table is
+// |fl(c) - c| + |fl(d) - d| (the latter times the fractional position, <= 1).  Returns the worst ratio, over all bins and
+// channels, of that error to its allowance -- 5e-6 of the bin's mean magnitude plus 1e-9 of the channel's maximum -- for the
+// integer origin that minimises it; `*line_out` gets the rows for that origin.  A ratio <= 1 means the form may be used:
+// a relative error eps per lookup moves a pixel by at most (2 + tau) * eps of its value (emission twice -- colour times alpha --
+// and the optical depth tau once), 6e-5 at tau = 10, where less than 5e-5 of what lies behind shows through anyway.
+static double line_form_rows(const double *const y[4], int nb, const std::vector<float4> &col, int *origin_out, std::vector<float4> *line_out)
+{
+    double cmax[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = 0; c < 4; c++)
+        for (int j = 0; j < nb; j++) cmax[c] = fmax(cmax[c], fabs(y[c][j]));
+    auto worst_bin = [&](int o, std::vector<float4> *out) {
+        double worst = 0.0;
+        for (int c = 0; c < 4; c++) {
+            for (int j = 0; j + 1 < nb; j++) {
+                const size_t r = (size_t)j + 2;
+                const float df = (&col[2 * r + 1].x)[c];
+                const double d64 = y[c][j + 1] - y[c][j];
+                const double c64 = y[c][j] - ((double)r - (double)o) * (double)df;
+                const float cf = (float)c64;
+                if (out) { (&(*out)[2 * r].x)[c] = cf; (&(*out)[2 * r + 1].x)[c] = df; }
+                const double abs_err = fabs((double)cf - c64) + fabs((double)df - d64);
+                const double lim = 5e-6 * 0.5 * (fabs(y[c][j]) + fabs(y[c][j + 1])) + 1e-9 * cmax[c];
+                if (!(abs_err <= lim)) worst = fmax(worst, (lim > 0.0 && abs_err == abs_err) ? abs_err / lim : 1e300);   // NaN fails
+                else if (lim > 0.0) worst = fmax(worst, abs_err / lim);
+            }
+        }
+        return worst;
+    };
+    double best = 1e300;
+    int origin = nb / 2 + 2;
+    for (int o = 2; o < nb + 2; o++) {
+        const double w = worst_bin(o, nullptr);
+        if (w < best) { best = w; origin = o; }
+    }
+    if (line_out) {
+        line_out->assign(col.size(), make_float4(0.f, 0.f, 0.f, 0.f));
+        best = fmax(best, worst_bin(origin, line_out));
+    }
+    if (origin_out) *origin_out = origin;
+    return best;
+}
+
+// The (value, increment) rows of the delta layout: row = bin + 2, rows 0, 1 and >= nbins + 1 are zero.
+static std::vector<float4> delta_rows(const double *const y[4], int nb)
+{
+    std::vector<float4> col(2 * ((size_t)nb + 2), make_float4(0.f, 0.f, 0.f, 0.f));
+    auto row = [&](int j) { return make_float4((float)y[0][j], (float)y[1][j], (float)y[2][j], (float)y[3][j]); };
+    for (int j = 0; j + 1 < nb; j++) {
+        const float4 a = row(j), b = row(j + 1);
+        col[2 * ((size_t)j + 2)] = a;
+        col[2 * ((size_t)j + 2) + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, b.w - a.w);
+    }
+    return col;
+}
+
+// Host-only probe of the decision ytb200_tf_create takes for a ColorTransferFunction's four tables (no device needed; the
+// CPU tests pin it): returns 1 if the table would be sampled through LINE-form rows, 0 if it keeps (value, increment) rows.
+extern "C" int ytb200_tf_line_form_probe(int nbins, const double *r, const double *g, const double *b, const double *a,
+                                         int *origin_out, double *worst_ratio_out)
+{
+    if (nbins < 2 || !r || !g || !b || !a) return fail(E_ARG, "bad argument");
+    const double *y4[4] = {r, g, b, a};
+    int origin = 0;
+    const double worst = nbins <= COLOUR_DELTA_MAX_BINS ? line_form_rows(y4, nbins, delta_rows(y4, nbins), &origin, nullptr) : 1e300;
+    if (origin_out) *origin_out = origin;
+    if (worst_ratio_out) *worst_ratio_out = worst;
+    return worst <= 1.0 ? 1 : 0;
+}
+
 extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nbins, const double *const *y,
                                 const double *bounds, const int32_t field_ids[6], const int32_t weight_field_ids[6],
                                 const int32_t weight_table_ids[6], const int32_t field_table_ids[6], int grey_opacity,
@@ -598,42 +669,17 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
         d.colour_edge = edge > 1e-30 ? 1 : 0;
         d.colour_line = 0; d.colour_clamp_lo = 0.5f; d.colour_magic = COLOUR_MAGIC;
         int origin = 0;
-        if (d.colour_delta && !d.colour_edge && !getenv("YTB200_NO_LINE")) {
+        if (d.colour_delta && !getenv("YTB200_NO_LINE")) {
             // LINE form (DevTF): row r holds (c, d) with c = y - (r - origin) * d, so that y(fs) = d * (fs - origin) + c needs
             // no fractional part (two instructions fewer per sample).  What it costs is accuracy: c is rounded to fp32 at a
-            // magnitude of up to |r - origin| * |d|, so the form is used only if EVERY bin keeps a relative accuracy of 4e-6 of
+            // magnitude of up to |r - origin| * |d|, so the form is used only if EVERY bin keeps a relative accuracy of 5e-6 of
             // its own mean magnitude (plus 1e-9 of the channel's maximum) -- computed here, per table, against the fp64
             // table; a table that fails keeps the (value, increment) rows.  d is the fp32 increment as stored, so the product
             // in c is exact and the error of a bin is |fl(c) - c| + |fl(d) - d| (the latter times the fractional position,
             // <= 1).  The origin is the integer row that minimises the worst bin.
-            double cmax[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int c = 0; c < 4; c++)
-                for (int j = 0; j < nb; j++) cmax[c] = fmax(cmax[c], fabs(y[c][j]));
-            auto worst_bin = [&](int o, std::vector<float4> *out) {
-                double worst = 0.0;
-                for (int c = 0; c < 4; c++) {
-                    for (int j = 0; j + 1 < nb; j++) {
-                        const size_t r = (size_t)j + 2;
-                        const float df = (&col[2 * r + 1].x)[c];
-                        const double d64 = y[c][j + 1] - y[c][j];
-                        const double c64 = y[c][j] - ((double)r - (double)o) * (double)df;
-                        const float cf = (float)c64;
-                        if (out) { (&(*out)[2 * r].x)[c] = cf; (&(*out)[2 * r + 1].x)[c] = df; }
-                        const double abs_err = fabs((double)cf - c64) + fabs((double)df - d64);
-                        const double lim = 4e-6 * 0.5 * (fabs(y[c][j]) + fabs(y[c][j + 1])) + 1e-9 * cmax[c];
-                        if (!(abs_err <= lim)) worst = fmax(worst, lim > 0.0 ? abs_err / lim : 1e300);
-                        else if (lim > 0.0) worst = fmax(worst, abs_err / lim);
-                    }
-                }
-                return worst;
-            };
-            double best = 1e300;
-            for (int o = 2; o < nb + 2; o++) {
-                const double w = worst_bin(o, nullptr);
-                if (w < best) { best = w; origin = o; }
-            }
-            std::vector<float4> line(col.size(), make_float4(0.f, 0.f, 0.f, 0.f));
-            const bool ok = best <= 1.0 && worst_bin(origin, &line) <= 1.0;
+            std::vector<float4> line;
+            const double *y4[4] = {y[0], y[1], y[2], y[3]};
+            const bool ok = line_form_rows(y4, nb, col, &origin, &line) <= 1.0;
             if (ok) {
                 col.swap(line);
                 d.colour_line = 1;
@@ -662,7 +708,7 @@ extern "C" int ytb200_tf_create(ytb200_ctx *ctx, int n_tables, const int32_t *nb
         for (int j = 0; j < nb; j++) if (!(y[3][j] >= 0.0)) d.colour_nonneg = 0;
         d.colour_lo = 2.f; d.colour_hi = (float)(nb + 1);
         d.colour_clamp_hi = (float)nb + 1.5f - (float)origin;
-        d.colour_mid = 0.5f * (float)(nb + 3); d.colour_half = 0.5f * (float)(nb - 1);
+        d.colour_mid = 0.5f * (float)(nb + 3) - (float)origin; d.colour_half = 0.5f * (float)(nb - 1);   // origin != 0: LINE form (delta layout)
         d.colour_band = 4e-6f * (float)(nb + 512);
         // row coordinate of the value 0, with the very operations load_corners_rows applies to a corner
         d.colour_zrow = fmaf(0.f - d.b0_hi[0], d.idbin_f[0], d.colour_c0);
