@@ -214,3 +214,18 @@ def test_orientation_fixture_equals_the_reference_construction():
         ds = fake_vr_orientation_test_ds(**kw)
         assert np.array_equal(ds.index.grids[0][("stream", "density")], want)
         assert np.array_equal(ds.domain_left_edge, bbox[:, 0]) and np.array_equal(ds.domain_right_edge, bbox[:, 1])
+
+
+def test_parallel_assign_fills_like_numpy():
+    """device.parallel_assign: slabs along axis 0 on a thread pool; strided views (one channel of an image), odd sizes,
+    small arrays (serial path) and non-finite values."""
+    from yt_b200.device import parallel_assign
+    img = np.empty((1031, 517, 4))
+    parallel_assign(img, 0.0)
+    parallel_assign(img[:, :, 3], 1)
+    assert (img[:, :, :3] == 0).all() and (img[:, :, 3] == 1).all()
+    z = np.empty((2048, 2048))
+    assert parallel_assign(z, np.inf) is z and np.isinf(z).all()
+    small = np.empty((5, 7))
+    parallel_assign(small, -2.5)
+    assert (small == -2.5).all()
