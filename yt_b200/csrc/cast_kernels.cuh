@@ -752,13 +752,21 @@ struct FastSampler {
             // lookups and the lit composite in fp32.  General, not tuned (the reference reaches it from old_camera only).
             double dp[3] = {xd, yd, zd};
             const double st[3] = {dc[0] * dt64, dc[1] * dt64, dc[2] * dt64};
+            // field 0's cell in registers: its value and the six gradient probes of every sample read these 8 corners
+            double c0[8];
+            {
+                const T *d = (const T *)br->data[0] + off;
+                c0[0] = (double)__ldg(d); c0[1] = (double)__ldg(d + 1); c0[2] = (double)__ldg(d + sy); c0[3] = (double)__ldg(d + sy + 1);
+                c0[4] = (double)__ldg(d + sx); c0[5] = (double)__ldg(d + sx + 1); c0[6] = (double)__ldg(d + sx + sy); c0[7] = (double)__ldg(d + sx + sy + 1);
+            }
             for (int s = 0; s < n_samples; s++) {
                 float dvs[6];
+                dvs[0] = (float)cell_interpolate64(c0, dp);
 #pragma unroll
-                for (int j = 0; j < 6; j++)
+                for (int j = 1; j < 6; j++)
                     dvs[j] = j < n_fields ? (float)offset_interpolate_t((const T *)br->data[j] + off, sx, sy, dp) : 0.f;
                 double grad[3];
-                eval_gradient_t((const T *)br->data[0] + off, sx, sy, dp, grad);
+                cell_gradient64(c0, dp, grad);
                 eval_transfer32_light<PARTIAL>(*tf, pairs, dt, dvs, grad, rgba, B);
 #pragma unroll
                 for (int i = 0; i < 3; i++) dp[i] += st[i];

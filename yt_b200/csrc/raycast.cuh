@@ -328,6 +328,50 @@ __device__ __forceinline__ void eval_gradient_t(const T *d, int sx, int sy, doub
     }
 }
 
+// The same two functions over the 8 corners of ONE cell held in registers (c[4 i + 2 j + k], fp64): the lit sampler
+// interpolates field 0 seven times per sample (value + six gradient probes), 56 corner loads that are 8 per cell here.
+__device__ __forceinline__ double cell_interpolate64(const double (&c)[8], const double (&dp)[3])
+{
+    double dv = dsub(1.0, dp[2]);
+    double v0 = dadd(dmul(dv, c[0]), dmul(dp[2], c[1]));
+    double v1 = dadd(dmul(dv, c[2]), dmul(dp[2], c[3]));
+    double v2 = dadd(dmul(dv, c[4]), dmul(dp[2], c[5]));
+    double v3 = dadd(dmul(dv, c[6]), dmul(dp[2], c[7]));
+    dv = dsub(1.0, dp[1]);
+    v0 = dadd(dmul(dv, v0), dmul(dp[1], v1));
+    v1 = dadd(dmul(dv, v2), dmul(dp[1], v3));
+    dv = dsub(1.0, dp[0]);
+    return dadd(dmul(dv, v0), dmul(dp[0], v1));
+}
+
+__device__ __forceinline__ void cell_gradient64(const double (&c)[8], double (&dp)[3], double (&grad)[3])
+{
+    double normval = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double backup = dp[i];
+        double plus, minus;
+        if (dp[i] >= 0.95) { plus = dp[i]; minus = dsub(dp[i], 0.05); }
+        else if (dp[i] <= 0.05) { plus = dadd(dp[i], 0.05); minus = 0.0; }
+        else { plus = dadd(dp[i], 0.05); minus = dsub(dp[i], 0.05); }
+        const double denom = dsub(plus, minus);
+        dp[i] = plus;
+        double g = dadd(0.0, ddiv(cell_interpolate64(c, dp), denom));
+        dp[i] = minus;
+        g = dsub(g, ddiv(cell_interpolate64(c, dp), denom));
+        dp[i] = backup;
+        grad[i] = g;
+        normval = dadd(normval, dmul(g, g));
+    }
+    if (normval != 0.0) {
+        normval = __dsqrt_rn(normval);
+#pragma unroll
+        for (int i = 0; i < 3; i++) grad[i] = ddiv(grad[i], -normval);
+    } else {
+        grad[0] = grad[1] = grad[2] = 0.0;
+    }
+}
+
 // FIT_eval_transfer_with_light (field_interpolation_tables.pxd:115-143); B only when PARTIAL
 template <bool PARTIAL>
 __device__ __forceinline__ void eval_transfer64_light(const DevTF &tf, const TFShared64 &t, double dt, const double (&dvs)[6],
