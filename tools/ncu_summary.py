@@ -33,6 +33,12 @@ dram__bytes_read.sum
 dram__bytes_write.sum
 gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed
 lts__t_sector_hit_rate.pct
+lts__t_bytes.sum
+lts__t_bytes.sum.per_second
+lts__throughput.avg.pct_of_peak_sustained_elapsed
+l1tex__m_xbar2l1tex_read_bytes.sum
+l1tex__m_xbar2l1tex_read_bytes.sum.per_second
+dram__bytes_read.sum.per_second
 l1tex__t_sector_hit_rate.pct
 l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum
 l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum
