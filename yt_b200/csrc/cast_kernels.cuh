@@ -19,7 +19,7 @@ namespace ytb {
 #define YTB_MIN_BLOCKS_PROJ 3   // the projection cast is load-latency bound: occupancy pays (ncu r01c)
 #endif
 #ifndef YTB_MIN_BLOCKS_IPROJ
-#define YTB_MIN_BLOCKS_IPROJ 3   // the interpolated projection's cell body is too short to hide its corner loads (ncu r02y: 40 % of
+#define YTB_MIN_BLOCKS_IPROJ 3   // (single field, fp32 storage: the corner-reuse walk) the interpolated projection's cell body is too short to hide its corner loads (ncu r02y: 40 % of
                                  // the stall samples wait on the prefetched face): a third resident CTA at 80 registers, 17.8 -> 15.8 ms
 #endif
 #ifndef YTB_PROJ_DEPTH
@@ -827,7 +827,8 @@ template <class A, class B> struct pick_sampler<false, A, B> { using type = B; }
 // can change the pixel by at most B times the brightest colour the rest could reach.  A warp whose rays are all
 // finished skips the remaining bricks (one vote per brick), a CTA whose warps are all finished leaves the list.
 template <int KIND, bool EXACT, int TFM, bool PARTIAL, bool NF1, typename T, bool MANY = false, bool ERT = false>
-__global__ void __launch_bounds__(CTA_THREADS, (KIND == KIND_PROJ && !EXACT) ? YTB_MIN_BLOCKS_PROJ : ((KIND == KIND_IPROJ && !EXACT) ? YTB_MIN_BLOCKS_IPROJ : YTB_MIN_BLOCKS))
+__global__ void __launch_bounds__(CTA_THREADS, (KIND == KIND_PROJ && !EXACT) ? YTB_MIN_BLOCKS_PROJ
+                                            : ((KIND == KIND_IPROJ && !EXACT && NF1 && std::is_same<T, float>::value) ? YTB_MIN_BLOCKS_IPROJ : YTB_MIN_BLOCKS))
 cast_kernel(const __grid_constant__ CastParams p)
 {
     static_assert(!ERT || (KIND == KIND_VR && !EXACT && tfm_grey(TFM) && NF1), "early termination: grey-opacity colour casts only");
